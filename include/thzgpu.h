@@ -1,0 +1,130 @@
+/* thzgpu.h -- C ABI of libthzgpu, the B200 (sm_100a) implementation of the
+ * thz-image-explorer filter-chain hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry
+ * point names the reference interface (file:line under the upstream repository) whose
+ * arithmetic it replaces.  The reference-side binding a maintainer would add (a Rust
+ * `extern "C"` block + `Filter` impls registered with `#[register_filter]`) is shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns an int status: THZ_OK (0), THZ_ABORTED (1) or a negative
+ *    THZ_E* code; the message is available from thz_last_error().  Nothing throws or
+ *    unwinds across this boundary (the reference never propagates errors out of a filter:
+ *    src/filters/deconvolution.rs:781-787, 1016-1024).
+ *  - cubes are C-contiguous [P][N] f32 with P = width*height and trace index
+ *    p = x*height + y, exactly `Array3<f32>` (x, y, t) in standard layout
+ *    (src/data_container.rs:109-162; src/math_tools.rs:374 relies on `as_slice()`).
+ *    Complex spectra are interleaved (re, im) f32 = `Array3<Complex32>` [P][F], F = N/2+1.
+ *  - pointers named d_* are device pointers obtained from thz_dev_alloc(); all others are
+ *    host pointers that the library only borrows for the duration of the call.
+ *  - there is NO CPU fallback: every compute entry point fails with THZ_ECUDA when no
+ *    sm_100 device is usable.
+ *  - calls on one context must come from one thread at a time (the reference drives the
+ *    chain from a single data thread, src/data_thread.rs:162-174, 1090).
+ */
+#ifndef THZGPU_H
+#define THZGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define THZ_OK 0
+#define THZ_ABORTED 1
+#define THZ_EINVAL (-1)   /* bad argument / unsupported size */
+#define THZ_ECUDA (-2)    /* CUDA runtime error, no device */
+#define THZ_ENOMEM (-3)
+#define THZ_ESTATE (-4)   /* call order violated (e.g. no plan) */
+
+#define THZ_MAX_BANDS 32
+#define THZ_FIR_TAPS 499  /* src/filters/deconvolution.rs:167 */
+
+typedef struct thz_ctx thz_ctx;
+
+/* progress callback, mirrors writes to `progress_lock` (src/filters/deconvolution.rs:774,
+ * 896-904, 1026-1037); called on the calling host thread. */
+typedef void (*thz_progress_fn)(float fraction, void* user);
+
+/* ---------------------------------------------------------------- context / memory ---- */
+/* Replaces the per-struct realfft plans `r2c` / `c2r` (src/data_container.rs:127-129,
+ * planned at src/io.rs:614-628): one context per GPU owns streams, twiddle tables, the
+ * multiplier vectors and scratch buffers. */
+int thz_device_count(void);
+int thz_ctx_create(int device, thz_ctx** out);
+void thz_ctx_destroy(thz_ctx* ctx);
+const char* thz_last_error(const thz_ctx* ctx); /* ctx may be NULL: last create error */
+int thz_ctx_device(const thz_ctx* ctx);
+int thz_ctx_sm_count(const thz_ctx* ctx);
+void* thz_ctx_stream(const thz_ctx* ctx);       /* cudaStream_t all kernels are launched on */
+int thz_sync(thz_ctx* ctx);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+int64_t thz_launch_count(const thz_ctx* ctx);
+
+int thz_dev_alloc(thz_ctx* ctx, size_t bytes, void** d_ptr);
+int thz_dev_free(thz_ctx* ctx, void* d_ptr);
+int thz_dev_memset(thz_ctx* ctx, void* d_ptr, int value, size_t bytes);
+int thz_copy_h2d(thz_ctx* ctx, void* d_dst, const void* src, size_t bytes);
+int thz_copy_d2h(thz_ctx* ctx, void* dst, const void* d_src, size_t bytes);
+int thz_host_alloc(size_t bytes, void** ptr);   /* pinned host memory */
+int thz_host_free(void* ptr);
+
+/* Synthetic scan: x[p,t] = A_p exp(-((t-t_p)/tau)^2) cos(2 pi f_c (t-t_p))
+ * + noise * N(0,1), time[i] = t0 + dt*i, generated on the device with a counter-based RNG.
+ * `row0` offsets the pixel index so that row-slab shards generate the same global cube. */
+int thz_generate_cube(thz_ctx* ctx, float* d_cube, int width, int height, int n, int row0,
+                      int total_width, uint64_t seed, float t0, float dt, float noise);
+
+/* -------------------------------------------------------------------- trace plan ------- */
+/* The pixel-independent multipliers the chain reduces to (all optional, NULL = ones):
+ *   m_pre[n]  : tilt taper x time gate x FFT window
+ *               (src/filters/tilt_compensation.rs:188, src/filters/band_pass_td_before_fft.rs:155-174,
+ *                src/math_tools.rs:102-198, 356-371)
+ *   band[n/2+1]: frequency band-pass taper (src/filters/band_pass_fd.rs:155-212)
+ *   m_post[n] : time gate after the inverse FFT (src/filters/band_pass_td_after_fft.rs)
+ * n must be a power of two in [64, 8192]. */
+int thz_plan_trace(thz_ctx* ctx, int n, const float* m_pre, const float* band, const float* m_post);
+
+/* ------------------------------------------------------- trace pass, device pointers --- */
+/* Slots 2..7 of the default chain in one kernel: x*m_pre -> rfft -> *band ->
+ * irfft/N -> *m_post; img[p] = sum_t out^2 (src/data_thread.rs:1288-1307).
+ * d_out may alias d_in.  d_img may be NULL. */
+int thz_trace_fused_dev(thz_ctx* ctx, const float* d_in, float* d_out, float* d_img, int64_t P);
+
+/* `math_tools::fft` (src/math_tools.rs:330-398): window (m_pre), unnormalised r2c, |s|,
+ * unwrap(arg s) (src/math_tools.rs:211-240).  d_windowed (nullable, may alias d_in) receives
+ * the windowed trace the reference leaves in `data` (:356-371). Any output may be NULL. */
+int thz_trace_forward_dev(thz_ctx* ctx, const float* d_in, float* d_windowed, float* d_fft,
+                          float* d_amp, float* d_phase, int64_t P);
+
+/* `FrequencyDomainBandPass::filter` (src/filters/band_pass_fd.rs:122-220): fft and amplitudes
+ * times the plan's band vector (zero outside the band); phases untouched. In place. */
+int thz_band_apply_dev(thz_ctx* ctx, float* d_fft, float* d_amp, int64_t P);
+
+/* `math_tools::ifft` (src/math_tools.rs:546-567): unnormalised c2r, / N (imaginary parts of
+ * DC and Nyquist ignored).  use_band != 0 multiplies by the plan's band vector first;
+ * use_post != 0 multiplies the result by m_post.  d_img (nullable) = sum_t out^2. */
+int thz_trace_inverse_dev(thz_ctx* ctx, const float* d_fft, int use_band, int use_post,
+                          float* d_out, float* d_img, int64_t P);
+
+/* Pixel means that `ifft` computes first (src/math_tools.rs:421-440): mean over all P traces
+ * of fft (2F floats), amplitudes (F), phases (F).  Host outputs, any may be NULL. */
+int thz_spectral_means(thz_ctx* ctx, const float* d_fft, const float* d_amp, const float* d_phase,
+                       int64_t P, float* avg_fft, float* avg_amp, float* avg_phase);
+
+/* ------------------------------------------------------- trace pass, host pointers ----- */
+/* Same operators on host arrays (the reference's `ScannedImageFilterData` lives in host
+ * memory).  Copies are chunked and overlapped with compute on three streams. */
+int thz_trace_fused_host(thz_ctx* ctx, const float* in, float* out, float* img, int64_t P);
+int thz_trace_forward_host(thz_ctx* ctx, const float* in, float* windowed, float* fft, float* amp,
+                           float* phase, int64_t P);
+int thz_trace_inverse_host(thz_ctx* ctx, const float* fft, int use_band, int use_post, float* out,
+                           float* img, int64_t P);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THZGPU_H */

@@ -1,0 +1,215 @@
+"""GPU parity tests of the trace pass (libthzgpu through its C ABI) against the CPU oracle.
+Tolerances are the north star's: max|a-b|/max|b| <= 1e-4 on spectra and filtered traces."""
+import numpy as np
+import pytest
+
+from helpers import (F32, TOL_TRACE, check_unwrapped_phase, default_multipliers, orc, pkg, rel_err, slot0,
+                     synthetic_cube, time_axis)
+
+pytestmark = pytest.mark.gpu
+
+ALL_N = [64, 128, 256, 512, 1024, 2048, 4096, 8192]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    m = pkg()
+    c = m.Context(0)
+    yield c
+    c.close()
+
+
+def _chain_oracle(cube, t, dx_dy=True):
+    s0 = slot0(cube, t, dx=0.5 if dx_dy else None, dy=0.5 if dx_dy else None)
+    return orc.run_default_chain(s0)
+
+
+@pytest.mark.parametrize("n", ALL_N)
+def test_forward_matches_oracle_fft(ctx, n):
+    """math_tools::fft: windowed data, spectrum, amplitudes, unwrapped phases; odd trace count
+    so the last pair is half empty and the last CTA pass is ragged."""
+    w, h = 3, 37 if n <= 2048 else 11
+    cube = synthetic_cube(w, h, n, seed=n)
+    t = time_axis(n)
+    cfg = orc.ConfigContainer()
+    ref = orc.fft(slot0(cube, t), cfg)
+    win = orc.fft_window_multiplier(t, cfg.fft_window_type, cfg.fft_window)
+    ctx.plan_trace(n, m_pre=win)
+    got = ctx.trace_forward(cube)
+    assert np.array_equal(got["windowed"], ref.data), "windowed trace must be bit-exact (one f32 multiply)"
+    assert rel_err(got["fft"], ref.fft) <= TOL_TRACE
+    assert rel_err(got["amp"], ref.amplitudes) <= TOL_TRACE
+    # phases: 1e-4 of the largest phase, but never tighter than 2e-3 rad
+    tol_rad = max(TOL_TRACE * float(np.abs(ref.phases).max()), 2e-3)
+    check_unwrapped_phase(got["phase"], ref.phases, ref.fft, tol_rad)
+    # float64 ground truth bounds both implementations
+    truth = np.fft.rfft(ref.data.astype(np.float64), axis=-1)
+    assert rel_err(got["fft"], truth.astype(np.complex128)) <= 2e-6 * np.log2(n)
+
+
+@pytest.mark.parametrize("n", ALL_N)
+def test_fused_chain_matches_oracle(ctx, n):
+    """Slots 2..7 of the default chain in one kernel vs the oracle run stage by stage."""
+    w, h = 5, 13
+    cube = synthetic_cube(w, h, n, seed=100 + n)
+    t, m_pre, band, m_post = default_multipliers(n)
+    slots = _chain_oracle(cube, t)
+    ctx.plan_trace(n, m_pre, band, m_post)
+    out, img = ctx.trace_fused(cube)
+    assert rel_err(out, slots[7].data) <= TOL_TRACE
+    assert rel_err(img, slots[7].img) <= TOL_TRACE
+    # gate zeros are exact (the default gates zero the last sample)
+    assert np.all(out[..., -1] == 0.0)
+
+
+@pytest.mark.parametrize("n", [64, 256, 2048, 4096])
+def test_inverse_matches_oracle_ifft(ctx, n):
+    w, h = 4, 9
+    cube = synthetic_cube(w, h, n, seed=7 + n)
+    t, m_pre, band, m_post = default_multipliers(n)
+    slots = _chain_oracle(cube, t)
+    ctx.plan_trace(n, m_pre, band, m_post)
+    # plain ifft of the band-passed spectrum (slot 5 -> slot 6)
+    out, _ = ctx.trace_inverse(slots[5].fft)
+    assert rel_err(out, slots[6].data) <= TOL_TRACE
+    # band-pass + ifft + gate fused (slot 4 -> slot 7)
+    out, img = ctx.trace_inverse(slots[4].fft, use_band=True, use_post=True, want_img=True)
+    assert rel_err(out, slots[7].data) <= TOL_TRACE
+    assert rel_err(img, slots[7].img) <= TOL_TRACE
+
+
+def test_stagewise_device_chain_equals_fused(ctx):
+    """forward -> band_apply -> inverse on device buffers == fused kernel (<= 1e-6 of peak), and
+    the FD band-pass leaves exact zeros outside [lower, upper) and phases untouched."""
+    n, w, h = 2048, 6, 10
+    P = w * h
+    F = n // 2 + 1
+    cube = synthetic_cube(w, h, n, seed=5)
+    t, m_pre, band, m_post = default_multipliers(n)
+    ctx.plan_trace(n, m_pre, band, m_post)
+    d_in = ctx.to_device(cube)
+    d_fft = ctx.alloc(P * F * 8)
+    d_amp = ctx.alloc(P * F * 4)
+    d_ph = ctx.alloc(P * F * 4)
+    d_out = ctx.alloc(P * n * 4)
+    d_img = ctx.alloc(P * 4)
+    ctx.trace_forward_dev(d_in.ptr, None, d_fft.ptr, d_amp.ptr, d_ph.ptr, P)
+    ph_before = d_ph.download((P, F))
+    ctx.band_apply_dev(d_fft.ptr, d_amp.ptr, P)
+    amp = d_amp.download((P, F))
+    fftv = d_fft.download((P, F), np.complex64)
+    lower, upper = orc.fd_band_indices(orc.frequency_axis(t), 0.2, 5.0)
+    assert np.all(amp[:, :lower] == 0) and np.all(amp[:, upper:] == 0)
+    assert np.all(fftv[:, :lower] == 0) and np.all(fftv[:, upper:] == 0)
+    assert np.all(amp[:, lower + 3:upper - 3] > 0)
+    assert np.array_equal(ph_before, d_ph.download((P, F)))
+    ctx.trace_inverse_dev(d_fft.ptr, 0, 1, d_out.ptr, d_img.ptr, P)
+    staged = d_out.download((P, n))
+    fused, img = ctx.trace_fused(cube)
+    assert rel_err(staged, fused.reshape(P, n)) <= 2e-6
+    assert rel_err(d_img.download((P,)), img.reshape(P)) <= 1e-5
+    # in-place fused on the device buffer gives the same bits as the host-pointer path
+    ctx.trace_fused_dev(d_in.ptr, d_in.ptr, d_img.ptr, P)
+    assert np.array_equal(d_in.download((P, n)), fused.reshape(P, n))
+
+
+def test_reference_fft_roundtrip(ctx):
+    """test_fft_roundtrip (src/math_tools.rs:843-897): 1x1x128 two-tone signal, window
+    disabled, ifft(fft(x)) == x to 1e-4 absolute."""
+    n = 128
+    t = np.linspace(0, 1, n, dtype=F32)
+    x = (np.sin(2 * np.pi * 5 * t) + 0.5 * np.sin(2 * np.pi * 12 * t)).astype(F32).reshape(1, 1, n)
+    ctx.plan_trace(n)  # fft_window = [0, 0] multiplies by exactly 1
+    spec = ctx.trace_forward(x, want=("fft",))["fft"]
+    back, _ = ctx.trace_inverse(spec)
+    assert np.max(np.abs(back - x)) < 1e-4
+
+
+def test_reference_fd_bandpass_zeros(ctx):
+    """band_pass_fd.rs:474-567: 1x1x256 sine at bin 9, frequency = i/50."""
+    n = 256
+    i = np.arange(n, dtype=F32)
+    x = np.sin(2 * np.pi * 9 * i / n).astype(F32).reshape(1, 1, n)
+    freq = (np.arange(n // 2 + 1, dtype=F32) / F32(50.0)).astype(F32)
+    band = orc.fd_band_multiplier(freq, 0.1, 1.0, 0.1)
+    lower, upper = orc.fd_band_indices(freq, 0.1, 1.0)
+    ctx.plan_trace(n, None, band, None)
+    d_in = ctx.to_device(x)
+    F = n // 2 + 1
+    d_fft, d_amp = ctx.alloc(F * 8), ctx.alloc(F * 4)
+    ctx.trace_forward_dev(d_in.ptr, None, d_fft.ptr, d_amp.ptr, None, 1)
+    ctx.band_apply_dev(d_fft.ptr, d_amp.ptr, 1)
+    amp = d_amp.download((F,))
+    assert amp.shape == (F,)
+    assert np.all(amp[:lower] == 0.0) and np.all(amp[upper:] == 0.0)
+    assert np.any(amp[lower:upper] > 0.0)
+
+
+def test_reference_td_gate_zeros(ctx):
+    """band_pass_td_before_fft.rs:389-443: 1x1x256, gate 0.25..0.55, window_width 0 -> exact
+    zeros outside, signal inside (the gate is a multiplier vector applied by the kernels)."""
+    n = 256
+    t = np.linspace(0, 1, n, dtype=F32)
+    x = np.ones((1, 1, n), F32)
+    gate = orc.td_gate_multiplier(t, 0.25, 0.55, 0.0)
+    lower, upper, _, _ = orc.td_gate_indices(t, 0.25, 0.55)
+    ctx.plan_trace(n, gate, None, None)
+    got = ctx.trace_forward(x, want=("windowed",))["windowed"].reshape(n)
+    assert np.all(got[:lower] == 0.0) and np.all(got[upper:] == 0.0)
+    assert np.sum(got[lower:upper] ** 2) > 0.0
+
+
+def test_empty_and_single_trace(ctx):
+    n = 1024
+    t, m_pre, band, m_post = default_multipliers(n)
+    ctx.plan_trace(n, m_pre, band, m_post)
+    out, img = ctx.trace_fused(np.zeros((0, 0, n), F32))
+    assert out.shape == (0, 0, n) and img.shape == (0, 0)
+    cube = synthetic_cube(1, 1, n, seed=3)
+    out, img = ctx.trace_fused(cube)
+    ref = _chain_oracle(cube, t)[7]
+    assert rel_err(out, ref.data) <= TOL_TRACE and rel_err(img, ref.img) <= TOL_TRACE
+
+
+def test_linearity_and_parseval_large(ctx):
+    """Size-independent properties on a device-generated cube (no oracle at this size):
+    chain(a x) == a chain(x); Parseval for the un-gated forward transform."""
+    n, w, h = 4096, 48, 64
+    P = w * h
+    F = n // 2 + 1
+    t, m_pre, band, m_post = default_multipliers(n)
+    ctx.plan_trace(n, m_pre, band, m_post)
+    d_x = ctx.alloc(P * n * 4)
+    ctx.generate_cube(d_x, w, h, n)
+    x = d_x.download((P, n))
+    assert np.isfinite(x).all() and float(np.abs(x).max()) > 0.5
+    y1, img1 = ctx.trace_fused(x)
+    y2, img2 = ctx.trace_fused((F32(2.0) * x).astype(F32))
+    assert np.array_equal(y2, F32(2.0) * y1)            # power-of-two scaling is exact in f32
+    assert np.array_equal(img2, F32(4.0) * img1)
+    ctx.plan_trace(n)                                    # no window
+    spec = ctx.trace_forward(x, want=("fft",))["fft"]
+    e_t = np.sum(x.astype(np.float64) ** 2, axis=-1)
+    wgt = np.full(F, 2.0)
+    wgt[0] = wgt[-1] = 1.0
+    e_f = np.sum(wgt * np.abs(spec.astype(np.complex128)) ** 2, axis=-1) / n
+    assert np.max(np.abs(e_f - e_t) / e_t) < 1e-5
+
+
+def test_spectral_means(ctx):
+    n, w, h = 1024, 7, 9
+    P, F = w * h, n // 2 + 1
+    cube = synthetic_cube(w, h, n, seed=11)
+    t, m_pre, band, m_post = default_multipliers(n)
+    slots = _chain_oracle(cube, t)
+    ctx.plan_trace(n, m_pre, band, m_post)
+    d_in = ctx.to_device(cube)
+    d_fft, d_amp, d_ph = ctx.alloc(P * F * 8), ctx.alloc(P * F * 4), ctx.alloc(P * F * 4)
+    ctx.trace_forward_dev(d_in.ptr, None, d_fft.ptr, d_amp.ptr, d_ph.ptr, P)
+    ctx.band_apply_dev(d_fft.ptr, d_amp.ptr, P)
+    a_fft, a_amp, a_ph = ctx.spectral_means(d_fft.ptr, d_amp.ptr, d_ph.ptr, P)
+    assert rel_err(a_fft, slots[6].avg_fft) <= TOL_TRACE
+    assert rel_err(a_amp, slots[6].avg_signal_fft) <= TOL_TRACE
+    # mean phases inherit unwrap ambiguities of single traces: compare with the means of the GPU's own phases
+    ph = d_ph.download((P, F)).astype(np.float64).mean(axis=0)
+    assert rel_err(a_ph, ph.astype(F32)) <= 1e-5

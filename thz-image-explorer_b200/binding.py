@@ -1,0 +1,295 @@
+"""ctypes binding of libthzgpu.so (include/thzgpu.h) and a numpy-facing ``Context``.
+
+No computation happens in this file: every method forwards to one C-ABI entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+HEADER = os.path.join(_ROOT, "include", "thzgpu.h")
+
+THZ_OK, THZ_ABORTED = 0, 1
+
+
+class ThzError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libthzgpu error {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libthzgpu.so")
+
+
+def declared_symbols(header: str = HEADER):
+    """Names of all functions declared in include/thzgpu.h."""
+    txt = open(header).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(thz_[a-z0-9_]+)\s*\(", txt)) - {"thz_progress_fn"})
+
+
+DECLARED_SYMBOLS = declared_symbols() if os.path.exists(HEADER) else []
+
+_lib = None
+
+
+def load_library():
+    """dlopen libthzgpu.so; raises ThzError when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise ThzError(-2, f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(path)
+    vp, i32, i64, u64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
+    fp = C.c_void_p  # float* (host or device), passed as integer addresses
+    sig = {
+        "thz_device_count": (i32, []),
+        "thz_ctx_create": (i32, [i32, C.POINTER(vp)]),
+        "thz_ctx_destroy": (None, [vp]),
+        "thz_last_error": (C.c_char_p, [vp]),
+        "thz_ctx_device": (i32, [vp]),
+        "thz_ctx_sm_count": (i32, [vp]),
+        "thz_ctx_stream": (vp, [vp]),
+        "thz_sync": (i32, [vp]),
+        "thz_launch_count": (i64, [vp]),
+        "thz_dev_alloc": (i32, [vp, sz, C.POINTER(vp)]),
+        "thz_dev_free": (i32, [vp, vp]),
+        "thz_dev_memset": (i32, [vp, vp, i32, sz]),
+        "thz_copy_h2d": (i32, [vp, vp, vp, sz]),
+        "thz_copy_d2h": (i32, [vp, vp, vp, sz]),
+        "thz_host_alloc": (i32, [sz, C.POINTER(vp)]),
+        "thz_host_free": (i32, [vp]),
+        "thz_generate_cube": (i32, [vp, fp, i32, i32, i32, i32, i32, u64, f32, f32, f32]),
+        "thz_plan_trace": (i32, [vp, i32, fp, fp, fp]),
+        "thz_trace_fused_dev": (i32, [vp, fp, fp, fp, i64]),
+        "thz_trace_forward_dev": (i32, [vp, fp, fp, fp, fp, fp, i64]),
+        "thz_band_apply_dev": (i32, [vp, fp, fp, i64]),
+        "thz_trace_inverse_dev": (i32, [vp, fp, i32, i32, fp, fp, i64]),
+        "thz_spectral_means": (i32, [vp, fp, fp, fp, i64, fp, fp, fp]),
+        "thz_trace_fused_host": (i32, [vp, fp, fp, fp, i64]),
+        "thz_trace_forward_host": (i32, [vp, fp, fp, fp, fp, fp, i64]),
+        "thz_trace_inverse_host": (i32, [vp, fp, i32, i32, fp, fp, i64]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._signatures = sig
+    _lib = L
+    return L
+
+
+class _LazyLib:
+    def __getattr__(self, name):
+        return getattr(load_library(), name)
+
+
+lib = _LazyLib()
+
+
+def _ptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    return a.ctypes.data
+
+
+def _f32c(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+class DeviceBuffer:
+    """A device allocation owned by a Context (thz_dev_alloc / thz_dev_free)."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        ctx._check(lib.thz_dev_alloc(ctx.handle, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr is not None and self.ctx.handle is not None:
+            lib.thz_dev_free(self.ctx.handle, self.ptr)
+        self.ptr = None
+
+    def upload(self, a: np.ndarray):
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        self.ctx._check(lib.thz_copy_h2d(self.ctx.handle, self.ptr, a.ctypes.data, a.nbytes))
+        return self
+
+    def download(self, shape, dtype=np.float32, offset_bytes=0):
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes + offset_bytes <= self.nbytes
+        self.ctx._check(lib.thz_copy_d2h(self.ctx.handle, out.ctypes.data, self.ptr + offset_bytes, out.nbytes))
+        return out
+
+    def zero(self):
+        self.ctx._check(lib.thz_dev_memset(self.ctx.handle, self.ptr, 0, self.nbytes))
+        return self
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU's libthzgpu context (thz_ctx_create)."""
+
+    def __init__(self, device: int = 0):
+        self.handle = None
+        h = C.c_void_p()
+        rc = lib.thz_ctx_create(int(device), C.byref(h))
+        if rc != THZ_OK:
+            raise ThzError(rc, (lib.thz_last_error(None) or b"").decode())
+        self.handle = h.value
+        self.n = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc not in (THZ_OK, THZ_ABORTED):
+            raise ThzError(rc, (lib.thz_last_error(self.handle) or b"").decode())
+        return rc
+
+    def close(self):
+        if self.handle is not None:
+            lib.thz_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def sm_count(self):
+        return lib.thz_ctx_sm_count(self.handle)
+
+    @property
+    def stream(self):
+        return lib.thz_ctx_stream(self.handle)
+
+    @property
+    def launches(self):
+        return int(lib.thz_launch_count(self.handle))
+
+    def sync(self):
+        self._check(lib.thz_sync(self.handle))
+
+    def alloc(self, nbytes) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, a: np.ndarray) -> DeviceBuffer:
+        a = np.ascontiguousarray(a)
+        return DeviceBuffer(self, max(a.nbytes, 16)).upload(a)
+
+    def generate_cube(self, buf: DeviceBuffer, width, height, n, row0=0, total_width=None, seed=20261018,
+                      t0=1000.0, dt=0.05, noise=0.01):
+        self._check(lib.thz_generate_cube(self.handle, buf.ptr, width, height, n, row0,
+                                          total_width if total_width is not None else width, seed, t0, dt, noise))
+
+    # ------------------------------------------------------------------ trace plan
+    def plan_trace(self, n, m_pre=None, band=None, m_post=None):
+        """thz_plan_trace: multiplier vectors are plain float32 arrays computed by the caller
+        (host.py computes them through the library's own host routines)."""
+        keep = []
+
+        def vec(a, ln):
+            if a is None:
+                return None
+            a = _f32c(a, (ln,))
+            keep.append(a)
+            return a.ctypes.data
+
+        self._check(lib.thz_plan_trace(self.handle, int(n), vec(m_pre, n), vec(band, n // 2 + 1), vec(m_post, n)))
+        self.n = int(n)
+
+    # ------------------------------------------------------------------ device-pointer ops
+    def trace_fused_dev(self, d_in, d_out, d_img, P):
+        self._check(lib.thz_trace_fused_dev(self.handle, d_in, d_out, d_img, int(P)))
+
+    def trace_forward_dev(self, d_in, d_win, d_fft, d_amp, d_phase, P):
+        self._check(lib.thz_trace_forward_dev(self.handle, d_in, d_win, d_fft, d_amp, d_phase, int(P)))
+
+    def trace_inverse_dev(self, d_fft, use_band, use_post, d_out, d_img, P):
+        self._check(lib.thz_trace_inverse_dev(self.handle, d_fft, int(use_band), int(use_post), d_out, d_img, int(P)))
+
+    def band_apply_dev(self, d_fft, d_amp, P):
+        self._check(lib.thz_band_apply_dev(self.handle, d_fft, d_amp, int(P)))
+
+    def spectral_means(self, d_fft, d_amp, d_phase, P):
+        F = self.n // 2 + 1
+        a_fft = np.empty(2 * F, np.float32)
+        a_amp = np.empty(F, np.float32)
+        a_ph = np.empty(F, np.float32)
+        self._check(lib.thz_spectral_means(self.handle, d_fft, d_amp, d_phase, int(P), a_fft.ctypes.data,
+                                           a_amp.ctypes.data if d_amp else None,
+                                           a_ph.ctypes.data if d_phase else None))
+        return a_fft.view(np.complex64), a_amp, a_ph
+
+    # ------------------------------------------------------------------ host-pointer ops
+    def trace_fused(self, data: np.ndarray, want_img=True):
+        """Slots 2..7 of the default chain on a host cube [..., N] -> (filtered, img)."""
+        data = _f32c(data)
+        n = data.shape[-1]
+        assert n == self.n, "plan_trace(n) first"
+        P = data.size // n if n else 0
+        out = np.empty_like(data)
+        img = np.empty(data.shape[:-1], np.float32) if want_img else None
+        self._check(lib.thz_trace_fused_host(self.handle, data.ctypes.data, out.ctypes.data, _ptr(img), P))
+        return out, img
+
+    def trace_forward(self, data: np.ndarray, want=("windowed", "fft", "amp", "phase")):
+        """`math_tools::fft` on a host cube -> dict(windowed, fft, amp, phase)."""
+        data = _f32c(data)
+        n = data.shape[-1]
+        assert n == self.n, "plan_trace(n) first"
+        P = data.size // n if n else 0
+        F = n // 2 + 1
+        lead = data.shape[:-1]
+        res = {}
+        if "windowed" in want:
+            res["windowed"] = np.empty_like(data)
+        if "fft" in want:
+            res["fft"] = np.empty(lead + (F,), np.complex64)
+        if "amp" in want:
+            res["amp"] = np.empty(lead + (F,), np.float32)
+        if "phase" in want:
+            res["phase"] = np.empty(lead + (F,), np.float32)
+        self._check(lib.thz_trace_forward_host(self.handle, data.ctypes.data, _ptr(res.get("windowed")),
+                                               _ptr(res.get("fft")), _ptr(res.get("amp")), _ptr(res.get("phase")), P))
+        return res
+
+    def trace_inverse(self, fft: np.ndarray, use_band=False, use_post=False, want_img=False):
+        """`math_tools::ifft` on a host spectrum cube [..., F] complex64 -> (data, img)."""
+        fft = np.ascontiguousarray(fft, dtype=np.complex64)
+        n = self.n
+        F = n // 2 + 1
+        assert fft.shape[-1] == F
+        P = fft.size // F
+        out = np.empty(fft.shape[:-1] + (n,), np.float32)
+        img = np.empty(fft.shape[:-1], np.float32) if want_img else None
+        self._check(lib.thz_trace_inverse_host(self.handle, fft.ctypes.data, int(use_band), int(use_post),
+                                               out.ctypes.data, _ptr(img), P))
+        return out, img

@@ -1,0 +1,415 @@
+// thz_api.cu -- the C ABI (include/thzgpu.h): context, plans, memory, host-pointer pipelines.
+#include "thz_internal.h"
+
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+
+static std::string g_create_err;
+static std::mutex g_mu;
+
+namespace thz {
+
+int set_err(thz_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  else {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_create_err = msg;
+  }
+  return code;
+}
+
+int cuda_fail(thz_ctx* c, cudaError_t e, const char* what) {
+  std::string m = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return set_err(c, e == cudaErrorMemoryAllocation ? THZ_ENOMEM : THZ_ECUDA, m);
+}
+
+int get_tables(thz_ctx* c, int n, const FftTables** out) {
+  auto it = c->tables.find(n);
+  if (it != c->tables.end()) {
+    *out = &it->second;
+    return THZ_OK;
+  }
+  std::vector<float2> tw;
+  if (build_twiddles(n, tw) != THZ_OK) return set_err(c, THZ_EINVAL, "unsupported FFT size");
+  FftTables tb;
+  tb.n = n;
+  THZ_CUDA(c, cudaMalloc((void**)&tb.d_tw, tw.size() * sizeof(float2)));
+  THZ_CUDA(c, cudaMemcpyAsync(tb.d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  auto ins = c->tables.emplace(n, tb);
+  *out = &ins.first->second;
+  return THZ_OK;
+}
+
+int ensure_scratch(thz_ctx* c, size_t bytes) {
+  if (c->scratch_bytes >= bytes) return THZ_OK;
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  c->d_scratch = nullptr;
+  c->scratch_bytes = 0;
+  THZ_CUDA(c, cudaMalloc((void**)&c->d_scratch, bytes));
+  c->scratch_bytes = bytes;
+  return THZ_OK;
+}
+
+static int upload_vec(thz_ctx* c, float** d, const float* h, size_t n) {
+  if (*d) {
+    cudaFree(*d);
+    *d = nullptr;
+  }
+  THZ_CUDA(c, cudaMalloc((void**)d, n * sizeof(float)));
+  THZ_CUDA(c, cudaMemcpyAsync(*d, h, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  return THZ_OK;
+}
+
+static int ensure_stage(thz_ctx* c, size_t bytes) {
+  if (c->stage_bytes >= bytes) return THZ_OK;
+  for (int i = 0; i < kHostStreams; ++i) {
+    if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+    c->d_stage[i] = nullptr;
+  }
+  c->stage_bytes = 0;
+  for (int i = 0; i < kHostStreams; ++i) THZ_CUDA(c, cudaMalloc(&c->d_stage[i], bytes));
+  c->stage_bytes = bytes;
+  return THZ_OK;
+}
+
+}  // namespace thz
+
+using namespace thz;
+
+#define CHECK_CTX(c)                \
+  do {                              \
+    if (!(c)) return THZ_EINVAL;    \
+    cudaError_t e_ = cudaSetDevice((c)->device); \
+    if (e_ != cudaSuccess) return cuda_fail((c), e_, "cudaSetDevice"); \
+  } while (0)
+
+extern "C" {
+
+int thz_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int thz_ctx_create(int device, thz_ctx** out) {
+  if (!out) return THZ_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return set_err(nullptr, THZ_ECUDA, "no CUDA device available (libthzgpu has no CPU fallback)");
+  }
+  if (device < 0 || device >= n) return set_err(nullptr, THZ_EINVAL, "device index out of range");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "device %d is sm_%d%d; libthzgpu is built for sm_100a only", device, prop.major,
+             prop.minor);
+    return set_err(nullptr, THZ_ECUDA, buf);
+  }
+  thz_ctx* c = new thz_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    return cuda_fail(nullptr, e, "cudaStreamCreate");
+  }
+  for (int i = 0; i < kHostStreams; ++i) {
+    e = cudaStreamCreateWithFlags(&c->hstream[i], cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete c;
+      return cuda_fail(nullptr, e, "cudaStreamCreate");
+    }
+  }
+  *out = c;
+  return THZ_OK;
+}
+
+void thz_ctx_destroy(thz_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c->tables)
+    if (kv.second.d_tw) cudaFree(kv.second.d_tw);
+  if (c->plan.d_m_pre) cudaFree(c->plan.d_m_pre);
+  if (c->plan.d_m_post) cudaFree(c->plan.d_m_post);
+  if (c->plan.d_band) cudaFree(c->plan.d_band);
+  if (c->plan.d_hq) cudaFree(c->plan.d_hq);
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  for (int i = 0; i < kHostStreams; ++i) {
+    if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+    if (c->hstream[i]) cudaStreamDestroy(c->hstream[i]);
+  }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* thz_last_error(const thz_ctx* c) {
+  if (c) return c->err.c_str();
+  return g_create_err.c_str();
+}
+
+int thz_ctx_device(const thz_ctx* c) { return c ? c->device : -1; }
+int thz_ctx_sm_count(const thz_ctx* c) { return c ? c->sm_count : 0; }
+void* thz_ctx_stream(const thz_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int64_t thz_launch_count(const thz_ctx* c) { return c ? c->launches : 0; }
+
+int thz_sync(thz_ctx* c) {
+  CHECK_CTX(c);
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < kHostStreams; ++i) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[i]));
+  return THZ_OK;
+}
+
+int thz_dev_alloc(thz_ctx* c, size_t bytes, void** d_ptr) {
+  CHECK_CTX(c);
+  if (!d_ptr) return set_err(c, THZ_EINVAL, "null out pointer");
+  *d_ptr = nullptr;
+  if (bytes == 0) bytes = 16;
+  THZ_CUDA(c, cudaMalloc(d_ptr, bytes));
+  return THZ_OK;
+}
+
+int thz_dev_free(thz_ctx* c, void* d_ptr) {
+  CHECK_CTX(c);
+  if (d_ptr) THZ_CUDA(c, cudaFree(d_ptr));
+  return THZ_OK;
+}
+
+int thz_dev_memset(thz_ctx* c, void* d_ptr, int value, size_t bytes) {
+  CHECK_CTX(c);
+  THZ_CUDA(c, cudaMemsetAsync(d_ptr, value, bytes, c->stream));
+  return THZ_OK;
+}
+
+int thz_copy_h2d(thz_ctx* c, void* d_dst, const void* src, size_t bytes) {
+  CHECK_CTX(c);
+  if (bytes == 0) return THZ_OK;
+  THZ_CUDA(c, cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  return THZ_OK;
+}
+
+int thz_copy_d2h(thz_ctx* c, void* dst, const void* d_src, size_t bytes) {
+  CHECK_CTX(c);
+  if (bytes == 0) return THZ_OK;
+  THZ_CUDA(c, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  return THZ_OK;
+}
+
+int thz_host_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return THZ_EINVAL;
+  *ptr = nullptr;
+  cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostAlloc");
+  return THZ_OK;
+}
+
+int thz_host_free(void* ptr) {
+  if (ptr) {
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFreeHost");
+  }
+  return THZ_OK;
+}
+
+int thz_generate_cube(thz_ctx* c, float* d_cube, int width, int height, int n, int row0, int total_width,
+                      uint64_t seed, float t0, float dt, float noise) {
+  CHECK_CTX(c);
+  if (!d_cube || width < 0 || height < 0 || n <= 0) return set_err(c, THZ_EINVAL, "bad cube shape");
+  return launch_generate(c, c->stream, d_cube, width, height, n, row0, total_width, seed, t0, dt, noise);
+}
+
+int thz_plan_trace(thz_ctx* c, int n, const float* m_pre, const float* band, const float* m_post) {
+  CHECK_CTX(c);
+  if (!supported_n(n)) return set_err(c, THZ_EINVAL, "n must be a power of two in [64, 8192]");
+  const FftTables* tb = nullptr;
+  int rc = get_tables(c, n, &tb);
+  if (rc != THZ_OK) return rc;
+  // make sure no kernel still reads the old vectors
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < kHostStreams; ++i) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[i]));
+  TracePlan& p = c->plan;
+  p.n = n;
+  p.has_pre = m_pre != nullptr;
+  p.has_post = m_post != nullptr;
+  p.has_band = band != nullptr;
+  if (m_pre && (rc = upload_vec(c, &p.d_m_pre, m_pre, n)) != THZ_OK) return rc;
+  if (m_post && (rc = upload_vec(c, &p.d_m_post, m_post, n)) != THZ_OK) return rc;
+  if (band && (rc = upload_vec(c, &p.d_band, band, n / 2 + 1)) != THZ_OK) return rc;
+  std::vector<float> hq;
+  if (build_hq(n, band, hq) != THZ_OK) return set_err(c, THZ_EINVAL, "unsupported n");
+  if ((rc = upload_vec(c, &p.d_hq, hq.data(), n)) != THZ_OK) return rc;
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));   // hq is a local
+  return THZ_OK;
+}
+
+int thz_trace_fused_dev(thz_ctx* c, const float* d_in, float* d_out, float* d_img, int64_t P) {
+  CHECK_CTX(c);
+  return launch_trace_fused(c, c->stream, d_in, d_out, d_img, P);
+}
+
+int thz_trace_forward_dev(thz_ctx* c, const float* d_in, float* d_windowed, float* d_fft, float* d_amp,
+                          float* d_phase, int64_t P) {
+  CHECK_CTX(c);
+  return launch_trace_forward(c, c->stream, d_in, d_windowed, (float2*)d_fft, d_amp, d_phase, P);
+}
+
+int thz_band_apply_dev(thz_ctx* c, float* d_fft, float* d_amp, int64_t P) {
+  CHECK_CTX(c);
+  return launch_band_apply(c, c->stream, (float2*)d_fft, d_amp, P);
+}
+
+int thz_trace_inverse_dev(thz_ctx* c, const float* d_fft, int use_band, int use_post, float* d_out, float* d_img,
+                          int64_t P) {
+  CHECK_CTX(c);
+  return launch_trace_inverse(c, c->stream, (const float2*)d_fft, use_band != 0, use_post != 0, d_out, d_img, P);
+}
+
+int thz_spectral_means(thz_ctx* c, const float* d_fft, const float* d_amp, const float* d_phase, int64_t P,
+                       float* avg_fft, float* avg_amp, float* avg_phase) {
+  CHECK_CTX(c);
+  if (c->plan.n == 0) return set_err(c, THZ_ESTATE, "thz_plan_trace has not been called");
+  if (P <= 0) return set_err(c, THZ_EINVAL, "P must be positive");
+  const int F = c->plan.n / 2 + 1;
+  int nb = c->sm_count * 4;
+  if ((int64_t)nb > P) nb = (int)P;
+  int rc = ensure_scratch(c, (size_t)nb * 2 * F * sizeof(float));
+  if (rc != THZ_OK) return rc;
+  std::vector<float> part((size_t)nb * 2 * F);
+  struct Job { const float* d; int cols; float* out; };
+  Job jobs[3] = {{d_fft, 2 * F, avg_fft}, {d_amp, F, avg_amp}, {d_phase, F, avg_phase}};
+  for (const Job& j : jobs) {
+    if (!j.d || !j.out) continue;
+    rc = launch_column_sums(c, c->stream, j.d, P, j.cols, c->d_scratch, nb);
+    if (rc != THZ_OK) return rc;
+    THZ_CUDA(c, cudaMemcpyAsync(part.data(), c->d_scratch, (size_t)nb * j.cols * sizeof(float),
+                                cudaMemcpyDeviceToHost, c->stream));
+    THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int col = 0; col < j.cols; ++col) {
+      double acc = 0.0;
+      for (int b = 0; b < nb; ++b) acc += (double)part[(size_t)b * j.cols + col];
+      j.out[col] = (float)(acc / (double)P);
+    }
+  }
+  return THZ_OK;
+}
+
+// ---------------------------------------------------------------- host-pointer pipelines
+// The cube is processed in chunks of whole trace pairs; chunk i uses stream i % 3 and that
+// stream's staging buffer, so that H2D of chunk i+1, the kernel of chunk i and D2H of chunk
+// i-1 overlap.
+static int64_t chunk_traces(int n, int floats_per_trace_total) {
+  // ~96 MiB of staging per stream
+  int64_t t = ((int64_t)96 << 20) / ((int64_t)floats_per_trace_total * 4);
+  t &= ~(int64_t)1023;
+  if (t < 1024) t = 1024;
+  (void)n;
+  return t;
+}
+
+int thz_trace_fused_host(thz_ctx* c, const float* in, float* out, float* img, int64_t P) {
+  CHECK_CTX(c);
+  if (c->plan.n == 0) return set_err(c, THZ_ESTATE, "thz_plan_trace has not been called");
+  if (P == 0) return THZ_OK;
+  if (!in || !out) return set_err(c, THZ_EINVAL, "null pointer");
+  const int n = c->plan.n;
+  const int64_t ct = chunk_traces(n, n + 1);
+  int rc = ensure_stage(c, (size_t)ct * (n + 1) * sizeof(float));
+  if (rc != THZ_OK) return rc;
+  int i = 0;
+  for (int64_t p = 0; p < P; p += ct, ++i) {
+    const int64_t np = std::min(ct, P - p);
+    const int k = i % kHostStreams;
+    cudaStream_t s = c->hstream[k];
+    float* d_buf = (float*)c->d_stage[k];
+    float* d_img = d_buf + (size_t)ct * n;
+    THZ_CUDA(c, cudaMemcpyAsync(d_buf, in + p * n, (size_t)np * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = launch_trace_fused(c, s, d_buf, d_buf, img ? d_img : nullptr, np);
+    if (rc != THZ_OK) return rc;
+    THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d_buf, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (img) THZ_CUDA(c, cudaMemcpyAsync(img + p, d_img, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
+  return THZ_OK;
+}
+
+int thz_trace_forward_host(thz_ctx* c, const float* in, float* windowed, float* fft, float* amp, float* phase,
+                           int64_t P) {
+  CHECK_CTX(c);
+  if (c->plan.n == 0) return set_err(c, THZ_ESTATE, "thz_plan_trace has not been called");
+  if (P == 0) return THZ_OK;
+  if (!in) return set_err(c, THZ_EINVAL, "null pointer");
+  const int n = c->plan.n, F = n / 2 + 1;
+  const int per = n + 4 * F;   // data + fft(2F) + amp + phase
+  const int64_t ct = chunk_traces(n, per);
+  int rc = ensure_stage(c, (size_t)ct * per * sizeof(float));
+  if (rc != THZ_OK) return rc;
+  int i = 0;
+  for (int64_t p = 0; p < P; p += ct, ++i) {
+    const int64_t np = std::min(ct, P - p);
+    const int k = i % kHostStreams;
+    cudaStream_t s = c->hstream[k];
+    float* d_data = (float*)c->d_stage[k];
+    float* d_fft = d_data + (size_t)ct * n;
+    float* d_amp = d_fft + (size_t)ct * 2 * F;
+    float* d_ph = d_amp + (size_t)ct * F;
+    THZ_CUDA(c, cudaMemcpyAsync(d_data, in + p * n, (size_t)np * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = launch_trace_forward(c, s, d_data, windowed ? d_data : nullptr, fft ? (float2*)d_fft : nullptr,
+                              amp ? d_amp : nullptr, phase ? d_ph : nullptr, np);
+    if (rc != THZ_OK) return rc;
+    if (windowed)
+      THZ_CUDA(c, cudaMemcpyAsync(windowed + p * n, d_data, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (fft)
+      THZ_CUDA(c, cudaMemcpyAsync(fft + p * 2 * F, d_fft, (size_t)np * 2 * F * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (amp) THZ_CUDA(c, cudaMemcpyAsync(amp + p * F, d_amp, (size_t)np * F * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (phase)
+      THZ_CUDA(c, cudaMemcpyAsync(phase + p * F, d_ph, (size_t)np * F * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
+  return THZ_OK;
+}
+
+int thz_trace_inverse_host(thz_ctx* c, const float* fft, int use_band, int use_post, float* out, float* img,
+                           int64_t P) {
+  CHECK_CTX(c);
+  if (c->plan.n == 0) return set_err(c, THZ_ESTATE, "thz_plan_trace has not been called");
+  if (P == 0) return THZ_OK;
+  if (!fft || !out) return set_err(c, THZ_EINVAL, "null pointer");
+  const int n = c->plan.n, F = n / 2 + 1;
+  const int per = n + 2 * F + 1;
+  const int64_t ct = chunk_traces(n, per);
+  int rc = ensure_stage(c, (size_t)ct * per * sizeof(float));
+  if (rc != THZ_OK) return rc;
+  int i = 0;
+  for (int64_t p = 0; p < P; p += ct, ++i) {
+    const int64_t np = std::min(ct, P - p);
+    const int k = i % kHostStreams;
+    cudaStream_t s = c->hstream[k];
+    float* d_fft = (float*)c->d_stage[k];
+    float* d_out = d_fft + (size_t)ct * 2 * F;
+    float* d_img = d_out + (size_t)ct * n;
+    THZ_CUDA(c, cudaMemcpyAsync(d_fft, fft + p * 2 * F, (size_t)np * 2 * F * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = launch_trace_inverse(c, s, (const float2*)d_fft, use_band != 0, use_post != 0, d_out, img ? d_img : nullptr, np);
+    if (rc != THZ_OK) return rc;
+    THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d_out, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (img) THZ_CUDA(c, cudaMemcpyAsync(img + p, d_img, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
+  return THZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+// thz_fft.cuh -- in-shared-memory mixed-radix complex FFT building blocks for sm_100a.
+//
+// One "group" of T = N/16 threads transforms one complex sequence of N points; every
+// thread keeps E = 16 complex points in registers.  A forward transform is a chain of
+// decimation-in-frequency (DIF) stages, each a radix-R (R in {2,4,8,16}) register
+// butterfly followed by a twiddle multiply; stages are separated by one exchange through
+// a padded float2 array in shared memory.  The result is left in *digit-reversed*
+// position order.  The inverse transform is the exact conjugate transpose (DIT): it
+// consumes digit-reversed order and produces natural order, so a forward -> pointwise
+// multiply -> inverse pipeline (the filter chain) needs no permutation and no exchange
+// between the last forward stage and the first inverse stage.
+//
+// This replaces the reference's per-trace calls into realfft/rustfft
+// (src/math_tools.rs:374-375 forward, :559-566 inverse; src/filters/deconvolution.rs:266-317).
+// Two real traces are packed as re/im of one complex sequence.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace thz {
+
+constexpr int kE = 16;          // complex points per thread
+constexpr int kPadShift = 4;    // one float2 of padding per 16 elements
+
+__host__ __device__ constexpr int pad_idx(int i) { return i + (i >> kPadShift); }
+__host__ __device__ constexpr int padded_len(int n) { return n + (n >> kPadShift); }
+
+// Radix plans (stage 0 first).  Chosen with tools/bank_conflicts.py so that every exchange
+// and the natural-order scatter are bank-conflict free (8192: at most 2-way on the scatter).
+template <int N> struct Plan;
+template <> struct Plan<64>   { static constexpr int ns = 2; static constexpr int r[4] = {4, 16, 1, 1}; };
+template <> struct Plan<128>  { static constexpr int ns = 2; static constexpr int r[4] = {8, 16, 1, 1}; };
+template <> struct Plan<256>  { static constexpr int ns = 2; static constexpr int r[4] = {16, 16, 1, 1}; };
+template <> struct Plan<512>  { static constexpr int ns = 3; static constexpr int r[4] = {8, 16, 4, 1}; };
+template <> struct Plan<1024> { static constexpr int ns = 3; static constexpr int r[4] = {16, 16, 4, 1}; };
+template <> struct Plan<2048> { static constexpr int ns = 3; static constexpr int r[4] = {16, 16, 8, 1}; };
+template <> struct Plan<4096> { static constexpr int ns = 3; static constexpr int r[4] = {16, 16, 16, 1}; };
+template <> struct Plan<8192> { static constexpr int ns = 4; static constexpr int r[4] = {8, 4, 16, 16}; };
+
+// sub-transform length at stage s: L_s = N / (r_0 ... r_{s-1})
+template <int N, int S> struct StageLen {
+  static constexpr int value = StageLen<N, S - 1>::value / Plan<N>::r[S - 1];
+};
+template <int N> struct StageLen<N, 0> { static constexpr int value = N; };
+
+// Offset (in float2) of stage s's twiddle table inside the per-N table.  Stage s (all but
+// the last) stores (R-1) * S entries laid out [q-1][j], j in [0, S), S = L/R:
+//   tw[q-1][j] = exp(-2 pi i * j * q / L)
+template <int N, int S> struct TwOffset {
+  static constexpr int Lp = StageLen<N, S - 1>::value;
+  static constexpr int Rp = Plan<N>::r[S - 1];
+  static constexpr int value = TwOffset<N, S - 1>::value + (Rp - 1) * (Lp / Rp);
+};
+template <int N> struct TwOffset<N, 0> { static constexpr int value = 0; };
+template <int N> struct TwTotal { static constexpr int value = TwOffset<N, Plan<N>::ns - 1>::value; };
+
+// ------------------------------------------------------------------------------------
+// complex helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+  return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 w) {  // a * conj(w)
+  return make_float2(fmaf(a.x, w.x, a.y * w.y), fmaf(a.y, w.x, -a.x * w.y));
+}
+// multiply by -i (forward) or +i (inverse)
+template <bool INV> __device__ __forceinline__ float2 rot90(float2 a) {
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+// multiply by exp(-+ i pi/4)
+template <bool INV> __device__ __forceinline__ float2 rot45(float2 a) {
+  constexpr float h = 0.70710678118654752440f;
+  return INV ? make_float2((a.x - a.y) * h, (a.x + a.y) * h) : make_float2((a.x + a.y) * h, (a.y - a.x) * h);
+}
+// multiply by exp(-+ i 3pi/4)
+template <bool INV> __device__ __forceinline__ float2 rot135(float2 a) {
+  constexpr float h = 0.70710678118654752440f;
+  return INV ? make_float2((-a.x - a.y) * h, (a.x - a.y) * h) : make_float2((a.y - a.x) * h, (-a.x - a.y) * h);
+}
+// multiply by exp(-+ 2 pi i k / 16) with compile-time (c, s) = (cos, sin)
+template <bool INV> __device__ __forceinline__ float2 rotcs(float2 a, float c, float s) {
+  // forward: (x + iy)(c - is) = (xc + ys) + i(yc - xs)
+  return INV ? make_float2(fmaf(a.x, c, -a.y * s), fmaf(a.y, c, a.x * s))
+             : make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s));
+}
+
+// ------------------------------------------------------------------------------------
+// register butterflies: in-place DFT of R points, natural order in and out
+// ------------------------------------------------------------------------------------
+template <bool INV> __device__ __forceinline__ void dft2(float2& a0, float2& a1) {
+  float2 t = a0;
+  a0 = cadd(t, a1);
+  a1 = csub(t, a1);
+}
+
+template <bool INV> __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  float2 t0 = cadd(a0, a2), t1 = csub(a0, a2);
+  float2 t2 = cadd(a1, a3), t3 = rot90<INV>(csub(a1, a3));
+  a0 = cadd(t0, t2);
+  a2 = csub(t0, t2);
+  a1 = cadd(t1, t3);
+  a3 = csub(t1, t3);
+}
+
+template <bool INV> __device__ __forceinline__ void dft8(float2 (&a)[8]) {
+  dft4<INV>(a[0], a[2], a[4], a[6]);   // even samples -> E[0..3] in a0,a2,a4,a6
+  dft4<INV>(a[1], a[3], a[5], a[7]);   // odd samples  -> O[0..3] in a1,a3,a5,a7
+  float2 o1 = rot45<INV>(a[3]), o2 = rot90<INV>(a[5]), o3 = rot135<INV>(a[7]);
+  float2 e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], o0 = a[1];
+  a[0] = cadd(e0, o0); a[4] = csub(e0, o0);
+  a[1] = cadd(e1, o1); a[5] = csub(e1, o1);
+  a[2] = cadd(e2, o2); a[6] = csub(e2, o2);
+  a[3] = cadd(e3, o3); a[7] = csub(e3, o3);
+}
+
+template <bool INV> __device__ __forceinline__ void dft16(float2 (&a)[16]) {
+  constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+  // n = 4*a_ + b : inner DFT4 over a_ for each b -> Y_b[c] stored at a[4c + b]
+#pragma unroll
+  for (int b = 0; b < 4; ++b) dft4<INV>(a[b], a[4 + b], a[8 + b], a[12 + b]);
+  // twiddle w16^(b*c)
+  a[5] = rotcs<INV>(a[5], c1, s1);      // b=1,c=1 : k=1
+  a[9] = rot45<INV>(a[9]);              // b=1,c=2 : k=2
+  a[13] = rotcs<INV>(a[13], s1, c1);    // b=1,c=3 : k=3
+  a[6] = rot45<INV>(a[6]);              // b=2,c=1 : k=2
+  a[10] = rot90<INV>(a[10]);            // b=2,c=2 : k=4
+  a[14] = rot135<INV>(a[14]);           // b=2,c=3 : k=6
+  a[7] = rotcs<INV>(a[7], s1, c1);      // b=3,c=1 : k=3
+  a[11] = rot135<INV>(a[11]);           // b=3,c=2 : k=6
+  a[15] = rotcs<INV>(a[15], -c1, -s1);  // b=3,c=3 : k=9 -> cos = -c1, sin(2pi9/16) = -s1
+  // outer DFT4 over b for each c -> X[c + 4d] lands in a[4c + d]
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dft4<INV>(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+  // a[4c + d] holds X[c + 4d]; transpose to natural order
+  float2 t;
+  t = a[1]; a[1] = a[4]; a[4] = t;
+  t = a[2]; a[2] = a[8]; a[8] = t;
+  t = a[3]; a[3] = a[12]; a[12] = t;
+  t = a[6]; a[6] = a[9]; a[9] = t;
+  t = a[7]; a[7] = a[13]; a[13] = t;
+  t = a[11]; a[11] = a[14]; a[14] = t;
+}
+
+template <int R, bool INV> __device__ __forceinline__ void dftR(float2 (&a)[R]) {
+  if constexpr (R == 2) dft2<INV>(a[0], a[1]);
+  else if constexpr (R == 4) dft4<INV>(a[0], a[1], a[2], a[3]);
+  else if constexpr (R == 8) dft8<INV>(a);
+  else dft16<INV>(a);
+}
+
+// ------------------------------------------------------------------------------------
+// One stage on the 16 register-resident points of thread t (t in [0, T)).
+// Register v[u + U*m] <-> element index b*L + j + m*S, with beta = t + u*T, b = beta / S,
+// j = beta % S, U = 16/R, S = L/R.
+//   forward (DIF): butterfly then twiddle;  inverse (DIT): conj twiddle then butterfly.
+// ------------------------------------------------------------------------------------
+template <int N, int S_IDX, bool INV>
+__device__ __forceinline__ void stage_compute(float2 (&v)[kE], int t, const float2* __restrict__ tw_base) {
+  constexpr int T = N / kE;
+  constexpr int L = StageLen<N, S_IDX>::value;
+  constexpr int R = Plan<N>::r[S_IDX];
+  constexpr int S = L / R;
+  constexpr int U = kE / R;
+  constexpr bool kTw = (S_IDX < Plan<N>::ns - 1);
+  const float2* tw = tw_base + TwOffset<N, S_IDX>::value;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = (t + u * T) & (S - 1);
+    float2 a[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) a[m] = v[u + U * m];
+    if constexpr (INV && kTw) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) a[q] = cmul_conj(a[q], __ldg(&tw[(q - 1) * S + j]));
+    }
+    dftR<R, INV>(a);
+    if constexpr (!INV && kTw) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) a[q] = cmul(a[q], __ldg(&tw[(q - 1) * S + j]));
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[u + U * m] = a[m];
+  }
+}
+
+// element index owned by register i = u + U*m of thread t at stage S_IDX
+template <int N, int S_IDX>
+__device__ __forceinline__ int stage_elem(int t, int i) {
+  constexpr int T = N / kE;
+  constexpr int L = StageLen<N, S_IDX>::value;
+  constexpr int R = Plan<N>::r[S_IDX];
+  constexpr int S = L / R;
+  constexpr int U = kE / R;
+  const int u = i % U, m = i / U;
+  const int beta = t + u * T;
+  return (beta / S) * L + (beta & (S - 1)) + m * S;
+}
+
+template <int N, int S_IDX>
+__device__ __forceinline__ void stage_store(const float2 (&v)[kE], int t, float2* __restrict__ sm) {
+#pragma unroll
+  for (int i = 0; i < kE; ++i) sm[pad_idx(stage_elem<N, S_IDX>(t, i))] = v[i];
+}
+template <int N, int S_IDX>
+__device__ __forceinline__ void stage_load(float2 (&v)[kE], int t, const float2* __restrict__ sm) {
+#pragma unroll
+  for (int i = 0; i < kE; ++i) v[i] = sm[pad_idx(stage_elem<N, S_IDX>(t, i))];
+}
+
+// natural-order bin k of the value at position p after the LAST forward stage:
+// position p = sum_s q_s * S_s  <->  k = q_0 + r_0 q_1 + r_0 r_1 q_2 + ...
+template <int N, int S_IDX = 0>
+__device__ __forceinline__ int pos_to_bin(int p) {
+  if constexpr (S_IDX == Plan<N>::ns) {
+    return 0;
+  } else {
+    constexpr int L = StageLen<N, S_IDX>::value;
+    constexpr int S = L / Plan<N>::r[S_IDX];
+    constexpr int W = N / L;   // r_0 * ... * r_{s-1}
+    const int q = p / S;
+    return q * W + pos_to_bin<N, S_IDX + 1>(p - q * S);
+  }
+}
+
+// Full forward transform: registers hold stage-0 layout (v[i] <-> element t + i*T) on entry,
+// last-stage layout (digit-reversed positions) on exit.  Uses 2 barriers per exchange.
+template <int N, int S_IDX = 0>
+__device__ __forceinline__ void fft_forward(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw) {
+  stage_compute<N, S_IDX, false>(v, t, tw);
+  if constexpr (S_IDX + 1 < Plan<N>::ns) {
+    __syncthreads();                       // previous readers of sm are done
+    stage_store<N, S_IDX>(v, t, sm);
+    __syncthreads();
+    stage_load<N, S_IDX + 1>(v, t, sm);
+    fft_forward<N, S_IDX + 1>(v, t, sm, tw);
+  }
+}
+
+// Full inverse (unnormalised) transform: last-stage layout in, stage-0 layout out.
+template <int N, int S_IDX = Plan<N>::ns - 1>
+__device__ __forceinline__ void fft_inverse(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw) {
+  stage_compute<N, S_IDX, true>(v, t, tw);
+  if constexpr (S_IDX > 0) {
+    __syncthreads();
+    stage_store<N, S_IDX>(v, t, sm);
+    __syncthreads();
+    stage_load<N, S_IDX - 1>(v, t, sm);
+    fft_inverse<N, S_IDX - 1>(v, t, sm, tw);
+  }
+}
+
+}  // namespace thz

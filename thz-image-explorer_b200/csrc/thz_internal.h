@@ -1,0 +1,76 @@
+// thz_internal.h -- context object and launcher prototypes shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/thzgpu.h"
+
+namespace thz {
+
+// per-N device tables: twiddles for the DIF stages + digit-reversal helpers
+struct FftTables {
+  int n = 0;
+  float2* d_tw = nullptr;       // TwTotal<N> entries
+};
+
+struct TracePlan {
+  int n = 0;                    // samples per trace (power of two)
+  float* d_m_pre = nullptr;     // [n] or null
+  float* d_m_post = nullptr;    // [n] or null
+  float* d_band = nullptr;      // [n/2+1] or null
+  float* d_hq = nullptr;        // [n] band (or ones) / n in last-stage register order (fused kernel)
+  bool has_pre = false, has_post = false, has_band = false;
+};
+
+constexpr int kHostStreams = 3;
+
+}  // namespace thz
+
+struct thz_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;                 // compute stream (device-pointer API)
+  cudaStream_t hstream[thz::kHostStreams] = {};  // host-pointer API pipelines
+  void* d_stage[thz::kHostStreams] = {};         // staging buffers of the host-pointer API
+  size_t stage_bytes = 0;
+  std::map<int, thz::FftTables> tables;
+  std::map<const void*, int> occ;                // resident CTAs per SM, per kernel
+  thz::TracePlan plan;
+  std::string err;
+  int64_t launches = 0;
+  float* d_scratch = nullptr;                    // reductions
+  size_t scratch_bytes = 0;
+};
+
+namespace thz {
+
+int set_err(thz_ctx* c, int code, const std::string& msg);
+int cuda_fail(thz_ctx* c, cudaError_t e, const char* what);
+#define THZ_CUDA(ctx, call)                                              \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) return ::thz::cuda_fail((ctx), e__, #call);  \
+  } while (0)
+
+int get_tables(thz_ctx* c, int n, const FftTables** out);
+int ensure_scratch(thz_ctx* c, size_t bytes);
+
+// thz_trace.cu
+int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P);
+int launch_trace_forward(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_win, float2* d_fft,
+                         float* d_amp, float* d_phase, int64_t P);
+int launch_trace_inverse(thz_ctx* c, cudaStream_t s, const float2* d_fft, bool use_band, bool use_post,
+                         float* d_out, float* d_img, int64_t P);
+int launch_band_apply(thz_ctx* c, cudaStream_t s, float2* d_fft, float* d_amp, int64_t P);
+int launch_column_sums(thz_ctx* c, cudaStream_t s, const float* d_x, int64_t rows, int cols, float* d_partials,
+                       int nblocks);
+int launch_generate(thz_ctx* c, cudaStream_t s, float* d_cube, int width, int height, int n, int row0,
+                    int total_width, uint64_t seed, float t0, float dt, float noise);
+int build_hq(int n, const float* band /*nullable, host*/, std::vector<float>& hq);
+int build_twiddles(int n, std::vector<float2>& tw);
+bool supported_n(int n);
+
+}  // namespace thz

@@ -1,0 +1,673 @@
+// thz_trace.cu -- the per-pixel trace pass: window -> real FFT -> amplitude / unwrapped phase
+// -> band-pass -> inverse FFT -> time gate -> intensity, as hand-written sm_100a kernels.
+//
+// Reference arithmetic being replaced (paths under the upstream repository):
+//   src/math_tools.rs:330-398   fft()   (window, r2c, |s|, unwrap(arg s))
+//   src/math_tools.rs:211-240   numpy_unwrap
+//   src/math_tools.rs:546-567   ifft()  (c2r, / N)
+//   src/filters/band_pass_fd.rs:155-212          (band multiplier on fft and amplitudes)
+//   src/filters/band_pass_td_before_fft.rs:155-174, tilt_compensation.rs:188  (time multipliers)
+//   src/data_thread.rs:1288-1307                 (intensity image)
+//
+// Layout: cube [P][N] f32, trace-major.  Two consecutive traces (2q, 2q+1) are packed as the
+// real / imaginary part of one complex sequence and transformed by a group of T = N/16
+// threads (thz_fft.cuh).  A CTA of 256 threads (512 for N = 8192) holds G = 256/T groups.
+// Every trace crosses HBM once per kernel: coalesced 128-byte-per-warp loads straight into
+// registers, streaming (evict-first) cache policy, multiplier vectors served from L1/L2.
+#include "thz_fft.cuh"
+#include "thz_internal.h"
+
+#include <math.h>
+
+namespace thz {
+
+template <int N> struct Geo {
+  static constexpr int T = N / kE;                       // threads per trace pair
+  static constexpr int NT = (T >= 256) ? T : 256;        // threads per CTA
+  static constexpr int G = NT / T;                       // trace pairs per CTA pass
+  static constexpr int kScr = 32 * G;                    // float scratch per CTA
+  static constexpr int kMinBlocks = (NT == 256) ? 2 : 1; // register cap: 128 per thread
+  static constexpr size_t smem_bytes = (size_t)G * padded_len(N) * sizeof(float2) + kScr * sizeof(float);
+};
+
+struct TraceArgs {
+  const float* in;        // [P][N]
+  float* out;             // [P][N]
+  float* img;             // [P] or null
+  const float* m_pre;     // [N] or null
+  const float* m_post;    // [N] or null
+  const float* hq;        // [N] (band / N) in last-stage register order
+  const float* band;      // [F] or null
+  const float2* tw;
+  float2* fft;            // [P][F]
+  const float2* fft_in;   // [P][F]
+  float* amp;
+  float* phase;
+  float* win;             // windowed trace out (forward) or null
+  int64_t P;
+};
+
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+
+// sum `a` and `b` over the T threads of a group; result valid in thread t == 0 of the group
+template <int N>
+__device__ __forceinline__ void group_reduce2(float& a, float& b, int t, int g, float* scr) {
+  constexpr int T = Geo<N>::T;
+  constexpr int W = (T < 32) ? T : 32;
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if constexpr (T > 32) {
+    constexpr int NW = T / 32;
+    float* s = scr + g * 32;
+    if ((t & 31) == 0) {
+      s[2 * (t >> 5)] = a;
+      s[2 * (t >> 5) + 1] = b;
+    }
+    __syncthreads();
+    if (t == 0) {
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        sa += s[2 * w];
+        sb += s[2 * w + 1];
+      }
+      a = sa;
+      b = sb;
+    }
+  }
+}
+
+// Load the pair (p0, p1) into stage-0 register layout, multiplied by m_pre.
+template <int N>
+__device__ __forceinline__ void load_pair(float2 (&v)[kE], const TraceArgs& a, int t, bool act0, bool act1,
+                                          int64_t p0) {
+  constexpr int T = Geo<N>::T;
+  const float* r0 = a.in + p0 * N + t;
+  const float* r1 = r0 + N;
+#pragma unroll
+  for (int i = 0; i < kE; ++i) {
+    v[i].x = act0 ? ld_stream(r0 + i * T) : 0.f;
+    v[i].y = act1 ? ld_stream(r1 + i * T) : 0.f;
+  }
+  if (a.m_pre != nullptr) {
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      const float m = __ldg(a.m_pre + t + i * T);
+      v[i].x *= m;
+      v[i].y *= m;
+    }
+  }
+}
+
+// multiply by m_post, store both traces, intensity = sum of squares of the stored values
+template <int N>
+__device__ __forceinline__ void store_pair(float2 (&v)[kE], const TraceArgs& a, int t, int g, bool act0,
+                                           bool act1, int64_t p0, bool use_post, float* scr) {
+  constexpr int T = Geo<N>::T;
+  if (use_post) {
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      const float m = __ldg(a.m_post + t + i * T);
+      v[i].x *= m;
+      v[i].y *= m;
+    }
+  }
+  float* r0 = a.out + p0 * N + t;
+  float* r1 = r0 + N;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kE; ++i) {
+    if (act0) st_stream(r0 + i * T, v[i].x);
+    if (act1) st_stream(r1 + i * T, v[i].y);
+    s0 = fmaf(v[i].x, v[i].x, s0);
+    s1 = fmaf(v[i].y, v[i].y, s1);
+  }
+  if (a.img != nullptr) {       // uniform over the CTA
+    group_reduce2<N>(s0, s1, t, g, scr);
+    if (t == 0) {
+      if (act0) a.img[p0] = s0;
+      if (act1) a.img[p0 + 1] = s1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// fused chain: one read and one write of the cube
+// ------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(const TraceArgs a) {
+  using GEO = Geo<N>;
+  constexpr int T = GEO::T, G = GEO::G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(N));
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(N);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  const bool use_post = a.m_post != nullptr;
+  constexpr int LAST = Plan<N>::ns - 1;
+  constexpr int RL = Plan<N>::r[LAST];
+  constexpr int UL = kE / RL;
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t pair = item * G + g;
+    const int64_t p0 = pair * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    float2 v[kE];
+    load_pair<N>(v, a, t, act0, act1, p0);
+    fft_forward<N>(v, t, sm, a.tw);
+    // band-pass in digit-reversed order: register (u, m) <-> position (t + u*T)*RL + m,
+    // hq is stored [m][beta] so that a warp reads consecutive floats
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      const int u = i % UL, m = i / UL;
+      const float h = __ldg(a.hq + m * (N / RL) + t + u * T);
+      v[i].x *= h;
+      v[i].y *= h;
+    }
+    fft_inverse<N>(v, t, sm, a.tw);
+    store_pair<N>(v, a, t, g, act0, act1, p0, use_post, scr);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// forward: spectra materialised (drop-in for math_tools::fft)
+// ------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_forward(const TraceArgs a) {
+  using GEO = Geo<N>;
+  constexpr int T = GEO::T, G = GEO::G;
+  constexpr int F = N / 2 + 1;
+  constexpr int PF = pad_idx(N / 2) + 1;   // padded floats per trace for the phase buffer
+  constexpr int H = T / 2;                 // threads per trace in the unwrap
+  constexpr int NU = (N / 2) / T + 1;      // bins per thread: k = t + u*T, u < NU (last only t == 0)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(N));
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(N);
+  float* phs = reinterpret_cast<float*>(sm);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<N>::ns - 1;
+  const bool want_phase = a.phase != nullptr;
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t pair = item * G + g;
+    const int64_t p0 = pair * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    float2 v[kE];
+    load_pair<N>(v, a, t, act0, act1, p0);
+    if (a.win != nullptr) {   // the reference leaves the windowed trace in `data`
+      float* w0 = a.win + p0 * N + t;
+      float* w1 = w0 + N;
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        if (act0) st_stream(w0 + i * T, v[i].x);
+        if (act1) st_stream(w1 + i * T, v[i].y);
+      }
+    }
+    fft_forward<N>(v, t, sm, a.tw);
+    // scatter to natural bin order
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = v[i];
+    __syncthreads();
+    // split the packed spectrum: X1 = (Z[k] + conj Z[N-k]) / 2, X2 = (Z[k] - conj Z[N-k]) / 2i
+    float ph0[NU], ph1[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int k = t + u * T;
+      ph0[u] = 0.f;
+      ph1[u] = 0.f;
+      if (u < NU - 1 || t == 0) {
+        const float2 z1 = sm[pad_idx(k)];
+        const float2 z2 = sm[pad_idx((N - k) & (N - 1))];
+        const float2 x0 = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+        const float2 x1 = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+        if (a.fft != nullptr) {
+          if (act0) __stcs(a.fft + p0 * F + k, x0);
+          if (act1) __stcs(a.fft + (p0 + 1) * F + k, x1);
+        }
+        if (a.amp != nullptr) {
+          if (act0) st_stream(a.amp + p0 * F + k, sqrtf(fmaf(x0.x, x0.x, x0.y * x0.y)));
+          if (act1) st_stream(a.amp + (p0 + 1) * F + k, sqrtf(fmaf(x1.x, x1.x, x1.y * x1.y)));
+        }
+        if (want_phase) {
+          ph0[u] = atan2f(x0.y, x0.x);
+          ph1[u] = atan2f(x1.y, x1.x);
+        }
+      }
+    }
+    if (want_phase) {   // uniform over the CTA
+      __syncthreads();  // all reads of Z done; reuse the buffer for raw phases
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int k = t + u * T;
+        if (u < NU - 1 || t == 0) {
+          phs[pad_idx(k)] = ph0[u];
+          phs[PF + pad_idx(k)] = ph1[u];
+        }
+      }
+      __syncthreads();
+      // threshold unwrap (src/math_tools.rs:224-237): thread (r, tau) owns bins 16 tau + 1 .. 16 tau + 16
+      const int r = t / H, tau = t % H;
+      float* pr = phs + r * PF;
+      const float kPi = 3.14159265358979323846f, kTwoPi = 2.0f * kPi;
+      float loc[16];
+      float prev = pr[pad_idx(16 * tau)];
+      float run = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float val = pr[pad_idx(16 * tau + 1 + c)];
+        float d = val - prev;
+        if (d > kPi) d -= kTwoPi;
+        else if (d < -kPi) d += kTwoPi;
+        run += d;
+        loc[c] = run;
+        prev = val;
+      }
+      // exclusive scan of `run` over tau (H threads, aligned to lanes)
+      constexpr int W = (H < 32) ? H : 32;
+      float inc = run;
+#pragma unroll
+      for (int o = 1; o < W; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, inc, o, W);
+        if ((tau & (W - 1)) >= o) inc += n;
+      }
+      float base = inc - run;
+      if constexpr (H > 32) {
+        constexpr int NW = H / 32;
+        float* s = scr + g * 32 + r * 16;
+        if ((tau & 31) == 31) s[tau >> 5] = inc;
+        __syncthreads();
+        const int wq = tau >> 5;
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+          if (w < wq) base += s[w];
+      } else {
+        __syncthreads();
+      }
+      base += pr[0];
+      // all neighbours have read their `prev` (barrier above) -> overwrite in place
+#pragma unroll
+      for (int c = 0; c < 16; ++c) pr[pad_idx(16 * tau + 1 + c)] = base + loc[c];
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int k = t + u * T;
+        if (u < NU - 1 || t == 0) {
+          if (act0) st_stream(a.phase + p0 * F + k, phs[pad_idx(k)]);
+          if (act1) st_stream(a.phase + (p0 + 1) * F + k, phs[PF + pad_idx(k)]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// inverse: spectra in (drop-in for math_tools::ifft, optionally fused with the FD band-pass
+// and the time gate after the inverse FFT)
+// ------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_inverse(const TraceArgs a) {
+  using GEO = Geo<N>;
+  constexpr int T = GEO::T, G = GEO::G;
+  constexpr int F = N / 2 + 1;
+  constexpr int NU = (N / 2) / T + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(N));
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(N);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<N>::ns - 1;
+  const bool use_post = a.m_post != nullptr;
+  const float inv_n = 1.0f / (float)N;
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t pair = item * G + g;
+    const int64_t p0 = pair * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    __syncthreads();   // previous iteration's readers of sm are done
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int k = t + u * T;
+      if (u < NU - 1 || t == 0) {
+        float2 x0 = act0 ? __ldcs(a.fft_in + p0 * F + k) : make_float2(0.f, 0.f);
+        float2 x1 = act1 ? __ldcs(a.fft_in + (p0 + 1) * F + k) : make_float2(0.f, 0.f);
+        const float s = (a.band != nullptr) ? __ldg(a.band + k) * inv_n : inv_n;
+        x0.x *= s; x0.y *= s; x1.x *= s; x1.y *= s;
+        if (k == 0 || k == N / 2) {   // c2r ignores the imaginary parts of DC and Nyquist
+          sm[pad_idx(k)] = make_float2(x0.x, x1.x);
+        } else {
+          sm[pad_idx(k)] = make_float2(x0.x - x1.y, x0.y + x1.x);
+          sm[pad_idx(N - k)] = make_float2(x0.x + x1.y, x1.x - x0.y);
+        }
+      }
+    }
+    __syncthreads();
+    float2 v[kE];
+#pragma unroll
+    for (int i = 0; i < kE; ++i) v[i] = sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))];
+    fft_inverse<N>(v, t, sm, a.tw);
+    store_pair<N>(v, a, t, g, act0, act1, p0, use_post, scr);
+  }
+}
+
+// fft *= band, amp *= band (src/filters/band_pass_fd.rs:155-212); one thread per bin pair
+__global__ void k_band_apply(float2* __restrict__ fft, float* __restrict__ amp, const float* __restrict__ band,
+                             int64_t total, int F) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const float b = __ldg(band + (int)(i % F));
+    if (fft != nullptr) {
+      float2 x = fft[i];
+      x.x *= b;
+      x.y *= b;
+      fft[i] = x;
+    }
+    if (amp != nullptr) amp[i] *= b;
+  }
+}
+
+// partial column sums of x[rows][cols]: block b sums rows [b*rpb, (b+1)*rpb) sequentially
+__global__ void k_column_sums(const float* __restrict__ x, int64_t rows, int cols, float* __restrict__ partials) {
+  const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rpb;
+  const int64_t r1 = (r0 + rpb < rows) ? r0 + rpb : rows;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float acc = 0.f;
+    int64_t r = r0;
+    for (; r + 4 <= r1; r += 4) {
+      const float v0 = __ldcs(x + r * cols + c), v1 = __ldcs(x + (r + 1) * cols + c);
+      const float v2 = __ldcs(x + (r + 2) * cols + c), v3 = __ldcs(x + (r + 3) * cols + c);
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; r < r1; ++r) acc += __ldcs(x + r * cols + c);
+    partials[(int64_t)blockIdx.x * cols + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// synthetic scan generator
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void k_generate(float* __restrict__ cube, int width, int height, int n, int row0, int total_width,
+                           uint64_t seed, float t0, float dt, float noise) {
+  const int64_t nq = (int64_t)width * height * (n / 4);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int q_per = n / 4;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+    const int64_t p = q / q_per;
+    const int i0 = (int)(q % q_per) * 4;
+    const int x = (int)(p / height) + row0, y = (int)(p % height);
+    // amplitude: bars / checker pattern at two pitches so that deconvolution has structure
+    const int c1 = ((x >> 4) + (y >> 4)) & 1, c2 = ((x >> 2) ^ (y >> 3)) & 1;
+    const float amp = 1.0f + 0.35f * (c1 ? 1.f : -1.f) + 0.12f * (c2 ? 1.f : -1.f);
+    const float up = 0.5f + 0.5f * __sinf(0.013f * (float)x + 0.021f * (float)y);
+    const float tp = 10.0f + 5.0f * up;   // pulse position relative to t0 (ps)
+    const float tau = 0.3f, fc = 1.0f;
+    const uint64_t gp = (uint64_t)x * (uint64_t)height + (uint64_t)y;
+    const uint64_t h0 = mix64(seed ^ mix64(gp * 0x100000001B3ull + (uint64_t)(i0 >> 2)));
+    const uint64_t h1 = mix64(h0);
+    float nz[4];
+    {
+      const float u0 = ((float)(uint32_t)(h0 & 0xffffffffu) + 0.5f) * (1.0f / 4294967296.0f);
+      const float u1 = ((float)(uint32_t)(h0 >> 32) + 0.5f) * (1.0f / 4294967296.0f);
+      const float u2 = ((float)(uint32_t)(h1 & 0xffffffffu) + 0.5f) * (1.0f / 4294967296.0f);
+      const float u3 = ((float)(uint32_t)(h1 >> 32) + 0.5f) * (1.0f / 4294967296.0f);
+      const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+      float s, c;
+      __sincosf(6.283185307179586f * u1, &s, &c);
+      nz[0] = ra * c; nz[1] = ra * s;
+      __sincosf(6.283185307179586f * u3, &s, &c);
+      nz[2] = rb * c; nz[3] = rb * s;
+    }
+    float4 o;
+    float* op = &o.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float tt = (float)(i0 + j) * dt - tp;
+      const float e = tt / tau;
+      op[j] = amp * __expf(-e * e) * __cosf(6.283185307179586f * fc * tt) + noise * nz[j];
+    }
+    (void)t0;
+    (void)total_width;
+    reinterpret_cast<float4*>(cube)[q] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host side: tables and launchers
+// ------------------------------------------------------------------------------------
+bool supported_n(int n) {
+  return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096 || n == 8192;
+}
+
+template <int N> static void host_plan(int& ns, int (&r)[4]) {
+  ns = Plan<N>::ns;
+  for (int i = 0; i < 4; ++i) r[i] = Plan<N>::r[i];
+}
+static bool plan_of(int n, int& ns, int (&r)[4]) {
+  switch (n) {
+    case 64: host_plan<64>(ns, r); return true;
+    case 128: host_plan<128>(ns, r); return true;
+    case 256: host_plan<256>(ns, r); return true;
+    case 512: host_plan<512>(ns, r); return true;
+    case 1024: host_plan<1024>(ns, r); return true;
+    case 2048: host_plan<2048>(ns, r); return true;
+    case 4096: host_plan<4096>(ns, r); return true;
+    case 8192: host_plan<8192>(ns, r); return true;
+    default: return false;
+  }
+}
+
+int build_twiddles(int n, std::vector<float2>& tw) {
+  int ns, r[4];
+  if (!plan_of(n, ns, r)) return THZ_EINVAL;
+  tw.clear();
+  int L = n;
+  for (int s = 0; s + 1 < ns; ++s) {
+    const int R = r[s], S = L / R;
+    for (int q = 1; q < R; ++q)
+      for (int j = 0; j < S; ++j) {
+        const double ang = -2.0 * M_PI * (double)j * (double)q / (double)L;
+        tw.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+      }
+    L = S;
+  }
+  if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
+  return THZ_OK;
+}
+
+static int host_pos_to_bin(int n, int ns, const int* r, int p) {
+  int k = 0, w = 1, L = n;
+  for (int s = 0; s < ns; ++s) {
+    const int S = L / r[s];
+    const int q = p / S;
+    p -= q * S;
+    k += q * w;
+    w *= r[s];
+    L = S;
+  }
+  return k;
+}
+
+// hq[m * (n / RL) + beta] = H[k(beta * RL + m)] / n with H the band multiplier mirrored to all n bins
+int build_hq(int n, const float* band, std::vector<float>& hq) {
+  int ns, r[4];
+  if (!plan_of(n, ns, r)) return THZ_EINVAL;
+  const int RL = r[ns - 1];
+  hq.assign(n, 0.f);
+  const float inv_n = 1.0f / (float)n;
+  for (int beta = 0; beta < n / RL; ++beta)
+    for (int m = 0; m < RL; ++m) {
+      const int k = host_pos_to_bin(n, ns, r, beta * RL + m);
+      const int kk = (k <= n / 2) ? k : n - k;
+      const float h = band ? band[kk] : 1.0f;
+      hq[(size_t)m * (n / RL) + beta] = h * inv_n;
+    }
+  return THZ_OK;
+}
+
+template <int N, typename K>
+static int launch_geo(thz_ctx* c, cudaStream_t s, K kernel, const TraceArgs& a) {
+  using GEO = Geo<N>;
+  const size_t smem = GEO::smem_bytes;
+  const void* key = (const void*)kernel;
+  auto it = c->occ.find(key);
+  if (it == c->occ.end()) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(smem)");
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, GEO::NT, smem);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (nb < 1) return set_err(c, THZ_ECUDA, "trace kernel does not fit on an SM");
+    it = c->occ.emplace(key, nb).first;
+  }
+  const int64_t npairs = (a.P + 1) / 2;
+  const int64_t nitems = (npairs + GEO::G - 1) / GEO::G;
+  if (nitems <= 0) return THZ_OK;
+  int64_t grid = (int64_t)c->sm_count * it->second;   // persistent: one wave of resident CTAs
+  if (grid > nitems) grid = nitems;
+  kernel<<<(unsigned)grid, GEO::NT, smem, s>>>(a);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "trace kernel launch");
+  return THZ_OK;
+}
+
+#define THZ_DISPATCH_N(n, FN, ...)                 \
+  switch (n) {                                     \
+    case 64: return FN<64>(__VA_ARGS__);           \
+    case 128: return FN<128>(__VA_ARGS__);         \
+    case 256: return FN<256>(__VA_ARGS__);         \
+    case 512: return FN<512>(__VA_ARGS__);         \
+    case 1024: return FN<1024>(__VA_ARGS__);       \
+    case 2048: return FN<2048>(__VA_ARGS__);       \
+    case 4096: return FN<4096>(__VA_ARGS__);       \
+    case 8192: return FN<8192>(__VA_ARGS__);       \
+    default: return THZ_EINVAL;                    \
+  }
+
+template <int N> static int do_fused(thz_ctx* c, cudaStream_t s, const TraceArgs& a) {
+  return launch_geo<N>(c, s, k_trace_fused<N>, a);
+}
+template <int N> static int do_forward(thz_ctx* c, cudaStream_t s, const TraceArgs& a) {
+  return launch_geo<N>(c, s, k_trace_forward<N>, a);
+}
+template <int N> static int do_inverse(thz_ctx* c, cudaStream_t s, const TraceArgs& a) {
+  return launch_geo<N>(c, s, k_trace_inverse<N>, a);
+}
+
+static int base_args(thz_ctx* c, TraceArgs& a, int64_t P) {
+  if (c->plan.n == 0) return set_err(c, THZ_ESTATE, "thz_plan_trace has not been called");
+  if (P < 0) return set_err(c, THZ_EINVAL, "negative trace count");
+  const FftTables* tb = nullptr;
+  int rc = get_tables(c, c->plan.n, &tb);
+  if (rc != THZ_OK) return rc;
+  a = TraceArgs{};
+  a.tw = tb->d_tw;
+  a.P = P;
+  return THZ_OK;
+}
+
+int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P) {
+  TraceArgs a;
+  int rc = base_args(c, a, P);
+  if (rc != THZ_OK) return rc;
+  if (P == 0) return THZ_OK;
+  if (!d_in || !d_out) return set_err(c, THZ_EINVAL, "null cube pointer");
+  a.in = d_in;
+  a.out = d_out;
+  a.img = d_img;
+  a.m_pre = c->plan.has_pre ? c->plan.d_m_pre : nullptr;
+  a.m_post = c->plan.has_post ? c->plan.d_m_post : nullptr;
+  a.hq = c->plan.d_hq;
+  THZ_DISPATCH_N(c->plan.n, do_fused, c, s, a);
+}
+
+int launch_trace_forward(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_win, float2* d_fft, float* d_amp,
+                         float* d_phase, int64_t P) {
+  TraceArgs a;
+  int rc = base_args(c, a, P);
+  if (rc != THZ_OK) return rc;
+  if (P == 0) return THZ_OK;
+  if (!d_in) return set_err(c, THZ_EINVAL, "null cube pointer");
+  a.in = d_in;
+  a.win = d_win;
+  a.fft = d_fft;
+  a.amp = d_amp;
+  a.phase = d_phase;
+  a.m_pre = c->plan.has_pre ? c->plan.d_m_pre : nullptr;
+  THZ_DISPATCH_N(c->plan.n, do_forward, c, s, a);
+}
+
+int launch_trace_inverse(thz_ctx* c, cudaStream_t s, const float2* d_fft, bool use_band, bool use_post, float* d_out,
+                         float* d_img, int64_t P) {
+  TraceArgs a;
+  int rc = base_args(c, a, P);
+  if (rc != THZ_OK) return rc;
+  if (P == 0) return THZ_OK;
+  if (!d_fft || !d_out) return set_err(c, THZ_EINVAL, "null pointer");
+  a.fft_in = d_fft;
+  a.out = d_out;
+  a.img = d_img;
+  a.band = (use_band && c->plan.has_band) ? c->plan.d_band : nullptr;
+  a.m_post = (use_post && c->plan.has_post) ? c->plan.d_m_post : nullptr;
+  THZ_DISPATCH_N(c->plan.n, do_inverse, c, s, a);
+}
+
+int launch_band_apply(thz_ctx* c, cudaStream_t s, float2* d_fft, float* d_amp, int64_t P) {
+  if (c->plan.n == 0) return set_err(c, THZ_ESTATE, "thz_plan_trace has not been called");
+  if (!c->plan.has_band || P == 0) return THZ_OK;   // band of ones
+  const int F = c->plan.n / 2 + 1;
+  const int64_t total = P * F;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)c->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  k_band_apply<<<(unsigned)blocks, 256, 0, s>>>(d_fft, d_amp, c->plan.d_band, total, F);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_band_apply launch");
+  return THZ_OK;
+}
+
+int launch_column_sums(thz_ctx* c, cudaStream_t s, const float* d_x, int64_t rows, int cols, float* d_partials,
+                       int nblocks) {
+  k_column_sums<<<nblocks, 256, 0, s>>>(d_x, rows, cols, d_partials);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_column_sums launch");
+  return THZ_OK;
+}
+
+int launch_generate(thz_ctx* c, cudaStream_t s, float* d_cube, int width, int height, int n, int row0,
+                    int total_width, uint64_t seed, float t0, float dt, float noise) {
+  if (n % 4 != 0) return set_err(c, THZ_EINVAL, "n must be a multiple of 4");
+  const int64_t nq = (int64_t)width * height * (n / 4);
+  if (nq == 0) return THZ_OK;
+  int64_t blocks = (nq + 255) / 256;
+  const int64_t cap = (int64_t)c->sm_count * 32;
+  if (blocks > cap) blocks = cap;
+  k_generate<<<(unsigned)blocks, 256, 0, s>>>(d_cube, width, height, n, row0, total_width, seed, t0, dt, noise);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_generate launch");
+  return THZ_OK;
+}
+
+}  // namespace thz
