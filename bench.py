@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the thz-image-explorer filter-chain hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over the synthetic cube BASELINE.json names
+(config 5: 2048 x 2048 pixels x 4096 samples): the fused trace pass (window -> rFFT ->
+band-pass -> irFFT -> gate -> intensity) and, when built, the PSF deconvolution that ends the
+chain.  The cube is row-slab sharded over the ranks (strong scaling: total work fixed).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
+
+`--impl reference` times the reference's CPU algorithm (the oracle port: the Rust reference
+cannot be built here, no rustc) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "thz-image-explorer_b200"
+
+METRIC = "pixel_traces_per_s"
+UNIT = "traces/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(pw))}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=2048)
+    ap.add_argument("--height", type=int, default=2048)
+    ap.add_argument("--samples", type=int, default=4096)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline slab (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"synthetic {a.width}x{a.height} pixels x {a.samples} samples, default filter chain (BASELINE config 5)"
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_chain_sample(a, rows, reps=1):
+    """Times the oracle's stage-by-stage default chain (slots 1..7) on a rows x height x N slab.
+    Returns (traces_per_s, seconds, cores)."""
+    from oracle import thz_oracle as orc   # the timed CPU baseline (cpu_baseline / --impl reference only)
+    cores = len(os.sched_getaffinity(0))
+    n, h = a.samples, a.height
+    rng = np.random.default_rng(1)
+    t = (np.float32(1000.0) + np.float32(0.05) * np.arange(n, dtype=np.float32)).astype(np.float32)
+    tt = np.arange(n) * 0.05 - 10.0
+    cube = (np.exp(-(tt / 0.3) ** 2) * np.cos(2 * np.pi * tt)
+            + 0.01 * rng.standard_normal((rows, h, n))).astype(np.float32)
+    f = orc.frequency_axis(t)
+    F = f.size
+    s0 = orc.ScannedImageFilterData(time=t, data=cube, frequency=f, fft=np.zeros((rows, h, F), np.complex64),
+                                    amplitudes=np.zeros((rows, h, F), np.float32),
+                                    phases=np.zeros((rows, h, F), np.float32), img=orc.intensity_image(cube),
+                                    dx=0.5, dy=0.5, width=rows, height=h)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.run_default_chain(s0, workers=cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return rows * h / best, best, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = a.cpu_rows or 4
+    vals = []
+    for _ in range(a.warmup):
+        cpu_chain_sample(a, rows)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        v, dt, cores = cpu_chain_sample(a, rows)
+        vals.append(dt)
+    total = time.perf_counter() - t0
+    ms = 1e3 * float(np.mean(vals))
+    value = rows * a.height / (ms / 1e3)
+    sample = f"{rows}x{a.height}x{a.samples} row slab per step (chain is linear in pixels)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample,
+                   "note": "restated reference (oracle port, numpy/scipy pocketfft f32; rustc unavailable)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": total,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    m = importlib.import_module(PKG)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+        torch.cuda.set_device(local)
+
+    W, H, N = a.width, a.height, a.samples
+    # row-slab partition over axis 0 (x), uneven last slab allowed
+    base, rem = divmod(W, world)
+    rows = base + (1 if rank < rem else 0)
+    row0 = rank * base + min(rank, rem)
+    P = rows * H
+    P_total = W * H
+
+    ctx = m.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    t_axis = (np.float32(1000.0) + np.float32(0.05) * np.arange(N, dtype=np.float32)).astype(np.float32)
+    m_pre, band, m_post = m.host.chain_multipliers(t_axis)
+    ctx.plan_trace(N, m_pre, band, m_post)
+
+    cube_bytes = P * N * 4
+    d_in = ctx.alloc(max(cube_bytes, 16))
+    d_out = ctx.alloc(max(cube_bytes, 16))
+    d_img = ctx.alloc(max(P * 4, 16))
+    ctx.generate_cube(d_in, rows, H, N, row0=row0, total_width=W)
+    ctx.sync()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        ctx.trace_fused_dev(d_in.ptr, d_out.ptr, d_img.ptr, P)
+
+    launches0 = None
+    for _ in range(a.warmup):
+        step()
+    ctx.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(a.steps):
+        step()
+        ev[i + 1].record(stream)
+    ctx.sync()
+    barrier()
+    launches = ctx.launches - launches0
+    per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
+    total_ms = ev[0].elapsed_time(ev[a.steps])
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / a.steps
+    value = P_total / (ms_per_step / 1e3)
+
+    # roofline of the dominant kernel (the fused trace pass): algorithmic bytes per launch = (8N + 4) * P
+    peak, peak_src = measured_peaks()
+    alg_bytes = (8 * N + 4) * P
+    kernel_ms = float(np.mean(per_step_ms))      # one launch per step on this stream
+    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"k_trace_fused<{N}>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms}
+
+    # end to end through the host-pointer C ABI: pinned host cube -> H2D -> chain -> D2H (filtered cube + img)
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, m, ctx, d_in, P, N, world, dist, barrier, P_total)
+
+    cpu = None
+    if rank == 0 and not a.no_cpu:
+        rows_cpu = a.cpu_rows or 4
+        cpu_chain_sample(a, 1)
+        v, dt, cores = cpu_chain_sample(a, rows_cpu, reps=2)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{rows_cpu}x{H}x{N} row slab, oracle port (numpy/scipy pocketfft f32), best of 2"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "partition": f"row slabs over x, {world} rank(s)",
+                       "l2": "inputs larger than L2 (cube >> 126 MB), no flush needed",
+                       "stages": ["trace pass (fused)"]},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    d_in.free(); d_out.free(); d_img.free()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_e2e(a, m, ctx, d_in, P, N, world, dist, barrier, P_total):
+    """Same metric through thz_trace_fused_host with HOST buffers (pinned), copies inside the
+    timed region.  The host slab is the rank's whole slab when it fits comfortably in RAM,
+    otherwise a bounded slab (stated in the result)."""
+    import ctypes as C
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except Exception:
+        avail = 64 << 30
+    budget = int(0.55 * avail / max(world, 1))
+    Pe = min(P, max(2, budget // (N * 4 + 4)))
+    Pe -= Pe % 2
+    nbytes = Pe * N * 4
+    hp = C.c_void_p()
+    hi = C.c_void_p()
+    if m.lib.thz_host_alloc(nbytes, C.byref(hp)) != 0 or m.lib.thz_host_alloc(Pe * 4, C.byref(hi)) != 0:
+        return None
+    try:
+        ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_in.ptr, nbytes))
+        reps = 2
+        # warm-up (allocates the staging ring)
+        ctx._check(m.lib.thz_trace_fused_host(ctx.handle, hp.value, hp.value, hi.value, min(Pe, 1 << 15)))
+        ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_in.ptr, nbytes))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx._check(m.lib.thz_trace_fused_host(ctx.handle, hp.value, hp.value, hi.value, Pe))
+        barrier()
+        dt = (time.perf_counter() - t0) / reps
+        if dist is not None:
+            import torch
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        total_traces = Pe * world if Pe < P else P_total
+        return {"value": total_traces / dt, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
+                "d2h_bytes_per_step": int(nbytes + Pe * 4), "traces_per_rank": int(Pe),
+                "note": "thz_trace_fused_host: pinned host cube in, filtered cube + intensity map out, "
+                        "chunked over 3 streams; wall clock around the call, max over ranks"}
+    finally:
+        m.lib.thz_host_free(hp.value)
+        m.lib.thz_host_free(hi.value)
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,6 +78,30 @@ int thz_host_free(void* ptr);
 int thz_generate_cube(thz_ctx* ctx, float* d_cube, int width, int height, int n, int row0,
                       int total_width, uint64_t seed, float t0, float dt, float noise);
 
+/* ------------------------------------------------- host-side multiplier vectors -------- */
+/* Pixel-independent vectors the reference recomputes for every trace; computed once here, in
+ * f32 exactly as the reference does, and handed to thz_plan_trace().  No GPU involved. */
+#define THZ_WINDOW_ADAPTED_BLACKMAN 0
+#define THZ_WINDOW_BLACKMAN 1
+#define THZ_WINDOW_HANNING 2
+#define THZ_WINDOW_HAMMING 3
+#define THZ_WINDOW_FLAT_TOP 4
+/* f[i] = i / (t[n-1] - t[0]), n/2+1 entries (src/io.rs:614-620) */
+int thz_frequency_axis(const float* time, int n, float* freq);
+/* apply_adapted_blackman_window on a vector of ones (src/math_tools.rs:81-122) */
+int thz_adapted_blackman(const float* axis, int n, float lo, float hi, float* mult);
+/* the FFT window selected by `FftWindowType` (src/math_tools.rs:356-371, 131-198);
+ * lo / hi = ConfigContainer::fft_window, used by the adapted Blackman only */
+int thz_window_multiplier(int window_type, const float* time, int n, float lo, float hi, float* mult);
+/* TimeDomainBandPassBeforeFFT / AfterFFT (src/filters/band_pass_td_before_fft.rs:134-174): clamps
+ * *low / *high to the axis (as the filter mutates its own fields), zero outside [lower, upper),
+ * adapted Blackman (ww, ww) inside.  lower / upper may be NULL. */
+int thz_time_gate_multiplier(const float* time, int n, double* low, double* high, double window_width,
+                             float* mult, int* lower, int* upper);
+/* FrequencyDomainBandPass (src/filters/band_pass_fd.rs:135-212) over all f bins */
+int thz_band_pass_multiplier(const float* freq, int f, double low, double high, double window_width,
+                             float* mult, int* lower, int* upper);
+
 /* -------------------------------------------------------------------- trace plan ------- */
 /* The pixel-independent multipliers the chain reduces to (all optional, NULL = ones):
  *   m_pre[n]  : tilt taper x time gate x FFT window

@@ -30,7 +30,8 @@ def rel_err(a, b):
     den = float(np.max(np.abs(b)))
     if den == 0.0:
         return float(np.max(np.abs(a)))
-    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))) / den)
+    wide = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    return float(np.max(np.abs(a.astype(wide) - b.astype(wide))) / den)
 
 
 def time_axis(n, t0=1000.0, dt=0.05):

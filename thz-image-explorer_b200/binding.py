@@ -69,6 +69,13 @@ def load_library():
         "thz_host_alloc": (i32, [sz, C.POINTER(vp)]),
         "thz_host_free": (i32, [vp]),
         "thz_generate_cube": (i32, [vp, fp, i32, i32, i32, i32, i32, u64, f32, f32, f32]),
+        "thz_frequency_axis": (i32, [fp, i32, fp]),
+        "thz_adapted_blackman": (i32, [fp, i32, f32, f32, fp]),
+        "thz_window_multiplier": (i32, [i32, fp, i32, f32, f32, fp]),
+        "thz_time_gate_multiplier": (i32, [fp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, fp,
+                                           C.POINTER(i32), C.POINTER(i32)]),
+        "thz_band_pass_multiplier": (i32, [fp, i32, C.c_double, C.c_double, C.c_double, fp, C.POINTER(i32),
+                                           C.POINTER(i32)]),
         "thz_plan_trace": (i32, [vp, i32, fp, fp, fp]),
         "thz_trace_fused_dev": (i32, [vp, fp, fp, fp, i64]),
         "thz_trace_forward_dev": (i32, [vp, fp, fp, fp, fp, fp, i64]),

@@ -1,0 +1,151 @@
+// thz_windows.cpp -- host-side, pixel-independent multiplier vectors of the filter chain.
+//
+// Every time-domain filter on the default path and the frequency band-pass reduce to a
+// vector that depends only on the axis and the filter parameters.  They are
+// computed here once per run, in f32 exactly as the reference computes them per trace, and
+// handed to the kernels through thz_plan_trace().
+//   blackman_window / apply_adapted_blackman_window ... src/math_tools.rs:81-122
+//   normalize_time, hamming/hanning/blackman/flat-top . src/math_tools.rs:131-198
+//   frequency axis ................................... src/io.rs:614-620
+//   time gate indices + taper ........................ src/filters/band_pass_td_before_fft.rs:134-174
+//   band-pass indices + taper ........................ src/filters/band_pass_fd.rs:135-212
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/thzgpu.h"
+
+namespace {
+
+const float kPi = 3.14159265358979323846f;  // std::f32::consts::PI
+
+// src/math_tools.rs:81-90
+float blackman_window(float n, float m) {
+  const float res = 0.42f - 0.5f * cosf(2.0f * kPi * n / m) + 0.08f * cosf(4.0f * kPi * n / m);
+  if (isnan(res)) return 1.0f;
+  return std::min(std::max(res, 0.0f), 1.0f);
+}
+
+// src/math_tools.rs:102-122 applied to a vector of ones
+void adapted_blackman(const float* axis, int n, float lo, float hi, float* mult) {
+  for (int i = 0; i < n; ++i) mult[i] = 1.0f;
+  if (n == 0) return;
+  const float a0 = axis[0], al = axis[n - 1];
+  for (int i = 0; i < n; ++i) {
+    const float t = axis[i];
+    if (t <= lo + a0) {
+      mult[i] = blackman_window(t - a0, 2.0f * lo);
+    } else if (t >= al - hi) {
+      mult[i] = blackman_window(t - (al - hi * 2.0f), 2.0f * hi);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int thz_frequency_axis(const float* time, int n, float* freq) {
+  if (!time || !freq || n < 2) return THZ_EINVAL;
+  const float rng = time[n - 1] - time[0];
+  for (int i = 0; i < n / 2 + 1; ++i) freq[i] = (float)i / rng;
+  return THZ_OK;
+}
+
+int thz_adapted_blackman(const float* axis, int n, float lo, float hi, float* mult) {
+  if ((!axis || !mult) && n > 0) return THZ_EINVAL;
+  if (n < 0) return THZ_EINVAL;
+  adapted_blackman(axis, n, lo, hi, mult);
+  return THZ_OK;
+}
+
+int thz_window_multiplier(int window_type, const float* time, int n, float lo, float hi, float* mult) {
+  if (!time || !mult || n <= 0) return THZ_EINVAL;
+  if (window_type == THZ_WINDOW_ADAPTED_BLACKMAN) {
+    adapted_blackman(time, n, lo, hi, mult);
+    return THZ_OK;
+  }
+  // normalize_time (src/math_tools.rs:131-135)
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = 0; i < n; ++i) {
+    mn = std::min(mn, time[i]);
+    mx = std::max(mx, time[i]);
+  }
+  for (int i = 0; i < n; ++i) {
+    const float t = (time[i] - mn) / (mx - mn);
+    switch (window_type) {
+      case THZ_WINDOW_BLACKMAN:
+        mult[i] = 0.42f - 0.5f * cosf(2.0f * kPi * t) + 0.08f * cosf(4.0f * kPi * t);
+        break;
+      case THZ_WINDOW_HANNING:
+        mult[i] = 0.5f * (1.0f - cosf(2.0f * kPi * t));
+        break;
+      case THZ_WINDOW_HAMMING:
+        mult[i] = 0.54f - 0.46f * cosf(2.0f * kPi * t);
+        break;
+      case THZ_WINDOW_FLAT_TOP:
+        mult[i] = 1.0f - 1.93f * cosf(2.0f * kPi * t) + 1.29f * cosf(4.0f * kPi * t) -
+                  0.388f * cosf(6.0f * kPi * t) + 0.028f * cosf(8.0f * kPi * t);
+        break;
+      default:
+        return THZ_EINVAL;
+    }
+  }
+  return THZ_OK;
+}
+
+int thz_time_gate_multiplier(const float* time, int n, double* low, double* high, double window_width,
+                             float* mult, int* lower_out, int* upper_out) {
+  if (!time || !mult || !low || !high || n <= 0) return THZ_EINVAL;
+  const float min_time = time[0], max_time = time[n - 1];
+  *low = std::max(*low, (double)min_time);     // the filter clamps its own fields (:134-138)
+  *high = std::min(*high, (double)max_time);
+  int lower = 0;
+  {
+    const float lo32 = (float)*low;
+    int i = 0;
+    while (i < n && !(time[i] >= lo32)) ++i;
+    lower = (i < n) ? i : 0;
+  }
+  int upper;
+  {
+    const float hi32 = (float)*high;
+    int i = 0;
+    while (i < n && !(time[i] >= hi32)) ++i;
+    upper = (i < n) ? i : std::max(n - 1, 0);
+  }
+  upper = std::min(std::max(upper, lower + 1), n);
+  for (int i = 0; i < n; ++i) mult[i] = 0.0f;
+  adapted_blackman(time + lower, upper - lower, (float)window_width, (float)window_width, mult + lower);
+  if (lower_out) *lower_out = lower;
+  if (upper_out) *upper_out = upper;
+  return THZ_OK;
+}
+
+int thz_band_pass_multiplier(const float* freq, int f, double low, double high, double window_width, float* mult,
+                             int* lower_out, int* upper_out) {
+  if (!freq || !mult || f <= 0) return THZ_EINVAL;
+  const float safe_low = (float)std::max(low, 0.0);
+  const float safe_high = (float)std::min(high, (double)freq[f - 1]);
+  int lower = 0;
+  {
+    int i = 0;
+    while (i < f && !(freq[i] >= safe_low)) ++i;
+    lower = (i < f) ? i : 0;
+  }
+  int upper = f;
+  {
+    int i = f - 1;
+    while (i >= 0 && !(freq[i] <= safe_high)) --i;
+    upper = (i >= 0) ? i + 1 : f;
+  }
+  for (int i = 0; i < f; ++i) mult[i] = 0.0f;
+  if (upper > lower)
+    adapted_blackman(freq + lower, upper - lower, (float)window_width, (float)window_width, mult + lower);
+  if (lower_out) *lower_out = lower;
+  if (upper_out) *upper_out = upper;
+  return THZ_OK;
+}
+
+}  // extern "C"
