@@ -139,6 +139,103 @@ int thz_trace_inverse_dev(thz_ctx* ctx, const float* d_fft, int use_band, int us
 int thz_spectral_means(thz_ctx* ctx, const float* d_fft, const float* d_amp, const float* d_phase,
                        int64_t P, float* avg_fft, float* avg_amp, float* avg_phase);
 
+/* ---------------------------------------------------------------- deconvolution -------- */
+/* PSF model as loaded from psf.npz (`load_psf`, src/io.rs:190-267; src/filters/psf.rs:7-22,
+ * 202-207): natural cubic splines per segment a + b dx + c dx^2 + d dx^3 and the hybrid fit
+ * w(f) = a/f + b + spline(f).  Arrays are borrowed. */
+typedef struct {
+  int n;                 /* knots */
+  const float* knots;    /* [n]  THz */
+  const float* values;   /* [n]  mm  */
+  const float* coeff_a;  /* [n-1] (arrays of length n are accepted) */
+  const float* coeff_b;
+  const float* coeff_c;
+  const float* coeff_d;
+} thz_spline;
+typedef struct { float base_a, base_b; thz_spline correction; } thz_hybrid_fit;
+typedef struct { thz_hybrid_fit wx_fit, wy_fit; thz_spline x0_spline, y0_spline; } thz_psf;
+
+#define THZ_MAX_PSF 255   /* PSF extent per axis, pixels */
+
+/* `Deconvolution` parameters (src/filters/deconvolution.rs:217-240, defaults :725-733) */
+typedef struct {
+  int n_iterations;   /* 500 */
+  int n_filters;      /* 25  */
+  float start_freq;   /* 0.1 THz */
+  float end_freq;     /* 10  THz */
+  float win_width;    /* 0.5 THz */
+} thz_deconv_params;
+
+/* Everything `Deconvolution::filter` derives per band before touching the cube
+ * (src/filters/deconvolution.rs:819-971): FIR taps, PSF factors (psf[i][j] = psf_x[i]*psf_y[j],
+ * axis 0 <-> x, src/filters/psf.rs:305-311), iteration count, and which branch `convolve2d`
+ * takes for this PSF (:484: area <= 256 -> direct *correlation*, else FFT *convolution*). */
+typedef struct {
+  float center_freq, wx, wy, x0, y0;
+  int kx, ky;                 /* PSF extent along x (axis 0) and y (axis 1) */
+  int n_iter;
+  int direct;                 /* 1: correlation branch, 0: convolution branch */
+  float psf_x[THZ_MAX_PSF];
+  float psf_y[THZ_MAX_PSF];
+  float fir[THZ_FIR_TAPS];
+} thz_band_plan;
+
+#define THZ_SKIP_NO_DXDY 2       /* the reference returns its input unchanged in these cases */
+#define THZ_SKIP_NO_PSF 3        /* (src/filters/deconvolution.rs:781-812, 873-885)         */
+#define THZ_SKIP_TOO_SMALL 4
+#define THZ_SKIP_PSF_TOO_LARGE 5
+
+/* `create_filter_bank` (src/filters/deconvolution.rs:160-211): n_filters x 499 Kaiser FIR
+ * taps (designed in f64, stored as f32) and the log-spaced centre frequencies. */
+int thz_fir_bank(int n_filters, double start_freq, double end_freq, double win_width, float t0, float t1,
+                 float* filters /*[n_filters][499]*/, float* center_freqs /*[n_filters]*/);
+/* psf.rs evaluators, exposed for tests */
+float thz_hybrid_eval(const thz_hybrid_fit* fit, float f);
+float thz_spline_eval_const_extrap(const thz_spline* s, float f);
+/* Host part of `Deconvolution::filter`: returns THZ_OK and fills bands[n_filters], or one of
+ * THZ_SKIP_* when the reference would return its input unchanged.  has_dxdy = 0 when the scan
+ * has no dx / dy metadata. */
+int thz_deconv_plan_bands(const thz_psf* psf, const thz_deconv_params* params, const float* time, int n,
+                          int img_rows, int img_cols, int has_dxdy, float dx, float dy, thz_band_plan* bands);
+
+/* Band energies: E[b][p] = sum_t (h_b * x[p])[t]^2 with the "same" alignment of `convolve1d`
+ * (src/filters/deconvolution.rs:266-317, 574-609, 963-966).  d_energy is [n_bands][P]. */
+int thz_deconv_energies_dev(thz_ctx* ctx, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
+                            int n_bands, float* d_energy);
+/* `richardson_lucy` (src/filters/deconvolution.rs:620-712) on one [rows][cols] image with a
+ * separable PSF: reflect pad, n_iter x { c = u (*) psf; r = d / (c + 1e-12); u *= r (*) mirror },
+ * crop; then clamp >= 0 and, when d_gain != NULL, gain = sqrt(u / d) (:975, 990-993).
+ * `direct` selects the correlation / convolution orientation of `convolve2d` (:484).
+ * abort (nullable) is polled between launches; progress (nullable) is called with
+ * progress_base + progress_span * done/n_iter. */
+int thz_rl_separable_dev(thz_ctx* ctx, const float* d_image, int rows, int cols, const float* psf_x, int kx,
+                         const float* psf_y, int ky, int direct, int n_iter, float* d_deconvolved,
+                         float* d_gain, const volatile int32_t* abort_flag, thz_progress_fn progress,
+                         void* progress_user, float progress_base, float progress_span);
+/* Same iteration for an arbitrary dense PSF psf[kx][ky] (odd extents), tiled 2-D filtering. */
+int thz_rl_dense_dev(thz_ctx* ctx, const float* d_image, int rows, int cols, const float* psf, int kx, int ky,
+                     int direct, int n_iter, float* d_deconvolved, float* d_gain,
+                     const volatile int32_t* abort_flag);
+/* One "same" 2-D filtering with zero boundary, exposed for tests: out = correlate(in, psf)
+ * (direct != 0, src/filters/deconvolution.rs:432-458) or convolve(in, psf) (direct == 0, :489-544). */
+int thz_conv2d_separable_dev(thz_ctx* ctx, const float* d_in, int rows, int cols, const float* psf_x, int kx,
+                             const float* psf_y, int ky, int direct, float* d_out);
+int thz_conv2d_dense_dev(thz_ctx* ctx, const float* d_in, int rows, int cols, const float* psf, int kx, int ky,
+                         int direct, float* d_out);
+/* Gain application and band sum (src/filters/deconvolution.rs:996-1012, 1030-1031):
+ * out[p] = sum_b gain[b][p] * (h_b * x[p]); img[p] = sum_t out^2.  d_gain is [n_bands][P]. */
+int thz_deconv_apply_dev(thz_ctx* ctx, const float* d_cube, const float* d_gain, int64_t P, int n,
+                         const thz_band_plan* bands, int n_bands, float* d_out, float* d_img);
+/* The whole filter on a device-resident cube [rows][cols][n] (slot 7 -> slot 8).  d_out may
+ * alias d_cube.  Returns THZ_ABORTED when abort_flag became non-zero. */
+int thz_deconvolution_dev(thz_ctx* ctx, const float* d_cube, int rows, int cols, int n,
+                          const thz_band_plan* bands, int n_bands, float* d_out, float* d_img,
+                          const volatile int32_t* abort_flag, thz_progress_fn progress, void* progress_user);
+/* Host-pointer drop-in for `Deconvolution::filter`. */
+int thz_deconvolution_host(thz_ctx* ctx, const float* cube, int rows, int cols, int n,
+                           const thz_band_plan* bands, int n_bands, float* out, float* img,
+                           const volatile int32_t* abort_flag, thz_progress_fn progress, void* progress_user);
+
 /* ------------------------------------------------------- trace pass, host pointers ----- */
 /* Same operators on host arrays (the reference's `ScannedImageFilterData` lives in host
  * memory).  Copies are chunked and overlapped with compute on three streams. */

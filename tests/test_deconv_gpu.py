@@ -1,0 +1,142 @@
+"""GPU parity tests of the deconvolution path against the CPU oracle (tolerance from the north
+star: max|a-b|/max|b| <= 1e-3 on deconvolved maps after N iterations)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import F32, TOL_MAP, TOL_TRACE, orc, pkg, rel_err, synthetic_cube, time_axis
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pkg().Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def psfs(psf_npz_path):
+    return pkg().host.PSF.load(psf_npz_path), orc.load_psf(psf_npz_path)
+
+
+def _gauss(k, c, w):
+    x = np.arange(k, dtype=np.float64) - k // 2
+    g = np.exp(-2 * (x - c) ** 2 / w ** 2)
+    return (g / g.max()).astype(F32)
+
+
+@pytest.mark.parametrize("shape,kx,ky", [((100, 77), 7, 7), ((64, 64), 17, 15), ((130, 141), 47, 57), ((33, 200), 3, 9),
+                                         ((70, 65), 1, 5)])
+def test_conv2d_both_orientations(ctx, shape, kx, ky):
+    """Tile kernel vs both branches of `convolve2d`: direct (a correlation) and FFT (a convolution);
+    off-centre factors make the two differ."""
+    rng = np.random.default_rng(kx * 100 + ky)
+    img = rng.uniform(0.1, 1.0, shape).astype(F32)
+    px, py = _gauss(kx, 0.6, max(kx / 4, 0.8)), _gauss(ky, -0.9, max(ky / 4, 0.8))
+    psf = np.outer(px, py).astype(F32)
+    corr = orc.direct_convolve2d(img.astype(np.float64), psf.astype(np.float64))
+    conv = orc.direct_convolve2d(img.astype(np.float64), psf[::-1, ::-1].astype(np.float64))
+    assert rel_err(ctx.conv2d(img, px, py, direct=True), corr) < 2e-6
+    assert rel_err(ctx.conv2d(img, px, py, direct=False), conv) < 2e-6
+    # dense (non-separable) kernel on the same PSF plus a perturbation that breaks separability
+    dense = (psf + 0.05 * rng.uniform(size=psf.shape)).astype(F32)
+    corr_d = orc.direct_convolve2d(img.astype(np.float64), dense.astype(np.float64))
+    conv_d = orc.direct_convolve2d(img.astype(np.float64), dense[::-1, ::-1].astype(np.float64))
+    assert rel_err(ctx.conv2d(img, dense=dense, direct=True), corr_d) < 2e-6
+    assert rel_err(ctx.conv2d(img, dense=dense, direct=False), conv_d) < 2e-6
+    # and the oracle's FFT branch really is the convolution (pins the orientation convention)
+    if kx * ky > 1:
+        assert rel_err(orc.fft_convolve2d(img, psf), conv.astype(F32)) < 1e-4
+
+
+@pytest.mark.parametrize("band_idx,n_iter", [(0, 30), (1, 60), (2, 127), (4, 13)])
+def test_richardson_lucy_matches_oracle(ctx, psfs, band_idx, n_iter):
+    """richardson_lucy + clamp + gain against the oracle, which takes the same convolve2d branch the
+    reference would (FFT for the two large PSFs, direct below 256 taps)."""
+    psf, opsf = psfs
+    shape = (96, 80)
+    t = time_axis(1024)
+    bands, _ = pkg().host.Deconvolution(n_filters=8).plan(t, (2048, 2048), 0.5, 0.5, psf)
+    obands, _ = orc.Deconvolution(n_filters=8).plan(t, (2048, 2048, 1024), 0.5, 0.5, opsf)
+    b, ob = bands[band_idx], obands[band_idx]
+    yy, xx = np.meshgrid(np.arange(shape[1]), np.arange(shape[0]))
+    img = (1.0 + 0.5 * ((xx // 8 + yy // 8) % 2) + 0.2 * np.sin(xx / 5.0)).astype(F32)
+    ref = np.maximum(orc.richardson_lucy(img, ob.psf, n_iter), 0).astype(F32)
+    u, gain = ctx.richardson_lucy(img, n_iter, b.psf_x_np(), b.psf_y_np(), direct=bool(b.direct), want_gain=True)
+    assert rel_err(u, ref) <= TOL_MAP
+    assert rel_err(gain, np.sqrt(ref / img)) <= TOL_MAP
+    # the dense kernel runs the same iteration
+    if b.kx * b.ky <= 31 * 29 and n_iter <= 60:
+        ud = ctx.richardson_lucy(img, n_iter, dense=ob.psf, direct=bool(b.direct))
+        assert rel_err(ud, ref) <= TOL_MAP
+
+
+@pytest.mark.parametrize("n", [256, 1024, 2048])
+def test_band_energies_match_oracle(ctx, psfs, n):
+    psf, opsf = psfs
+    w, h = 5, 7
+    cube = synthetic_cube(w, h, n, seed=n, noise=0.02)
+    t = time_axis(n)
+    bands, _ = pkg().host.Deconvolution(n_filters=6).plan(t, (64, 64), 0.5, 0.5, psf)
+    obands, _ = orc.Deconvolution(n_filters=6).plan(t, (64, 64, n), 0.5, 0.5, opsf)
+    P = w * h
+    d_cube = ctx.to_device(cube)
+    d_e = ctx.alloc(len(bands) * P * 4)
+    ctx.deconv_energies_dev(d_cube.ptr, P, n, bands, d_e.ptr)
+    e = d_e.download((len(bands), w, h))
+    for i, ob in enumerate(obands):
+        filt = orc.filter_scan(cube, ob.fir)
+        ref = np.sum(filt * filt, axis=2, dtype=F32)
+        assert rel_err(e[i], ref) <= 1e-5, i
+
+
+def test_full_deconvolution_matches_oracle(ctx, psfs):
+    """Deconvolution::filter end to end (FIR bank -> band energies -> RL -> gains -> band sum ->
+    intensity) on a 40x36x512 cube, 6 bands, 40 iterations max."""
+    psf, opsf = psfs
+    w, h, n = 40, 36, 512
+    cube = synthetic_cube(w, h, n, seed=9, noise=0.02)
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w))
+    cube *= (1.0 + 0.5 * ((xx // 6 + yy // 6) % 2)).astype(F32)[:, :, None]
+    t = time_axis(n)
+    dec = pkg().host.Deconvolution(n_filters=6, n_iterations=40)
+    bands, why = dec.plan(t, (w, h), 1.0, 1.0, psf)
+    assert why is None
+    f = orc.frequency_axis(t)
+    s = orc.ScannedImageFilterData(time=t, data=cube, frequency=f, img=orc.intensity_image(cube), dx=1.0, dy=1.0,
+                                   width=w, height=h)
+    ref = orc.Deconvolution(n_filters=6, n_iterations=40).filter(s, opsf)
+    seen = []
+    out, img, rc = ctx.deconvolution(cube, bands, progress=lambda frac, _u: seen.append(frac))
+    assert rc == 0
+    assert rel_err(out, ref.data) <= TOL_MAP
+    assert rel_err(img, ref.img) <= TOL_MAP
+    assert seen and seen[0] == 0.0 and seen[-1] == 1.0 and all(b >= a for a, b in zip(seen, seen[1:]))
+
+
+def test_dead_pixel_gives_nan_only_there(ctx, psfs):
+    """Quirk 10: gain = sqrt(u/d) is NaN where a band's energy is 0; the reference's output is NaN for
+    that pixel only.  Traces are processed in pairs on the GPU: the neighbour must stay finite."""
+    psf, _ = psfs
+    w, h, n = 32, 32, 256
+    cube = synthetic_cube(w, h, n, seed=4, noise=0.02)
+    cube[10, 11, :] = 0.0
+    bands, _ = pkg().host.Deconvolution(n_filters=4, n_iterations=5).plan(time_axis(n), (w, h), 1.0, 1.0, psf)
+    out, img, rc = ctx.deconvolution(cube, bands)
+    assert rc == 0
+    bad = ~np.isfinite(out).all(axis=2)
+    assert bad[10, 11] and bad.sum() == 1
+    assert np.isnan(img[10, 11]) and np.isfinite(np.delete(img.ravel(), 10 * h + 11)).all()
+
+
+def test_abort_flag_stops_the_filter(ctx, psfs):
+    psf, _ = psfs
+    w, h, n = 32, 32, 256
+    cube = synthetic_cube(w, h, n, seed=5)
+    bands, _ = pkg().host.Deconvolution(n_filters=4, n_iterations=500).plan(time_axis(n), (w, h), 1.0, 1.0, psf)
+    flag = ctypes.c_int32(1)
+    out, img, rc = ctx.deconvolution(cube, bands, abort_flag=flag)
+    assert rc == 1   # THZ_ABORTED: the shim keeps the previous slot, like the cancellable loops

@@ -37,6 +37,48 @@ def declared_symbols(header: str = HEADER):
 
 DECLARED_SYMBOLS = declared_symbols() if os.path.exists(HEADER) else []
 
+THZ_MAX_PSF = 255
+THZ_FIR_TAPS = 499
+THZ_MAX_BANDS = 32
+SKIP_REASONS = {2: "no dx/dy", 3: "no psf", 4: "image too small", 5: "psf too large"}
+
+
+class SplineC(C.Structure):
+    _fields_ = [("n", C.c_int), ("knots", C.c_void_p), ("values", C.c_void_p), ("coeff_a", C.c_void_p),
+                ("coeff_b", C.c_void_p), ("coeff_c", C.c_void_p), ("coeff_d", C.c_void_p)]
+
+
+class HybridFitC(C.Structure):
+    _fields_ = [("base_a", C.c_float), ("base_b", C.c_float), ("correction", SplineC)]
+
+
+class PsfC(C.Structure):
+    _fields_ = [("wx_fit", HybridFitC), ("wy_fit", HybridFitC), ("x0_spline", SplineC), ("y0_spline", SplineC)]
+
+
+class DeconvParamsC(C.Structure):
+    _fields_ = [("n_iterations", C.c_int), ("n_filters", C.c_int), ("start_freq", C.c_float),
+                ("end_freq", C.c_float), ("win_width", C.c_float)]
+
+
+class BandPlanC(C.Structure):
+    _fields_ = [("center_freq", C.c_float), ("wx", C.c_float), ("wy", C.c_float), ("x0", C.c_float),
+                ("y0", C.c_float), ("kx", C.c_int), ("ky", C.c_int), ("n_iter", C.c_int), ("direct", C.c_int),
+                ("psf_x", C.c_float * THZ_MAX_PSF), ("psf_y", C.c_float * THZ_MAX_PSF),
+                ("fir", C.c_float * THZ_FIR_TAPS)]
+
+    def psf_x_np(self):
+        return np.ctypeslib.as_array(self.psf_x)[: self.kx].copy()
+
+    def psf_y_np(self):
+        return np.ctypeslib.as_array(self.psf_y)[: self.ky].copy()
+
+    def fir_np(self):
+        return np.ctypeslib.as_array(self.fir).copy()
+
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_float, C.c_void_p)
+
 _lib = None
 
 
@@ -82,6 +124,19 @@ def load_library():
         "thz_band_apply_dev": (i32, [vp, fp, fp, i64]),
         "thz_trace_inverse_dev": (i32, [vp, fp, i32, i32, fp, fp, i64]),
         "thz_spectral_means": (i32, [vp, fp, fp, fp, i64, fp, fp, fp]),
+        "thz_fir_bank": (i32, [i32, C.c_double, C.c_double, C.c_double, f32, f32, fp, fp]),
+        "thz_hybrid_eval": (f32, [C.POINTER(HybridFitC), f32]),
+        "thz_spline_eval_const_extrap": (f32, [C.POINTER(SplineC), f32]),
+        "thz_deconv_plan_bands": (i32, [C.POINTER(PsfC), C.POINTER(DeconvParamsC), fp, i32, i32, i32, i32, f32, f32,
+                                        C.POINTER(BandPlanC)]),
+        "thz_deconv_energies_dev": (i32, [vp, fp, i64, i32, C.POINTER(BandPlanC), i32, fp]),
+        "thz_rl_separable_dev": (i32, [vp, fp, i32, i32, fp, i32, fp, i32, i32, i32, fp, fp, vp, vp, vp, f32, f32]),
+        "thz_rl_dense_dev": (i32, [vp, fp, i32, i32, fp, i32, i32, i32, i32, fp, fp, vp]),
+        "thz_conv2d_separable_dev": (i32, [vp, fp, i32, i32, fp, i32, fp, i32, i32, fp]),
+        "thz_conv2d_dense_dev": (i32, [vp, fp, i32, i32, fp, i32, i32, i32, fp]),
+        "thz_deconv_apply_dev": (i32, [vp, fp, fp, i64, i32, C.POINTER(BandPlanC), i32, fp, fp]),
+        "thz_deconvolution_dev": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
+        "thz_deconvolution_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_trace_fused_host": (i32, [vp, fp, fp, fp, i64]),
         "thz_trace_forward_host": (i32, [vp, fp, fp, fp, fp, fp, i64]),
         "thz_trace_inverse_host": (i32, [vp, fp, i32, i32, fp, fp, i64]),
@@ -300,3 +355,60 @@ class Context:
         self._check(lib.thz_trace_inverse_host(self.handle, fft.ctypes.data, int(use_band), int(use_post),
                                                out.ctypes.data, _ptr(img), P))
         return out, img
+
+    # ------------------------------------------------------------------ deconvolution
+    def deconv_energies_dev(self, d_cube, P, n, bands, d_energy):
+        self._check(lib.thz_deconv_energies_dev(self.handle, d_cube, int(P), int(n), bands, len(bands), d_energy))
+
+    def deconv_apply_dev(self, d_cube, d_gain, P, n, bands, d_out, d_img):
+        self._check(lib.thz_deconv_apply_dev(self.handle, d_cube, d_gain, int(P), int(n), bands, len(bands), d_out,
+                                             d_img))
+
+    def conv2d(self, image, psf_x=None, psf_y=None, dense=None, direct=True):
+        """One 'same' zero-boundary 2-D filtering (test hook of the RL tile kernel)."""
+        image = _f32c(image)
+        rows, cols = image.shape
+        d_in = self.to_device(image)
+        d_out = self.alloc(image.nbytes)
+        if dense is None:
+            px, py = _f32c(psf_x), _f32c(psf_y)
+            self._check(lib.thz_conv2d_separable_dev(self.handle, d_in.ptr, rows, cols, px.ctypes.data, px.size,
+                                                     py.ctypes.data, py.size, int(direct), d_out.ptr))
+        else:
+            k = _f32c(dense)
+            self._check(lib.thz_conv2d_dense_dev(self.handle, d_in.ptr, rows, cols, k.ctypes.data, k.shape[0],
+                                                 k.shape[1], int(direct), d_out.ptr))
+        return d_out.download((rows, cols))
+
+    def richardson_lucy(self, image, n_iter, psf_x=None, psf_y=None, dense=None, direct=True, want_gain=False):
+        """`richardson_lucy` + clamp (+ gain) on a host image."""
+        image = _f32c(image)
+        rows, cols = image.shape
+        d_in = self.to_device(image)
+        d_u = self.alloc(image.nbytes)
+        d_g = self.alloc(image.nbytes) if want_gain else None
+        if dense is None:
+            px, py = _f32c(psf_x), _f32c(psf_y)
+            rc = lib.thz_rl_separable_dev(self.handle, d_in.ptr, rows, cols, px.ctypes.data, px.size, py.ctypes.data,
+                                          py.size, int(direct), int(n_iter), d_u.ptr, d_g.ptr if d_g else None,
+                                          None, None, None, 0.0, 0.0)
+        else:
+            k = _f32c(dense)
+            rc = lib.thz_rl_dense_dev(self.handle, d_in.ptr, rows, cols, k.ctypes.data, k.shape[0], k.shape[1],
+                                      int(direct), int(n_iter), d_u.ptr, d_g.ptr if d_g else None, None)
+        self._check(rc)
+        u = d_u.download((rows, cols))
+        return (u, d_g.download((rows, cols))) if want_gain else u
+
+    def deconvolution(self, cube, bands, abort_flag=None, progress=None):
+        """`Deconvolution::filter` on a host cube [rows][cols][n] -> (out, img, status)."""
+        cube = _f32c(cube)
+        rows, cols, n = cube.shape
+        out = np.empty_like(cube)
+        img = np.empty((rows, cols), np.float32)
+        cb = PROGRESS_FN(progress) if progress is not None else None
+        rc = self._check(lib.thz_deconvolution_host(
+            self.handle, cube.ctypes.data, rows, cols, n, bands, len(bands), out.ctypes.data, img.ctypes.data,
+            C.addressof(abort_flag) if abort_flag is not None else None,
+            C.cast(cb, C.c_void_p) if cb is not None else None, None))
+        return out, img, rc

@@ -1,0 +1,928 @@
+// thz_deconv.cu -- PSF-based frequency-dependent Richardson-Lucy deconvolution on sm_100a.
+//
+// Reference (paths under the upstream repository):
+//   src/filters/deconvolution.rs:266-317, 574-609  convolve1d / filter_scan (FIR per trace)
+//   src/filters/deconvolution.rs:620-712           richardson_lucy
+//   src/filters/deconvolution.rs:432-545           direct_convolve2d / FFT convolve2d
+//   src/filters/deconvolution.rs:963-1012, 1030    band energy, gains, band sum, intensity
+//
+// Restructuring (exact up to f32 rounding):
+//  * The reference materialises one full band cube per FIR band.  Deconvolution is linear
+//    per pixel, out[p] = sum_b g_b[p] (h_b * x[p]) = (sum_b g_b[p] h_b) * x[p], so the cube
+//    is only streamed twice: pass A computes the B band-energy images, pass C applies the
+//    per-pixel combined filter in the frequency domain.
+//  * The FIR is symmetric (linear phase) and the reference keeps samples [249, 249+N) of the
+//    full convolution, i.e. it applies the zero-phase centred filter: its spectrum is real.
+//    A zero-padded transform of M >= N + 249 points makes the circular result identical.
+//  * The PSF is an outer product (src/filters/psf.rs:305-311): each Richardson-Lucy 2-D
+//    filtering is a row pass + a column pass on a TMA-staged tile (zero fill outside the
+//    padded domain comes from the TMA out-of-bounds rule).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "thz_fft.cuh"
+#include "thz_internal.h"
+
+#include <math.h>
+#include <algorithm>
+
+namespace thz {
+
+template <int M> struct DGeo {
+  static constexpr int T = M / kE;
+  static constexpr int NT = (T >= 256) ? T : 256;
+  static constexpr int G = NT / T;
+  static constexpr int kScr = 32 * G;
+  static constexpr size_t smem_bytes = (size_t)G * padded_len(M) * sizeof(float2) + kScr * sizeof(float);
+  static constexpr int kMinBlocks = (NT == 256) ? 2 : 1;
+};
+
+struct FirArgs {
+  const float* x;        // [P][N]
+  int n;                 // samples per trace (<= M - 249)
+  int64_t P;
+  const float* hq;       // [B][M] zero-phase FIR spectra / M in last-stage register order
+  int B;
+  float* energy;         // [B][P]                 (pass A)
+  const float* gain;     // [B][P]                 (pass C)
+  float* out;            // [P][N]                 (pass C)
+  float* img;            // [P] or null            (pass C)
+  const float2* tw;
+};
+
+template <int M>
+__device__ __forceinline__ void dreduce2(float& a, float& b, int t, int g, float* scr) {
+  constexpr int T = DGeo<M>::T;
+  constexpr int W = (T < 32) ? T : 32;
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if constexpr (T > 32) {
+    constexpr int NW = T / 32;
+    float* s = scr + g * 32;   // reuse is separated by the barriers of the next transform
+    if ((t & 31) == 0) {
+      s[2 * (t >> 5)] = a;
+      s[2 * (t >> 5) + 1] = b;
+    }
+    __syncthreads();
+    if (t == 0) {
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        sa += s[2 * w];
+        sb += s[2 * w + 1];
+      }
+      a = sa;
+      b = sb;
+    }
+  }
+}
+
+template <int M>
+__device__ __forceinline__ void load_padded_pair(float2 (&v)[kE], const FirArgs& a, int t, bool act0, bool act1,
+                                                 int64_t p0) {
+  constexpr int T = DGeo<M>::T;
+  const float* r0 = a.x + p0 * a.n;
+  const float* r1 = r0 + a.n;
+#pragma unroll
+  for (int i = 0; i < kE; ++i) {
+    const int e = t + i * T;
+    const bool in = e < a.n;
+    v[i].x = (act0 && in) ? __ldcs(r0 + e) : 0.f;
+    v[i].y = (act1 && in) ? __ldcs(r1 + e) : 0.f;
+  }
+}
+
+// ---- pass A: band energies ------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_energy(const FirArgs a) {
+  using GEO = DGeo<M>;
+  constexpr int T = GEO::T, G = GEO::G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(M));
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(M);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<M>::ns - 1;
+  constexpr int RL = Plan<M>::r[LAST];
+  constexpr int UL = kE / RL;
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t p0 = (item * G + g) * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    float2 z[kE];
+    load_padded_pair<M>(z, a, t, act0, act1, p0);
+    fft_forward<M>(z, t, sm, a.tw);
+    for (int b = 0; b < a.B; ++b) {
+      const float* hq = a.hq + (size_t)b * M;
+      float2 w[kE];
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        const int u = i % UL, m = i / UL;
+        const float h = __ldg(hq + m * (M / RL) + t + u * T);
+        w[i] = make_float2(z[i].x * h, z[i].y * h);
+      }
+      fft_inverse<M>(w, t, sm, a.tw);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        if (t + i * T < a.n) {
+          s0 = fmaf(w[i].x, w[i].x, s0);
+          s1 = fmaf(w[i].y, w[i].y, s1);
+        }
+      }
+      dreduce2<M>(s0, s1, t, g, scr);
+      if (t == 0) {
+        if (act0) a.energy[(size_t)b * a.P + p0] = s0;
+        if (act1) a.energy[(size_t)b * a.P + p0 + 1] = s1;
+      }
+    }
+  }
+}
+
+// ---- pass C: per-pixel combined filter sum_b g_b[p] h_b ------------------------------------
+template <int M>
+__global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_apply(const FirArgs a) {
+  using GEO = DGeo<M>;
+  constexpr int T = GEO::T, G = GEO::G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(M));
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(M);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<M>::ns - 1;
+  constexpr int RL = Plan<M>::r[LAST];
+  constexpr int UL = kE / RL;
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t p0 = (item * G + g) * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    float2 z[kE];
+    load_padded_pair<M>(z, a, t, act0, act1, p0);
+    fft_forward<M>(z, t, sm, a.tw);
+    // natural-order copy so that every thread can fetch the mirror bin Z[M - k]
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<M>(stage_elem<M, LAST>(t, i)))] = z[i];
+    __syncthreads();
+    // S = (G0 + G1) / 2, D = (G0 - G1) / 2 with G_r[k] = sum_b gain[b][p_r] H_b[k] / M
+    float sacc[kE], dacc[kE];
+#pragma unroll
+    for (int i = 0; i < kE; ++i) sacc[i] = dacc[i] = 0.f;
+    bool bad0 = false, bad1 = false;   // non-finite gain: the reference's output trace is NaN (quirk 10)
+    for (int b = 0; b < a.B; ++b) {
+      float g0 = act0 ? __ldg(a.gain + (size_t)b * a.P + p0) : 0.f;
+      float g1 = act1 ? __ldg(a.gain + (size_t)b * a.P + p0 + 1) : 0.f;
+      if (!(fabsf(g0) <= 3.0e38f)) { bad0 = true; g0 = 0.f; }
+      if (!(fabsf(g1) <= 3.0e38f)) { bad1 = true; g1 = 0.f; }
+      const float gs = 0.5f * (g0 + g1), gd = 0.5f * (g0 - g1);
+      const float* hq = a.hq + (size_t)b * M;
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        const int u = i % UL, m = i / UL;
+        const float h = __ldg(hq + m * (M / RL) + t + u * T);
+        sacc[i] = fmaf(gs, h, sacc[i]);
+        dacc[i] = fmaf(gd, h, dacc[i]);
+      }
+    }
+    // Y[k] = S Z[k] + D conj(Z[M-k])
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      const int k = pos_to_bin<M>(stage_elem<M, LAST>(t, i));
+      const float2 zp = sm[pad_idx((M - k) & (M - 1))];
+      z[i] = make_float2(fmaf(sacc[i], z[i].x, dacc[i] * zp.x), fmaf(sacc[i], z[i].y, -dacc[i] * zp.y));
+    }
+    fft_inverse<M>(z, t, sm, a.tw);
+    const float kNaN = __int_as_float(0x7fc00000);
+    float* r0 = a.out + p0 * a.n;
+    float* r1 = r0 + a.n;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      const int e = t + i * T;
+      if (e < a.n) {
+        const float y0 = bad0 ? kNaN : z[i].x, y1 = bad1 ? kNaN : z[i].y;
+        if (act0) __stcs(r0 + e, y0);
+        if (act1) __stcs(r1 + e, y1);
+        s0 = fmaf(y0, y0, s0);
+        s1 = fmaf(y1, y1, s1);
+      }
+    }
+    if (a.img != nullptr) {
+      dreduce2<M>(s0, s1, t, g, scr);
+      if (t == 0) {
+        if (act0) a.img[p0] = s0;
+        if (act1) a.img[p0 + 1] = s1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Richardson-Lucy: TMA-staged tiled 2-D filtering
+// ------------------------------------------------------------------------------------
+constexpr int kTH = 64, kTW = 64;          // output tile
+constexpr int kMidStride = 68;             // 4 * odd -> conflict-free 128-bit rows
+constexpr int kMaxTaps = 256;              // padded taps per axis
+
+struct ConvArgs {
+  int Hp, Wp, pitch;      // padded-domain image [Hp][pitch], valid width Wp
+  int kx, ky;             // taps along rows (axis 0) and columns (axis 1), both odd
+  int kxp, kyp;           // taps padded to a multiple of 8
+  int box_rows, box_cols; // TMA box: kTH + kx - 1 rows, >= kTW + kyp - 1 columns (4 * odd)
+  const float* wx;        // [kxp] row-direction taps (correlation order), zero padded
+  const float* wy;        // [kyp]
+  const float* wdense;    // [kx][kyp] dense taps (dense kernel) or null
+  const float* d;         // mode 1: relative blur numerator (padded image)
+  float* out;             // mode 0: conv result; mode 1: r = d / (conv + eps); mode 2: u *= conv (in place)
+  float eps;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(mbar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(mbar)
+      : "memory");
+}
+
+// correlation: out[i][j] = sum_m sum_n in[i + m - kx/2][j + n - ky/2] * wx[m] * wy[n]
+// MODE 0: out = c;  MODE 1: out = d / (c + eps);  MODE 2: out *= c
+template <int MODE, bool DENSE>
+__global__ void __launch_bounds__(256, 2) k_rl_conv(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);                       // [box_rows][box_cols]
+  const int tile_floats = a.box_rows * a.box_cols;
+  float* mid = tile + ((tile_floats + 31) & ~31);                         // [box_rows][kMidStride]
+  float* wxs = mid + (DENSE ? 0 : a.box_rows * kMidStride);
+  float* wys = wxs + (DENSE ? 0 : a.kxp);                                 // separable: [kxp] then [kyp]
+  __shared__ __align__(8) uint64_t mbar_storage;
+  const uint32_t mbar = smem_u32(&mbar_storage);
+  const int row0 = blockIdx.y * kTH, col0 = blockIdx.x * kTW;
+
+  if (threadIdx.x == 0) mbar_init(mbar, 1);
+  if constexpr (DENSE) {
+    for (int i = threadIdx.x; i < a.kx * a.kyp; i += blockDim.x) wxs[i] = a.wdense[i];
+  } else {
+    for (int i = threadIdx.x; i < a.kxp; i += blockDim.x) wxs[i] = a.wx[i];
+    for (int i = threadIdx.x; i < a.kyp; i += blockDim.x) wys[i] = a.wy[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(mbar, (uint32_t)(tile_floats * sizeof(float)));
+    tma_load_2d(smem_u32(tile), &tmap, col0 - a.ky / 2, row0 - a.kx / 2, mbar);
+  }
+  while (!mbar_try_wait(mbar, 0)) {
+  }
+
+  const int bc = a.box_cols;
+  if constexpr (!DENSE) {
+    // pass 1: filter along columns (axis 1).  item = (tile row r, group of 8 output columns)
+    const int nitems = a.box_rows * (kTW / 8);
+    for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
+      const int r = it % a.box_rows, cg = it / a.box_rows;
+      const float* src = tile + r * bc + cg * 8;
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+      float win[16];
+      {
+        const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+        win[0] = v0.x; win[1] = v0.y; win[2] = v0.z; win[3] = v0.w;
+        win[4] = v1.x; win[5] = v1.y; win[6] = v1.z; win[7] = v1.w;
+      }
+      for (int nb = 0; nb < a.kyp; nb += 8) {
+        const float4 v0 = *reinterpret_cast<const float4*>(src + nb + 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + nb + 12);
+        win[8] = v0.x; win[9] = v0.y; win[10] = v0.z; win[11] = v0.w;
+        win[12] = v1.x; win[13] = v1.y; win[14] = v1.z; win[15] = v1.w;
+        const float4 w0 = *reinterpret_cast<const float4*>(wys + nb), w1 = *reinterpret_cast<const float4*>(wys + nb + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[n], win[q + n], acc[q]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) win[q] = win[q + 8];
+      }
+      float* dst = mid + r * kMidStride + cg * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+  }
+  // pass 2: filter along rows (axis 0).  item = (output column c, group of 8 output rows)
+  {
+    const int nitems = kTW * (kTH / 8);
+    for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
+      const int c = it % kTW, rg = it / kTW;
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+      if constexpr (!DENSE) {
+        const float* src = mid + (rg * 8) * kMidStride + c;
+        float win[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) win[q] = src[q * kMidStride];
+        for (int mb = 0; mb < a.kxp; mb += 8) {
+          // rows beyond the box are multiplied by zero taps; clamp the address instead of reading them
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int rr = rg * 8 + mb + 8 + q;
+            win[8 + q] = (rr < a.box_rows) ? mid[rr * kMidStride + c] : 0.f;
+          }
+          const float4 w0 = *reinterpret_cast<const float4*>(wxs + mb), w1 = *reinterpret_cast<const float4*>(wxs + mb + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[n], win[q + n], acc[q]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) win[q] = win[q + 8];
+        }
+      } else {
+        // dense taps: out[r][c] = sum_m sum_n tile[r + m][c + n] w[m][n]; 8 consecutive rows per item,
+        // tap rows outermost so that one tap value serves 8 accumulators
+        for (int m = 0; m < a.kx + 7; ++m) {
+          // input row rg*8 + m contributes to output row q with tap row m - q
+          const float* srow = tile + (rg * 8 + m) * bc + c;
+          if (rg * 8 + m >= a.box_rows) break;
+          for (int n = 0; n < a.ky; ++n) {
+            const float v = srow[n];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int mq = m - q;
+              if (mq >= 0 && mq < a.kx) acc[q] = fmaf(v, wxs[mq * a.kyp + n], acc[q]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int gr = row0 + rg * 8 + q, gc = col0 + c;
+        if (gr < a.Hp && gc < a.Wp) {
+          const size_t o = (size_t)gr * a.pitch + gc;
+          if constexpr (MODE == 0) a.out[o] = acc[q];
+          else if constexpr (MODE == 1) a.out[o] = a.d[o] / (acc[q] + a.eps);
+          else a.out[o] = a.out[o] * acc[q];
+        }
+      }
+    }
+  }
+}
+
+// numpy-"reflect" padding exactly as richardson_lucy writes it (deconvolution.rs:638-667)
+__global__ void k_reflect_pad(const float* __restrict__ img, int h, int w, int pad_y, int pad_x, float* __restrict__ out,
+                              int pitch) {
+  const int Hp = h + 2 * pad_y, Wp = w + 2 * pad_x;
+  const int64_t total = (int64_t)Hp * Wp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / Wp), c = (int)(i % Wp);
+    int sr, sc;
+    if (r < pad_y) sr = pad_y - r;
+    else if (r >= pad_y + h) sr = h - 2 - (r - pad_y - h);
+    else sr = r - pad_y;
+    if (c < pad_x) sc = pad_x - c;
+    else if (c >= pad_x + w) sc = w - 2 - (c - pad_x - w);
+    else sc = c - pad_x;
+    out[(size_t)r * pitch + c] = img[(size_t)sr * w + sc];
+  }
+}
+
+// crop, clamp >= 0, gain = sqrt(u / d)  (deconvolution.rs:708, 975, 990-993)
+__global__ void k_rl_finish(const float* __restrict__ u, int pitch, int pad_y, int pad_x, int h, int w,
+                            const float* __restrict__ d_img, float* __restrict__ deconv, float* __restrict__ gain) {
+  const int64_t total = (int64_t)h * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / w), c = (int)(i % w);
+    const float v = fmaxf(u[(size_t)(r + pad_y) * pitch + c + pad_x], 0.0f);
+    if (deconv) deconv[i] = v;
+    if (gain) gain[i] = sqrtf(v / d_img[i]);
+  }
+}
+
+__global__ void k_copy2d(const float* __restrict__ src, int rows, int cols, int spitch, float* __restrict__ dst,
+                         int dpitch) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    dst[(size_t)r * dpitch + c] = src[(size_t)r * spitch + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+static int fir_fft_size(int n) {
+  int m = 64;
+  while (m < n + (THZ_FIR_TAPS - 1) / 2) m <<= 1;   // circular result exact for M >= N + 249
+  return m;
+}
+
+template <int M> static void host_plan_m(int& ns, int (&r)[4]) {
+  ns = Plan<M>::ns;
+  for (int i = 0; i < 4; ++i) r[i] = Plan<M>::r[i];
+}
+static bool plan_of_m(int m, int& ns, int (&r)[4]) {
+  switch (m) {
+    case 64: host_plan_m<64>(ns, r); return true;
+    case 128: host_plan_m<128>(ns, r); return true;
+    case 256: host_plan_m<256>(ns, r); return true;
+    case 512: host_plan_m<512>(ns, r); return true;
+    case 1024: host_plan_m<1024>(ns, r); return true;
+    case 2048: host_plan_m<2048>(ns, r); return true;
+    case 4096: host_plan_m<4096>(ns, r); return true;
+    case 8192: host_plan_m<8192>(ns, r); return true;
+    default: return false;
+  }
+}
+
+// zero-phase spectrum of the centred FIR at M points, / M, in last-stage register order
+static int build_fir_hq(int m, const float* fir, std::vector<float>& hq) {
+  int ns, r[4];
+  if (!plan_of_m(m, ns, r)) return THZ_EINVAL;
+  const int taps = THZ_FIR_TAPS, half = (taps - 1) / 2;
+  std::vector<double> H(m / 2 + 1), ctab(m);
+  for (int i = 0; i < m; ++i) ctab[i] = cos(2.0 * M_PI * (double)i / (double)m);
+  for (int k = 0; k <= m / 2; ++k) {
+    double acc = (double)fir[half];
+    for (int j = 1; j <= half; ++j) {
+      // taps are symmetric up to f32 rounding; use both sides so that the real part is exact
+      acc += ((double)fir[half + j] + (double)fir[half - j]) * ctab[(int)(((long)j * k) & (m - 1))];
+    }
+    H[k] = acc;
+  }
+  const int RLs = r[ns - 1];
+  hq.assign(m, 0.f);
+  for (int beta = 0; beta < m / RLs; ++beta)
+    for (int mm = 0; mm < RLs; ++mm) {
+      int p = beta * RLs + mm, k = 0, w = 1, L = m;
+      for (int s = 0; s < ns; ++s) {
+        const int S = L / r[s];
+        const int q = p / S;
+        p -= q * S;
+        k += q * w;
+        w *= r[s];
+        L = S;
+      }
+      const int kk = (k <= m / 2) ? k : m - k;
+      hq[(size_t)mm * (m / RLs) + beta] = (float)(H[kk] / (double)m);
+    }
+  return THZ_OK;
+}
+
+struct FirTables {
+  int m = 0, B = 0;
+  float* d_hq = nullptr;
+};
+
+static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_plan* bands, int B, FirTables& ft) {
+  const int m = fir_fft_size(n);
+  int ns, r[4];
+  if (!plan_of_m(m, ns, r)) return set_err(c, THZ_EINVAL, "trace too long for the FIR transform (n + 249 must be <= 8192)");
+  std::vector<float> all((size_t)B * m), one;
+  for (int b = 0; b < B; ++b) {
+    if (build_fir_hq(m, bands[b].fir, one) != THZ_OK) return set_err(c, THZ_EINVAL, "bad FIR transform size");
+    std::copy(one.begin(), one.end(), all.begin() + (size_t)b * m);
+  }
+  THZ_CUDA(c, cudaMalloc((void**)&ft.d_hq, all.size() * sizeof(float)));
+  THZ_CUDA(c, cudaMemcpyAsync(ft.d_hq, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  THZ_CUDA(c, cudaStreamSynchronize(s));
+  ft.m = m;
+  ft.B = B;
+  return THZ_OK;
+}
+
+template <int M, typename K>
+static int launch_fir(thz_ctx* c, cudaStream_t s, K kernel, const FirArgs& a) {
+  using GEO = DGeo<M>;
+  const size_t smem = GEO::smem_bytes;
+  const void* key = (const void*)kernel;
+  auto it = c->occ.find(key);
+  if (it == c->occ.end()) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(smem)");
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, GEO::NT, smem);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (nb < 1) return set_err(c, THZ_ECUDA, "FIR kernel does not fit on an SM");
+    it = c->occ.emplace(key, nb).first;
+  }
+  const int64_t npairs = (a.P + 1) / 2;
+  const int64_t nitems = (npairs + GEO::G - 1) / GEO::G;
+  if (nitems <= 0) return THZ_OK;
+  int64_t grid = (int64_t)c->sm_count * it->second;
+  if (grid > nitems) grid = nitems;
+  kernel<<<(unsigned)grid, GEO::NT, smem, s>>>(a);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "FIR kernel launch");
+  return THZ_OK;
+}
+
+template <int M> static int do_energy(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
+  return launch_fir<M>(c, s, k_fir_energy<M>, a);
+}
+template <int M> static int do_apply(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
+  return launch_fir<M>(c, s, k_fir_apply<M>, a);
+}
+
+#define THZ_DISPATCH_M(m, FN, ...)                 \
+  switch (m) {                                     \
+    case 64: return FN<64>(__VA_ARGS__);           \
+    case 128: return FN<128>(__VA_ARGS__);         \
+    case 256: return FN<256>(__VA_ARGS__);         \
+    case 512: return FN<512>(__VA_ARGS__);         \
+    case 1024: return FN<1024>(__VA_ARGS__);       \
+    case 2048: return FN<2048>(__VA_ARGS__);       \
+    case 4096: return FN<4096>(__VA_ARGS__);       \
+    case 8192: return FN<8192>(__VA_ARGS__);       \
+    default: return THZ_EINVAL;                    \
+  }
+
+static int dispatch_energy(thz_ctx* c, cudaStream_t s, int m, const FirArgs& a) { THZ_DISPATCH_M(m, do_energy, c, s, a); }
+static int dispatch_apply(thz_ctx* c, cudaStream_t s, int m, const FirArgs& a) { THZ_DISPATCH_M(m, do_apply, c, s, a); }
+
+int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
+                    int B, float* d_energy) {
+  if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
+  if (P == 0) return THZ_OK;
+  if (!d_cube || !d_energy || n < 2) return set_err(c, THZ_EINVAL, "null pointer");
+  FirTables ft;
+  int rc = upload_fir_tables(c, s, n, bands, B, ft);
+  if (rc != THZ_OK) return rc;
+  const FftTables* tb = nullptr;
+  rc = get_tables(c, ft.m, &tb);
+  if (rc == THZ_OK) {
+    FirArgs a{};
+    a.x = d_cube; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.energy = d_energy; a.tw = tb->d_tw;
+    rc = dispatch_energy(c, s, ft.m, a);
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(ft.d_hq);
+  return rc;
+}
+
+int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d_gain, int64_t P, int n,
+                 const thz_band_plan* bands, int B, float* d_out, float* d_img) {
+  if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
+  if (P == 0) return THZ_OK;
+  if (!d_cube || !d_gain || !d_out || n < 2) return set_err(c, THZ_EINVAL, "null pointer");
+  FirTables ft;
+  int rc = upload_fir_tables(c, s, n, bands, B, ft);
+  if (rc != THZ_OK) return rc;
+  const FftTables* tb = nullptr;
+  rc = get_tables(c, ft.m, &tb);
+  if (rc == THZ_OK) {
+    FirArgs a{};
+    a.x = d_cube; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.gain = d_gain; a.out = d_out; a.img = d_img;
+    a.tw = tb->d_tw;
+    rc = dispatch_apply(c, s, ft.m, a);
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(ft.d_hq);
+  return rc;
+}
+
+// ---- TMA descriptor -----------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode(thz_ctx* c) {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    set_err(c, THZ_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    return nullptr;
+  }
+  fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  return fn;
+}
+
+static int make_tmap(thz_ctx* c, CUtensorMap* map, const float* base, int Hp, int Wp, int pitch, int box_rows,
+                     int box_cols) {
+  auto enc = get_encode(c);
+  if (!enc) return THZ_ECUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)Wp, (cuuint64_t)Hp};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return set_err(c, THZ_ECUDA, buf);
+  }
+  return THZ_OK;
+}
+
+struct ConvPlan {
+  ConvArgs a{};
+  size_t smem = 0;
+  bool dense = false;
+  float* d_w = nullptr;   // device taps: [wx (kxp) | wy (kyp)] x 2 orientations, or dense [2][kx][kyp]
+  int wstride = 0;        // floats between the two orientations
+};
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// taps for conv #1 (u (*) psf) and conv #2 (r (*) mirror) as correlation taps
+static int make_conv_plan(thz_ctx* c, cudaStream_t s, int Hp, int Wp, int pitch, const float* psf_x, int kx,
+                          const float* psf_y, int ky, const float* dense, int direct, ConvPlan& cp) {
+  if (kx < 1 || ky < 1 || (kx & 1) == 0 || (ky & 1) == 0) return set_err(c, THZ_EINVAL, "PSF extents must be odd");
+  if (kx > THZ_MAX_PSF || ky > THZ_MAX_PSF) return set_err(c, THZ_EINVAL, "PSF larger than THZ_MAX_PSF");
+  ConvArgs& a = cp.a;
+  a.Hp = Hp; a.Wp = Wp; a.pitch = pitch; a.kx = kx; a.ky = ky;
+  a.kxp = round_up(kx, 8);
+  a.kyp = round_up(ky, 8);
+  a.box_rows = kTH + kx - 1;
+  int bc = kTW + a.kyp + 8;             // pass 1 reads up to column cg*8 + kyp + 15
+  bc = round_up(bc, 4);
+  if (((bc / 4) & 1) == 0) bc += 4;     // 4 * odd: conflict-free 128-bit row accesses
+  a.box_cols = bc;
+  a.eps = 1e-12f;
+  cp.dense = dense != nullptr;
+  if (a.box_rows > 256 || a.box_cols > 256) return set_err(c, THZ_EINVAL, "PSF too large for one TMA box");
+  const int tile_floats = (a.box_rows * a.box_cols + 31) & ~31;
+  std::vector<float> w;
+  if (!cp.dense) {
+    cp.smem = (size_t)(tile_floats + a.box_rows * kMidStride + a.kxp + a.kyp) * sizeof(float);
+    cp.wstride = a.kxp + a.kyp;
+    w.assign(2 * cp.wstride, 0.f);
+    // orientation 0 = first conv of the iteration (u with psf), 1 = second (r with the mirrored psf).
+    // direct branch: correlation with the given kernel; FFT branch: convolution = correlation with the flip.
+    for (int o = 0; o < 2; ++o) {
+      const bool flip = (o == 0) ? (direct == 0) : (direct != 0);
+      for (int i = 0; i < kx; ++i) w[o * cp.wstride + i] = psf_x[flip ? kx - 1 - i : i];
+      for (int j = 0; j < ky; ++j) w[o * cp.wstride + a.kxp + j] = psf_y[flip ? ky - 1 - j : j];
+    }
+  } else {
+    cp.smem = (size_t)(tile_floats + kx * a.kyp) * sizeof(float);
+    cp.wstride = kx * a.kyp;
+    w.assign(2 * cp.wstride, 0.f);
+    for (int o = 0; o < 2; ++o) {
+      const bool flip = (o == 0) ? (direct == 0) : (direct != 0);
+      for (int i = 0; i < kx; ++i)
+        for (int j = 0; j < ky; ++j)
+          w[o * cp.wstride + i * a.kyp + j] = dense[(flip ? kx - 1 - i : i) * ky + (flip ? ky - 1 - j : j)];
+    }
+  }
+  if (cp.smem > 227 * 1024) return set_err(c, THZ_EINVAL, "PSF too large for the shared-memory tile");
+  THZ_CUDA(c, cudaMalloc((void**)&cp.d_w, w.size() * sizeof(float)));
+  THZ_CUDA(c, cudaMemcpyAsync(cp.d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  THZ_CUDA(c, cudaStreamSynchronize(s));
+  return THZ_OK;
+}
+
+template <int MODE>
+static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUtensorMap& map, int orient,
+                       const float* d, float* out) {
+  ConvArgs a = cp.a;
+  if (cp.dense) {
+    a.wdense = cp.d_w + (size_t)orient * cp.wstride;
+  } else {
+    a.wx = cp.d_w + (size_t)orient * cp.wstride;
+    a.wy = a.wx + a.kxp;
+  }
+  a.d = d;
+  a.out = out;
+  dim3 grid((a.Wp + kTW - 1) / kTW, (a.Hp + kTH - 1) / kTH);
+  cudaError_t e;
+  if (cp.dense) {
+    e = cudaFuncSetAttribute(k_rl_conv<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl dense)");
+    k_rl_conv<MODE, true><<<grid, 256, cp.smem, s>>>(map, a);
+  } else {
+    e = cudaFuncSetAttribute(k_rl_conv<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl)");
+    k_rl_conv<MODE, false><<<grid, 256, cp.smem, s>>>(map, a);
+  }
+  c->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_conv launch");
+  return THZ_OK;
+}
+
+static int grid_for(thz_ctx* c, int64_t total) {
+  int64_t b = (total + 255) / 256;
+  const int64_t cap = (int64_t)c->sm_count * 8;
+  return (int)std::max<int64_t>(1, std::min(b, cap));
+}
+
+int conv2d_once(thz_ctx* c, cudaStream_t s, const float* d_in, int rows, int cols, const float* psf_x, int kx,
+                const float* psf_y, int ky, const float* dense, int direct, float* d_out) {
+  if (!d_in || !d_out || rows < 1 || cols < 1) return set_err(c, THZ_EINVAL, "bad image");
+  const int pitch = round_up(cols, 4);
+  float *d_a = nullptr, *d_b = nullptr;
+  THZ_CUDA(c, cudaMalloc((void**)&d_a, (size_t)rows * pitch * sizeof(float)));
+  THZ_CUDA(c, cudaMalloc((void**)&d_b, (size_t)rows * pitch * sizeof(float)));
+  k_copy2d<<<grid_for(c, (int64_t)rows * cols), 256, 0, s>>>(d_in, rows, cols, cols, d_a, pitch);
+  c->launches++;
+  ConvPlan cp;
+  int rc = make_conv_plan(c, s, rows, cols, pitch, psf_x, kx, psf_y, ky, dense, direct ? 1 : 0, cp);
+  CUtensorMap map;
+  if (rc == THZ_OK) rc = make_tmap(c, &map, d_a, rows, cols, pitch, cp.a.box_rows, cp.a.box_cols);
+  // orientation 0 is "the kernel as given": correlation when direct, convolution otherwise
+  if (rc == THZ_OK) rc = launch_conv<0>(c, s, cp, map, 0, nullptr, d_b);
+  if (rc == THZ_OK) {
+    k_copy2d<<<grid_for(c, (int64_t)rows * cols), 256, 0, s>>>(d_b, rows, cols, pitch, d_out, cols);
+    c->launches++;
+  }
+  cudaStreamSynchronize(s);
+  cudaError_t e = cudaGetLastError();
+  cudaFree(d_a);
+  cudaFree(d_b);
+  if (cp.d_w) cudaFree(cp.d_w);
+  if (rc == THZ_OK && e != cudaSuccess) return cuda_fail(c, e, "conv2d");
+  return rc;
+}
+
+int richardson_lucy(thz_ctx* c, cudaStream_t s, const float* d_image, int rows, int cols, const float* psf_x, int kx,
+                    const float* psf_y, int ky, const float* dense, int direct, int n_iter, float* d_deconv,
+                    float* d_gain, const volatile int32_t* abort_flag, thz_progress_fn progress, void* puser,
+                    float pbase, float pspan) {
+  if (!d_image || rows < 2 || cols < 2) return set_err(c, THZ_EINVAL, "bad image");
+  const int pad_y = kx / 2, pad_x = ky / 2;   // psf.nrows()/2 pads axis 0 (deconvolution.rs:629-631)
+  if (pad_y >= rows - 1 || pad_x >= cols - 1) return set_err(c, THZ_EINVAL, "PSF larger than the image");
+  const int Hp = rows + 2 * pad_y, Wp = cols + 2 * pad_x, pitch = round_up(Wp, 4);
+  const size_t img_bytes = (size_t)Hp * pitch * sizeof(float);
+  float *d_d = nullptr, *d_u = nullptr, *d_r = nullptr;
+  THZ_CUDA(c, cudaMalloc((void**)&d_d, img_bytes));
+  THZ_CUDA(c, cudaMalloc((void**)&d_u, img_bytes));
+  THZ_CUDA(c, cudaMalloc((void**)&d_r, img_bytes));
+  THZ_CUDA(c, cudaMemsetAsync(d_d, 0, img_bytes, s));
+  k_reflect_pad<<<grid_for(c, (int64_t)Hp * Wp), 256, 0, s>>>(d_image, rows, cols, pad_y, pad_x, d_d, pitch);
+  c->launches++;
+  THZ_CUDA(c, cudaMemcpyAsync(d_u, d_d, img_bytes, cudaMemcpyDeviceToDevice, s));
+  THZ_CUDA(c, cudaMemsetAsync(d_r, 0, img_bytes, s));
+  ConvPlan cp;
+  int rc = make_conv_plan(c, s, Hp, Wp, pitch, psf_x, kx, psf_y, ky, dense, direct ? 1 : 0, cp);
+  CUtensorMap map_u, map_r;
+  if (rc == THZ_OK) rc = make_tmap(c, &map_u, d_u, Hp, Wp, pitch, cp.a.box_rows, cp.a.box_cols);
+  if (rc == THZ_OK) rc = make_tmap(c, &map_r, d_r, Hp, Wp, pitch, cp.a.box_rows, cp.a.box_cols);
+  bool aborted = false;
+  for (int it = 0; rc == THZ_OK && it < n_iter; ++it) {
+    rc = launch_conv<1>(c, s, cp, map_u, 0, d_d, d_r);          // r = d / (u (*) psf + eps)
+    if (rc == THZ_OK) rc = launch_conv<2>(c, s, cp, map_r, 1, nullptr, d_u);   // u *= r (*) mirror
+    if ((it & 15) == 15 || it == n_iter - 1) {
+      if (abort_flag && *abort_flag) { aborted = true; break; }
+      if (progress || abort_flag) {
+        cudaError_t e = cudaStreamSynchronize(s);   // keep the queue short so that abort is responsive
+        if (e != cudaSuccess) { rc = cuda_fail(c, e, "richardson_lucy"); break; }
+        if (progress) progress(pbase + pspan * (float)(it + 1) / (float)n_iter, puser);
+      }
+    }
+  }
+  if (rc == THZ_OK && !aborted) {
+    k_rl_finish<<<grid_for(c, (int64_t)rows * cols), 256, 0, s>>>(d_u, pitch, pad_y, pad_x, rows, cols, d_image,
+                                                                  d_deconv, d_gain);
+    c->launches++;
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(d_d);
+  cudaFree(d_u);
+  cudaFree(d_r);
+  if (cp.d_w) cudaFree(cp.d_w);
+  if (rc == THZ_OK && e != cudaSuccess) return cuda_fail(c, e, "richardson_lucy");
+  if (rc == THZ_OK && aborted) return THZ_ABORTED;
+  return rc;
+}
+
+}  // namespace thz
+
+using namespace thz;
+
+#define CHECK_CTX(c)                                                   \
+  do {                                                                 \
+    if (!(c)) return THZ_EINVAL;                                       \
+    cudaError_t e_ = cudaSetDevice((c)->device);                       \
+    if (e_ != cudaSuccess) return cuda_fail((c), e_, "cudaSetDevice"); \
+  } while (0)
+
+extern "C" {
+
+int thz_deconv_energies_dev(thz_ctx* c, const float* d_cube, int64_t P, int n, const thz_band_plan* bands, int n_bands,
+                            float* d_energy) {
+  CHECK_CTX(c);
+  return deconv_energies(c, c->stream, d_cube, P, n, bands, n_bands, d_energy);
+}
+
+int thz_deconv_apply_dev(thz_ctx* c, const float* d_cube, const float* d_gain, int64_t P, int n,
+                         const thz_band_plan* bands, int n_bands, float* d_out, float* d_img) {
+  CHECK_CTX(c);
+  return deconv_apply(c, c->stream, d_cube, d_gain, P, n, bands, n_bands, d_out, d_img);
+}
+
+int thz_rl_separable_dev(thz_ctx* c, const float* d_image, int rows, int cols, const float* psf_x, int kx,
+                         const float* psf_y, int ky, int direct, int n_iter, float* d_deconvolved, float* d_gain,
+                         const volatile int32_t* abort_flag, thz_progress_fn progress, void* progress_user,
+                         float progress_base, float progress_span) {
+  CHECK_CTX(c);
+  if (!psf_x || !psf_y) return set_err(c, THZ_EINVAL, "null PSF");
+  return richardson_lucy(c, c->stream, d_image, rows, cols, psf_x, kx, psf_y, ky, nullptr, direct, n_iter,
+                         d_deconvolved, d_gain, abort_flag, progress, progress_user, progress_base, progress_span);
+}
+
+int thz_rl_dense_dev(thz_ctx* c, const float* d_image, int rows, int cols, const float* psf, int kx, int ky, int direct,
+                     int n_iter, float* d_deconvolved, float* d_gain, const volatile int32_t* abort_flag) {
+  CHECK_CTX(c);
+  if (!psf) return set_err(c, THZ_EINVAL, "null PSF");
+  return richardson_lucy(c, c->stream, d_image, rows, cols, nullptr, kx, nullptr, ky, psf, direct, n_iter,
+                         d_deconvolved, d_gain, abort_flag, nullptr, nullptr, 0.f, 0.f);
+}
+
+int thz_conv2d_separable_dev(thz_ctx* c, const float* d_in, int rows, int cols, const float* psf_x, int kx,
+                             const float* psf_y, int ky, int direct, float* d_out) {
+  CHECK_CTX(c);
+  if (!psf_x || !psf_y) return set_err(c, THZ_EINVAL, "null PSF");
+  return conv2d_once(c, c->stream, d_in, rows, cols, psf_x, kx, psf_y, ky, nullptr, direct, d_out);
+}
+
+int thz_conv2d_dense_dev(thz_ctx* c, const float* d_in, int rows, int cols, const float* psf, int kx, int ky,
+                         int direct, float* d_out) {
+  CHECK_CTX(c);
+  if (!psf) return set_err(c, THZ_EINVAL, "null PSF");
+  return conv2d_once(c, c->stream, d_in, rows, cols, nullptr, kx, nullptr, ky, psf, direct, d_out);
+}
+
+int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, int n, const thz_band_plan* bands,
+                          int n_bands, float* d_out, float* d_img, const volatile int32_t* abort_flag,
+                          thz_progress_fn progress, void* progress_user) {
+  CHECK_CTX(c);
+  if (!bands || n_bands < 1 || n_bands > THZ_MAX_BANDS) return set_err(c, THZ_EINVAL, "bad band count");
+  const int64_t P = (int64_t)rows * cols;
+  if (P == 0) return THZ_OK;
+  if (progress) progress(0.0f, progress_user);
+  float *d_energy = nullptr, *d_gain = nullptr;
+  THZ_CUDA(c, cudaMalloc((void**)&d_energy, (size_t)n_bands * P * sizeof(float)));
+  THZ_CUDA(c, cudaMalloc((void**)&d_gain, (size_t)n_bands * P * sizeof(float)));
+  int rc = deconv_energies(c, c->stream, d_cube, P, n, bands, n_bands, d_energy);
+  long total_iter = 0, done_iter = 0;
+  for (int b = 0; b < n_bands; ++b) total_iter += std::max(bands[b].n_iter, 1);
+  for (int b = 0; rc == THZ_OK && b < n_bands; ++b) {
+    if (abort_flag && *abort_flag) { rc = THZ_ABORTED; break; }
+    const float base = 0.1f + 0.8f * (float)done_iter / (float)total_iter;
+    const float span = 0.8f * (float)std::max(bands[b].n_iter, 1) / (float)total_iter;
+    rc = richardson_lucy(c, c->stream, d_energy + (size_t)b * P, rows, cols, bands[b].psf_x, bands[b].kx,
+                         bands[b].psf_y, bands[b].ky, nullptr, bands[b].direct, bands[b].n_iter, nullptr,
+                         d_gain + (size_t)b * P, abort_flag, progress, progress_user, base, span);
+    done_iter += std::max(bands[b].n_iter, 1);
+  }
+  if (rc == THZ_OK) rc = deconv_apply(c, c->stream, d_cube, d_gain, P, n, bands, n_bands, d_out, d_img);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_energy);
+  cudaFree(d_gain);
+  if (rc == THZ_OK && progress) progress(1.0f, progress_user);
+  return rc;
+}
+
+int thz_deconvolution_host(thz_ctx* c, const float* cube, int rows, int cols, int n, const thz_band_plan* bands,
+                           int n_bands, float* out, float* img, const volatile int32_t* abort_flag,
+                           thz_progress_fn progress, void* progress_user) {
+  CHECK_CTX(c);
+  const int64_t P = (int64_t)rows * cols;
+  if (P == 0) return THZ_OK;
+  if (!cube || !out) return set_err(c, THZ_EINVAL, "null pointer");
+  float *d_cube = nullptr, *d_img = nullptr;
+  THZ_CUDA(c, cudaMalloc((void**)&d_cube, (size_t)P * n * sizeof(float)));
+  THZ_CUDA(c, cudaMalloc((void**)&d_img, (size_t)P * sizeof(float)));
+  THZ_CUDA(c, cudaMemcpyAsync(d_cube, cube, (size_t)P * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  int rc = thz_deconvolution_dev(c, d_cube, rows, cols, n, bands, n_bands, d_cube, d_img, abort_flag, progress,
+                                 progress_user);
+  if (rc == THZ_OK) {
+    cudaMemcpyAsync(out, d_cube, (size_t)P * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (img) cudaMemcpyAsync(img, d_img, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_cube);
+  cudaFree(d_img);
+  if (rc == THZ_OK && e != cudaSuccess) return cuda_fail(c, e, "thz_deconvolution_host");
+  return rc;
+}
+
+}  // extern "C"

@@ -11,7 +11,8 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .binding import ThzError, lib
+from .binding import (BandPlanC, DeconvParamsC, HybridFitC, PsfC, SplineC, ThzError, lib, SKIP_REASONS,
+                      THZ_FIR_TAPS)
 
 FFT_WINDOW_TYPES = {"AdaptedBlackman": 0, "Blackman": 1, "Hanning": 2, "Hamming": 3, "FlatTop": 4}
 
@@ -109,3 +110,88 @@ def chain_multipliers(time, cfg: ChainConfig = None, dx_dy_present=True):
     else:
         m_post = None
     return m_pre.astype(np.float32), band, m_post
+
+
+# ----------------------------------------------------------------------------------------
+# Deconvolution: PSF container (`load_psf`, src/io.rs:190-267) and the band planner
+# ----------------------------------------------------------------------------------------
+class PSF:
+    """The 26 arrays of psf.npz cast to f32, held alive for the C structs that borrow them."""
+
+    def __init__(self, arrays: dict):
+        self._keep = []
+        self.c = PsfC()
+
+        def arr(name):
+            a = np.ascontiguousarray(np.asarray(arrays[name], dtype=np.float64).reshape(-1).astype(np.float32))
+            self._keep.append(a)
+            return a
+
+        def spline(prefix, dst: SplineC):
+            k = arr(f"{prefix}_knots_thz")
+            dst.n = k.size
+            dst.knots = k.ctypes.data
+            dst.values = arr(f"{prefix}_values_mm").ctypes.data
+            for nm in "abcd":
+                setattr(dst, f"coeff_{nm}", arr(f"{prefix}_coeff_{nm}").ctypes.data)
+
+        def hybrid(prefix, dst: HybridFitC):
+            dst.base_a = float(arr(f"{prefix}_base_a")[0])
+            dst.base_b = float(arr(f"{prefix}_base_b")[0])
+            spline(f"{prefix}_corr", dst.correction)
+
+        hybrid("wx", self.c.wx_fit)
+        hybrid("wy", self.c.wy_fit)
+        spline("x0", self.c.x0_spline)
+        spline("y0", self.c.y0_spline)
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path)
+        return cls({k: z[k] for k in z.files})
+
+    def wx(self, f):
+        return float(lib.thz_hybrid_eval(C.byref(self.c.wx_fit), float(f)))
+
+    def wy(self, f):
+        return float(lib.thz_hybrid_eval(C.byref(self.c.wy_fit), float(f)))
+
+    def x0(self, f):
+        return float(lib.thz_spline_eval_const_extrap(C.byref(self.c.x0_spline), float(f)))
+
+    def y0(self, f):
+        return float(lib.thz_spline_eval_const_extrap(C.byref(self.c.y0_spline), float(f)))
+
+
+def fir_bank(n_filters, start_freq, end_freq, win_width, time):
+    t = _t32(time)
+    filt = np.empty((n_filters, THZ_FIR_TAPS), np.float32)
+    cen = np.empty(n_filters, np.float32)
+    _chk(lib.thz_fir_bank(int(n_filters), float(start_freq), float(end_freq), float(win_width), float(t[0]),
+                          float(t[1]), filt.ctypes.data, cen.ctypes.data), "thz_fir_bank")
+    return filt, cen
+
+
+@dataclass
+class Deconvolution:
+    """`Deconvolution` filter parameters (src/filters/deconvolution.rs:725-733)."""
+    n_iterations: int = 500
+    n_filters: int = 25
+    start_freq: float = 0.1
+    end_freq: float = 10.0
+    win_width: float = 0.5
+
+    def plan(self, time, shape, dx, dy, psf: PSF):
+        """-> (bands ctypes array, None) or (None, reason) when the reference returns its input."""
+        t = _t32(time)
+        prm = DeconvParamsC(int(self.n_iterations), int(self.n_filters), float(np.float32(self.start_freq)),
+                            float(np.float32(self.end_freq)), float(np.float32(self.win_width)))
+        bands = (BandPlanC * int(self.n_filters))()
+        has = dx is not None and dy is not None
+        rc = lib.thz_deconv_plan_bands(C.byref(psf.c) if psf is not None else None, C.byref(prm), t.ctypes.data,
+                                       t.size, int(shape[0]), int(shape[1]), int(has), float(dx or 0.0),
+                                       float(dy or 0.0), bands)
+        if rc in SKIP_REASONS:
+            return None, SKIP_REASONS[rc]
+        _chk(rc, "thz_deconv_plan_bands")
+        return bands, None
