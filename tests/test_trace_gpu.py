@@ -213,3 +213,28 @@ def test_spectral_means(ctx):
     # mean phases inherit unwrap ambiguities of single traces: compare with the means of the GPU's own phases
     ph = d_ph.download((P, F)).astype(np.float64).mean(axis=0)
     assert rel_err(a_ph, ph.astype(F32)) <= 1e-5
+
+
+def test_all_zero_traces_stay_exactly_zero(ctx):
+    """A dead pixel (all-zero trace) gives exact zeros in the reference, which transforms every
+    trace on its own.  Traces are transformed in pairs here; the zero one must not pick up
+    rounding leakage from its neighbour (and its phase must be atan2(0, 0) = 0)."""
+    for n in (256, 2048, 4096):
+        w, h = 3, 6
+        cube = synthetic_cube(w, h, n, seed=21)
+        cube[0, 1] = 0.0      # second of a pair
+        cube[1, 2] = 0.0      # first of a pair
+        cube[2, 4:6] = 0.0    # both of a pair
+        t, m_pre, band, m_post = default_multipliers(n)
+        ctx.plan_trace(n, m_pre, band, m_post)
+        out, img = ctx.trace_fused(cube)
+        for (i, j) in [(0, 1), (1, 2), (2, 4), (2, 5)]:
+            assert not out[i, j].any() and img[i, j] == 0.0
+        assert np.abs(out[0, 0]).max() > 0
+        got = ctx.trace_forward(cube, want=("fft", "amp", "phase"))
+        for (i, j) in [(0, 1), (1, 2), (2, 4), (2, 5)]:
+            assert not got["fft"][i, j].any() and not got["amp"][i, j].any() and not got["phase"][i, j].any()
+        spec = got["fft"].copy()
+        back, _ = ctx.trace_inverse(spec)
+        for (i, j) in [(0, 1), (1, 2), (2, 4), (2, 5)]:
+            assert not back[i, j].any()

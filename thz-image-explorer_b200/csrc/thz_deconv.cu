@@ -32,7 +32,7 @@ template <int M> struct DGeo {
   static constexpr int T = M / kE;
   static constexpr int NT = (T >= 256) ? T : 256;
   static constexpr int G = NT / T;
-  static constexpr int kScr = 32 * G;
+  static constexpr int kScr = (32 + kNzWords) * G;
   static constexpr size_t smem_bytes = (size_t)G * padded_len(M) * sizeof(float2) + kScr * sizeof(float);
   static constexpr int kMinBlocks = (NT == 256) ? 2 : 1;
 };
@@ -82,16 +82,19 @@ __device__ __forceinline__ void dreduce2(float& a, float& b, int t, int g, float
 
 template <int M>
 __device__ __forceinline__ void load_padded_pair(float2 (&v)[kE], const FirArgs& a, int t, bool act0, bool act1,
-                                                 int64_t p0) {
+                                                 int64_t p0, bool& nz0, bool& nz1) {
   constexpr int T = DGeo<M>::T;
   const float* r0 = a.x + p0 * a.n;
   const float* r1 = r0 + a.n;
+  nz0 = nz1 = false;
 #pragma unroll
   for (int i = 0; i < kE; ++i) {
     const int e = t + i * T;
     const bool in = e < a.n;
     v[i].x = (act0 && in) ? __ldcs(r0 + e) : 0.f;
     v[i].y = (act1 && in) ? __ldcs(r1 + e) : 0.f;
+    nz0 |= (v[i].x != 0.f);
+    nz1 |= (v[i].y != 0.f);
   }
 }
 
@@ -111,12 +114,17 @@ __global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_energy
   constexpr int RL = Plan<M>::r[LAST];
   constexpr int UL = kE / RL;
 
-  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+  unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
+  int parity = 0;
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
     const int64_t p0 = (item * G + g) * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
     float2 z[kE];
-    load_padded_pair<M>(z, a, t, act0, act1, p0);
+    bool nz0, nz1, z0, z1;
+    load_padded_pair<M>(z, a, t, act0, act1, p0, nz0, nz1);
+    nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
     fft_forward<M>(z, t, sm, a.tw);
+    nz_resolve<T>(g, parity, nzbuf, z0, z1);
     for (int b = 0; b < a.B; ++b) {
       const float* hq = a.hq + (size_t)b * M;
       float2 w[kE];
@@ -137,8 +145,9 @@ __global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_energy
       }
       dreduce2<M>(s0, s1, t, g, scr);
       if (t == 0) {
-        if (act0) a.energy[(size_t)b * a.P + p0] = s0;
-        if (act1) a.energy[(size_t)b * a.P + p0 + 1] = s1;
+        // an all-zero trace has exactly zero band energy in the reference (-> NaN gain, quirk 10)
+        if (act0) a.energy[(size_t)b * a.P + p0] = z0 ? 0.f : s0;
+        if (act1) a.energy[(size_t)b * a.P + p0 + 1] = z1 ? 0.f : s1;
       }
     }
   }
@@ -164,7 +173,8 @@ __global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_apply(
     const int64_t p0 = (item * G + g) * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
     float2 z[kE];
-    load_padded_pair<M>(z, a, t, act0, act1, p0);
+    bool nz0, nz1;
+    load_padded_pair<M>(z, a, t, act0, act1, p0, nz0, nz1);
     fft_forward<M>(z, t, sm, a.tw);
     // natural-order copy so that every thread can fetch the mirror bin Z[M - k]
     __syncthreads();
@@ -242,6 +252,7 @@ struct ConvArgs {
   const float* d;         // mode 1: relative blur numerator (padded image)
   float* out;             // mode 0: conv result; mode 1: r = d / (conv + eps); mode 2: u *= conv (in place)
   float eps;
+  int col_shift;          // tile-grid column offset that keeps the TMA box start 16-byte aligned
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -274,14 +285,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 template <int MODE, bool DENSE>
 __global__ void __launch_bounds__(256, 2) k_rl_conv(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);                       // [box_rows][box_cols]
+  // TMA destinations must be 128-byte aligned: align by hand (the launch adds 128 bytes of slack),
+  // the mbarrier lives in the first 16 bytes of the aligned block
+  unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint64_t* mbar_ptr = reinterpret_cast<uint64_t*>(base);
+  float* tile = reinterpret_cast<float*>(base + 128);                     // [box_rows][box_cols]
   const int tile_floats = a.box_rows * a.box_cols;
   float* mid = tile + ((tile_floats + 31) & ~31);                         // [box_rows][kMidStride]
   float* wxs = mid + (DENSE ? 0 : a.box_rows * kMidStride);
   float* wys = wxs + (DENSE ? 0 : a.kxp);                                 // separable: [kxp] then [kyp]
-  __shared__ __align__(8) uint64_t mbar_storage;
-  const uint32_t mbar = smem_u32(&mbar_storage);
-  const int row0 = blockIdx.y * kTH, col0 = blockIdx.x * kTW;
+  const uint32_t mbar = smem_u32(mbar_ptr);
+  // TMA needs a 16-byte aligned box start: the innermost coordinate col0 - ky/2 must be a multiple of
+  // 4 floats, so the tile grid is shifted left by col_shift in {0, -3, -2, -1} columns
+  const int row0 = blockIdx.y * kTH, col0 = blockIdx.x * kTW + a.col_shift;
 
   if (threadIdx.x == 0) mbar_init(mbar, 1);
   if constexpr (DENSE) {
@@ -383,7 +399,7 @@ __global__ void __launch_bounds__(256, 2) k_rl_conv(const __grid_constant__ CUte
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int gr = row0 + rg * 8 + q, gc = col0 + c;
-        if (gr < a.Hp && gc < a.Wp) {
+        if (gr < a.Hp && gc >= 0 && gc < a.Wp) {
           const size_t o = (size_t)gr * a.pitch + gc;
           if constexpr (MODE == 0) a.out[o] = acc[q];
           else if constexpr (MODE == 1) a.out[o] = a.d[o] / (acc[q] + a.eps);
@@ -666,12 +682,13 @@ static int make_conv_plan(thz_ctx* c, cudaStream_t s, int Hp, int Wp, int pitch,
   if (((bc / 4) & 1) == 0) bc += 4;     // 4 * odd: conflict-free 128-bit row accesses
   a.box_cols = bc;
   a.eps = 1e-12f;
+  a.col_shift = ((ky / 2) % 4 == 0) ? 0 : (ky / 2) % 4 - 4;
   cp.dense = dense != nullptr;
   if (a.box_rows > 256 || a.box_cols > 256) return set_err(c, THZ_EINVAL, "PSF too large for one TMA box");
   const int tile_floats = (a.box_rows * a.box_cols + 31) & ~31;
   std::vector<float> w;
   if (!cp.dense) {
-    cp.smem = (size_t)(tile_floats + a.box_rows * kMidStride + a.kxp + a.kyp) * sizeof(float);
+    cp.smem = (size_t)(tile_floats + a.box_rows * kMidStride + a.kxp + a.kyp) * sizeof(float) + 256;
     cp.wstride = a.kxp + a.kyp;
     w.assign(2 * cp.wstride, 0.f);
     // orientation 0 = first conv of the iteration (u with psf), 1 = second (r with the mirrored psf).
@@ -682,7 +699,7 @@ static int make_conv_plan(thz_ctx* c, cudaStream_t s, int Hp, int Wp, int pitch,
       for (int j = 0; j < ky; ++j) w[o * cp.wstride + a.kxp + j] = psf_y[flip ? ky - 1 - j : j];
     }
   } else {
-    cp.smem = (size_t)(tile_floats + kx * a.kyp) * sizeof(float);
+    cp.smem = (size_t)(tile_floats + kx * a.kyp) * sizeof(float) + 256;
     cp.wstride = kx * a.kyp;
     w.assign(2 * cp.wstride, 0.f);
     for (int o = 0; o < 2; ++o) {
@@ -711,7 +728,7 @@ static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUt
   }
   a.d = d;
   a.out = out;
-  dim3 grid((a.Wp + kTW - 1) / kTW, (a.Hp + kTH - 1) / kTH);
+  dim3 grid((a.Wp - a.col_shift + kTW - 1) / kTW, (a.Hp + kTH - 1) / kTH);
   cudaError_t e;
   if (cp.dense) {
     e = cudaFuncSetAttribute(k_rl_conv<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);

@@ -251,4 +251,50 @@ __device__ __forceinline__ void fft_inverse(float2 (&v)[kE], int t, float2* sm, 
   }
 }
 
+// ------------------------------------------------------------------------------------
+// "is this trace entirely zero?" flags for a pair of traces packed as re / im.
+// Packing two real traces into one complex transform leaks ~1e-7 of one trace into the other
+// through rounding; the reference transforms traces separately, so an all-zero trace (a dead
+// pixel) stays exactly zero there.  The kernels detect all-zero inputs at load time and write
+// exact zeros for them.  Groups narrower than a warp resolve with one ballot; wider groups
+// publish one word per warp to shared memory and read it back after the next barrier (the
+// first exchange of the transform), double-buffered by item parity so that no extra barrier
+// is needed.
+// ------------------------------------------------------------------------------------
+constexpr int kNzWords = 64;   // per group: 2 parities x 16 warps x 2 traces
+
+template <int T>
+__device__ __forceinline__ void nz_publish(bool nz0, bool nz1, int t, int g, int parity, unsigned* nzbuf, bool& z0,
+                                           bool& z1) {
+  const unsigned b0 = __ballot_sync(0xffffffffu, nz0), b1 = __ballot_sync(0xffffffffu, nz1);
+  if constexpr (T < 32) {
+    const unsigned lane0 = (threadIdx.x & 31u) / T * T;
+    const unsigned mask = ((1u << T) - 1u) << lane0;
+    z0 = (b0 & mask) == 0u;
+    z1 = (b1 & mask) == 0u;
+  } else {
+    if ((t & 31) == 0) {
+      unsigned* w = nzbuf + g * kNzWords + parity * 32 + (t >> 5) * 2;
+      w[0] = b0;
+      w[1] = b1;
+    }
+    z0 = z1 = false;   // resolved by nz_resolve after a barrier
+  }
+}
+
+template <int T>
+__device__ __forceinline__ void nz_resolve(int g, int parity, const unsigned* nzbuf, bool& z0, bool& z1) {
+  if constexpr (T >= 32) {
+    const unsigned* w = nzbuf + g * kNzWords + parity * 32;
+    unsigned a0 = 0u, a1 = 0u;
+#pragma unroll
+    for (int i = 0; i < T / 32; ++i) {
+      a0 |= w[2 * i];
+      a1 |= w[2 * i + 1];
+    }
+    z0 = a0 == 0u;
+    z1 = a1 == 0u;
+  }
+}
+
 }  // namespace thz

@@ -25,7 +25,7 @@ template <int N> struct Geo {
   static constexpr int T = N / kE;                       // threads per trace pair
   static constexpr int NT = (T >= 256) ? T : 256;        // threads per CTA
   static constexpr int G = NT / T;                       // trace pairs per CTA pass
-  static constexpr int kScr = 32 * G;                    // float scratch per CTA
+  static constexpr int kScr = (32 + kNzWords) * G;       // per-CTA scratch words: reductions + zero-trace flags
   static constexpr int kMinBlocks = (NT == 256) ? 2 : 1; // register cap: 128 per thread
   static constexpr size_t smem_bytes = (size_t)G * padded_len(N) * sizeof(float2) + kScr * sizeof(float);
 };
@@ -84,14 +84,17 @@ __device__ __forceinline__ void group_reduce2(float& a, float& b, int t, int g, 
 // Load the pair (p0, p1) into stage-0 register layout, multiplied by m_pre.
 template <int N>
 __device__ __forceinline__ void load_pair(float2 (&v)[kE], const TraceArgs& a, int t, bool act0, bool act1,
-                                          int64_t p0) {
+                                          int64_t p0, bool& nz0, bool& nz1) {
   constexpr int T = Geo<N>::T;
   const float* r0 = a.in + p0 * N + t;
   const float* r1 = r0 + N;
+  nz0 = nz1 = false;
 #pragma unroll
   for (int i = 0; i < kE; ++i) {
     v[i].x = act0 ? ld_stream(r0 + i * T) : 0.f;
     v[i].y = act1 ? ld_stream(r1 + i * T) : 0.f;
+    nz0 |= (v[i].x != 0.f);
+    nz1 |= (v[i].y != 0.f);
   }
   if (a.m_pre != nullptr) {
 #pragma unroll
@@ -106,8 +109,15 @@ __device__ __forceinline__ void load_pair(float2 (&v)[kE], const TraceArgs& a, i
 // multiply by m_post, store both traces, intensity = sum of squares of the stored values
 template <int N>
 __device__ __forceinline__ void store_pair(float2 (&v)[kE], const TraceArgs& a, int t, int g, bool act0,
-                                           bool act1, int64_t p0, bool use_post, float* scr) {
+                                           bool act1, int64_t p0, bool use_post, float* scr, bool z0, bool z1) {
   constexpr int T = Geo<N>::T;
+  if (z0 || z1) {   // all-zero input trace: exact zeros out, as when transformed on its own
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      if (z0) v[i].x = 0.f;
+      if (z1) v[i].y = 0.f;
+    }
+  }
   if (use_post) {
 #pragma unroll
     for (int i = 0; i < kE; ++i) {
@@ -153,13 +163,17 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(
   constexpr int LAST = Plan<N>::ns - 1;
   constexpr int RL = Plan<N>::r[LAST];
   constexpr int UL = kE / RL;
+  unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
+  int parity = 0;
 
-  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
     const int64_t pair = item * G + g;
     const int64_t p0 = pair * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
     float2 v[kE];
-    load_pair<N>(v, a, t, act0, act1, p0);
+    bool nz0, nz1, z0, z1;
+    load_pair<N>(v, a, t, act0, act1, p0, nz0, nz1);
+    nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
     fft_forward<N>(v, t, sm, a.tw);
     // band-pass in digit-reversed order: register (u, m) <-> position (t + u*T)*RL + m,
     // hq is stored [m][beta] so that a warp reads consecutive floats
@@ -171,7 +185,8 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(
       v[i].y *= h;
     }
     fft_inverse<N>(v, t, sm, a.tw);
-    store_pair<N>(v, a, t, g, act0, act1, p0, use_post, scr);
+    nz_resolve<T>(g, parity, nzbuf, z0, z1);
+    store_pair<N>(v, a, t, g, act0, act1, p0, use_post, scr, z0, z1);
   }
 }
 
@@ -196,13 +211,17 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_forwar
   const int64_t nitems = (npairs + G - 1) / G;
   constexpr int LAST = Plan<N>::ns - 1;
   const bool want_phase = a.phase != nullptr;
+  unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
+  int parity = 0;
 
-  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
     const int64_t pair = item * G + g;
     const int64_t p0 = pair * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
     float2 v[kE];
-    load_pair<N>(v, a, t, act0, act1, p0);
+    bool nz0, nz1, z0, z1;
+    load_pair<N>(v, a, t, act0, act1, p0, nz0, nz1);
+    nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
     if (a.win != nullptr) {   // the reference leaves the windowed trace in `data`
       float* w0 = a.win + p0 * N + t;
       float* w1 = w0 + N;
@@ -218,6 +237,7 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_forwar
 #pragma unroll
     for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = v[i];
     __syncthreads();
+    nz_resolve<T>(g, parity, nzbuf, z0, z1);
     // split the packed spectrum: X1 = (Z[k] + conj Z[N-k]) / 2, X2 = (Z[k] - conj Z[N-k]) / 2i
     float ph0[NU], ph1[NU];
 #pragma unroll
@@ -226,10 +246,12 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_forwar
       ph0[u] = 0.f;
       ph1[u] = 0.f;
       if (u < NU - 1 || t == 0) {
-        const float2 z1 = sm[pad_idx(k)];
-        const float2 z2 = sm[pad_idx((N - k) & (N - 1))];
-        const float2 x0 = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
-        const float2 x1 = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+        const float2 za = sm[pad_idx(k)];
+        const float2 zb = sm[pad_idx((N - k) & (N - 1))];
+        float2 x0 = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
+        float2 x1 = make_float2(0.5f * (za.y + zb.y), 0.5f * (zb.x - za.x));
+        if (z0) x0 = make_float2(0.f, 0.f);   // all-zero trace: exact zero spectrum (and phase 0)
+        if (z1) x1 = make_float2(0.f, 0.f);
         if (a.fft != nullptr) {
           if (act0) __stcs(a.fft + p0 * F + k, x0);
           if (act1) __stcs(a.fft + (p0 + 1) * F + k, x1);
@@ -330,11 +352,14 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_invers
   constexpr int LAST = Plan<N>::ns - 1;
   const bool use_post = a.m_post != nullptr;
   const float inv_n = 1.0f / (float)N;
+  unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
+  int parity = 0;
 
-  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
     const int64_t pair = item * G + g;
     const int64_t p0 = pair * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    bool nz0 = false, nz1 = false, z0, z1;
     __syncthreads();   // previous iteration's readers of sm are done
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
@@ -344,6 +369,8 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_invers
         float2 x1 = act1 ? __ldcs(a.fft_in + (p0 + 1) * F + k) : make_float2(0.f, 0.f);
         const float s = (a.band != nullptr) ? __ldg(a.band + k) * inv_n : inv_n;
         x0.x *= s; x0.y *= s; x1.x *= s; x1.y *= s;
+        nz0 |= (x0.x != 0.f) | (x0.y != 0.f);
+        nz1 |= (x1.x != 0.f) | (x1.y != 0.f);
         if (k == 0 || k == N / 2) {   // c2r ignores the imaginary parts of DC and Nyquist
           sm[pad_idx(k)] = make_float2(x0.x, x1.x);
         } else {
@@ -352,12 +379,14 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_invers
         }
       }
     }
+    nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
     __syncthreads();
     float2 v[kE];
 #pragma unroll
     for (int i = 0; i < kE; ++i) v[i] = sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))];
     fft_inverse<N>(v, t, sm, a.tw);
-    store_pair<N>(v, a, t, g, act0, act1, p0, use_post, scr);
+    nz_resolve<T>(g, parity, nzbuf, z0, z1);
+    store_pair<N>(v, a, t, g, act0, act1, p0, use_post, scr, z0, z1);
   }
 }
 
