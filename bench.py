@@ -110,6 +110,9 @@ def parse_args():
     ap.add_argument("--height", type=int, default=2048)
     ap.add_argument("--samples", type=int, default=4096)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-deconv", action="store_true", help="trace pass only (skip the PSF deconvolution)")
+    ap.add_argument("--bands", type=int, default=8)
+    ap.add_argument("--rl-iterations", type=int, default=500)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline slab (0 = auto)")
     return ap.parse_args()
@@ -196,9 +199,8 @@ def run_ours(a):
 
     W, H, N = a.width, a.height, a.samples
     # row-slab partition over axis 0 (x), uneven last slab allowed
-    base, rem = divmod(W, world)
-    rows = base + (1 if rank < rem else 0)
-    row0 = rank * base + min(rank, rem)
+    row0, row1 = m.sharding.slab_bounds(W, world, rank)
+    rows = row1 - row0
     P = rows * H
     P_total = W * H
 
@@ -220,8 +222,56 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # deconvolution plan: BASELINE config 5 = 8 FIR bands, shipped psf.npz, dx = dy = 0.5 mm
+    bands = None
+    if not a.no_deconv:
+        psf = m.host.PSF.load(os.path.join(ROOT, "tests", "golden", "psf.npz"))
+        dec = m.host.Deconvolution(n_filters=a.bands, n_iterations=a.rl_iterations)
+        bands, why = dec.plan(t_axis, (W, H), 0.5, 0.5, psf)
+        if bands is None:
+            raise SystemExit(f"deconvolution plan refused: {why}")
+    n_rl_iter = sum(b.n_iter for b in bands) if bands is not None else 0
+    B = len(bands) if bands is not None else 0
+    class GpuOps:
+        """libthzgpu stage calls on torch device tensors (raw pointers through the C ABI)."""
+
+        def __init__(self):
+            self.dev = torch.device("cuda", local)
+            self.taps = [(np.ascontiguousarray(b.psf_x_np()), np.ascontiguousarray(b.psf_y_np())) for b in bands]
+
+        def energies(self, slab_ptr):
+            e = torch.empty((B, P), dtype=torch.float32, device=self.dev)
+            ctx.deconv_energies_dev(slab_ptr, P, N, bands, e.data_ptr())
+            ctx.sync()
+            return e
+
+        def rl_gain(self, b, image):
+            image = image.contiguous()
+            g = torch.empty(W * H, dtype=torch.float32, device=self.dev)
+            torch.cuda.synchronize()
+            px, py = self.taps[b]
+            ctx._check(m.lib.thz_rl_separable_dev(ctx.handle, image.data_ptr(), W, H, px.ctypes.data, px.size,
+                                                  py.ctypes.data, py.size, bands[b].direct, bands[b].n_iter, None,
+                                                  g.data_ptr(), None, None, None, 0.0, 0.0))
+            ctx.sync()
+            return g
+
+        def apply(self, slab_ptr, g_slab):
+            torch.cuda.synchronize()
+            ctx.deconv_apply_dev(slab_ptr, g_slab.data_ptr(), P, N, bands, slab_ptr, d_img.ptr)
+            ctx.sync()
+
+    ops = GpuOps() if (bands is not None and world > 1) else None
+
     def step():
         ctx.trace_fused_dev(d_in.ptr, d_out.ptr, d_img.ptr, P)
+        if bands is None:
+            return
+        if world == 1:
+            ctx._check(m.lib.thz_deconvolution_dev(ctx.handle, d_out.ptr, rows, H, N, bands, B, d_out.ptr,
+                                                   d_img.ptr, None, None, None))
+        else:
+            m.sharding.sharded_deconvolution(ops, d_out.ptr, W, H, B, dist, world, rank)
 
     launches0 = None
     for _ in range(a.warmup):
@@ -251,14 +301,42 @@ def run_ours(a):
     ms_per_step = total_ms / a.steps
     value = P_total / (ms_per_step / 1e3)
 
-    # roofline of the dominant kernel (the fused trace pass): algorithmic bytes per launch = (8N + 4) * P
+    # stage breakdown of the last step (CUDA events inside the library) + fused trace kernel timed alone
     peak, peak_src = measured_peaks()
-    alg_bytes = (8 * N + 4) * P
-    kernel_ms = float(np.mean(per_step_ms))      # one launch per step on this stream
-    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": f"k_trace_fused<{N}>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record(stream)
+    for _ in range(reps):
+        ctx.trace_fused_dev(d_in.ptr, d_out.ptr, d_img.ptr, P)
+    e1.record(stream)
+    ctx.sync()
+    trace_ms = e0.elapsed_time(e1) / reps
+    stages = {"trace_fused": {"ms": trace_ms, "kernel": f"k_trace_fused<{N}>", "algorithmic_bytes": (8 * N + 4) * P}}
+    if bands is not None and world == 1:
+        st = ctx.deconv_stage_ms()
+        M = 64
+        while M < N + 249:
+            M *= 2
+        stages["deconv_energies"] = {"ms": st["energies_ms"], "kernel": f"k_fir_energy<{M}>",
+                                     "algorithmic_bytes": (4 * N + 4 * B) * P}
+        stages["deconv_apply"] = {"ms": st["apply_ms"], "kernel": f"k_fir_apply<{M}>",
+                                  "algorithmic_bytes": (8 * N + 4 * B) * P}
+        stages["richardson_lucy"] = {"ms": st["rl_ms"], "kernel": "k_rl_conv<1|2,separable>",
+                                     "iterations": st["rl_iterations"],
+                                     "iters_per_s": st["rl_iterations"] / (st["rl_ms"] / 1e3) if st["rl_ms"] > 0 else None}
+    for v in stages.values():
+        if "algorithmic_bytes" in v:
+            v["gbs"] = v["algorithmic_bytes"] / (v["ms"] / 1e3) / 1e9
+            v["frac_of_hbm_peak"] = v["gbs"] / peak
+    dom = max((k for k in stages if "algorithmic_bytes" in stages[k]), key=lambda k: stages[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": stages[dom]["kernel"], "stage": dom, "achieved": stages[dom]["gbs"],
+                "peak": peak, "unit": "GB/s", "frac": stages[dom]["gbs"] / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"],
+                "kernel_ms": stages[dom]["ms"]}
+    # whole-step roofline: 20N + 8B + 4 bytes per trace for the three cube passes
+    chain_bytes = ((20 * N + 8 * B + 4) if bands is not None else (8 * N + 4)) * P
+    chain = {"algorithmic_bytes_per_step": chain_bytes, "gbs": chain_bytes / (ms_per_step / 1e3) / 1e9,
+             "frac_of_hbm_peak": chain_bytes / (ms_per_step / 1e3) / 1e9 / peak}
 
     # end to end through the host-pointer C ABI: pinned host cube -> H2D -> chain -> D2H (filtered cube + img)
     e2e = None
@@ -280,7 +358,10 @@ def run_ours(a):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "partition": f"row slabs over x, {world} rank(s)",
                        "l2": "inputs larger than L2 (cube >> 126 MB), no flush needed",
-                       "stages": ["trace pass (fused)"]},
+                       "stages": ["trace pass (fused)"] + (["deconvolution: band energies, Richardson-Lucy "
+                                                           f"({n_rl_iter} iterations over {len(bands)} bands), "
+                                                           "gain application"] if bands is not None else [])},
+            "stage_breakdown": stages, "chain_roofline": chain,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))

@@ -231,6 +231,10 @@ int thz_deconv_apply_dev(thz_ctx* ctx, const float* d_cube, const float* d_gain,
 int thz_deconvolution_dev(thz_ctx* ctx, const float* d_cube, int rows, int cols, int n,
                           const thz_band_plan* bands, int n_bands, float* d_out, float* d_img,
                           const volatile int32_t* abort_flag, thz_progress_fn progress, void* progress_user);
+/* CUDA-event timings of the last thz_deconvolution_dev call on this context, the per-filter
+ * wall time the reference shows beside the filter header (src/data_thread.rs:1107, 1169-1184):
+ * ms4 = {band energies, Richardson-Lucy, gain application, number of RL iterations run}. */
+int thz_deconv_stage_ms(const thz_ctx* ctx, float* ms4);
 /* Host-pointer drop-in for `Deconvolution::filter`. */
 int thz_deconvolution_host(thz_ctx* ctx, const float* cube, int rows, int cols, int n,
                            const thz_band_plan* bands, int n_bands, float* out, float* img,

@@ -16,3 +16,4 @@ from __future__ import annotations
 from .binding import (Context, DeviceBuffer, ThzError, lib, library_path, load_library,  # noqa: F401
                       DECLARED_SYMBOLS)
 from . import host  # noqa: F401,E402
+from . import sharding  # noqa: F401,E402

@@ -136,6 +136,7 @@ def load_library():
         "thz_conv2d_dense_dev": (i32, [vp, fp, i32, i32, fp, i32, i32, i32, fp]),
         "thz_deconv_apply_dev": (i32, [vp, fp, fp, i64, i32, C.POINTER(BandPlanC), i32, fp, fp]),
         "thz_deconvolution_dev": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
+        "thz_deconv_stage_ms": (i32, [vp, fp]),
         "thz_deconvolution_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_trace_fused_host": (i32, [vp, fp, fp, fp, i64]),
         "thz_trace_forward_host": (i32, [vp, fp, fp, fp, fp, fp, i64]),
@@ -412,3 +413,8 @@ class Context:
             C.addressof(abort_flag) if abort_flag is not None else None,
             C.cast(cb, C.c_void_p) if cb is not None else None, None))
         return out, img, rc
+
+    def deconv_stage_ms(self):
+        ms = np.zeros(4, np.float32)
+        self._check(lib.thz_deconv_stage_ms(self.handle, ms.ctypes.data))
+        return {"energies_ms": float(ms[0]), "rl_ms": float(ms[1]), "apply_ms": float(ms[2]), "rl_iterations": int(ms[3])}

@@ -53,6 +53,23 @@ int ensure_scratch(thz_ctx* c, size_t bytes) {
   return THZ_OK;
 }
 
+int ws_get(thz_ctx* c, int slot, size_t bytes, void** out) {
+  auto& e = c->ws[slot];
+  if (e.second < bytes) {
+    if (e.first) {
+      cudaError_t er = cudaFree(e.first);   // synchronises: nothing still uses the old buffer
+      if (er != cudaSuccess) return cuda_fail(c, er, "cudaFree(workspace)");
+    }
+    e = {nullptr, 0};
+    void* p = nullptr;
+    cudaError_t er = cudaMalloc(&p, bytes);
+    if (er != cudaSuccess) return cuda_fail(c, er, "cudaMalloc(workspace)");
+    e = {p, bytes};
+  }
+  *out = e.first;
+  return THZ_OK;
+}
+
 static int upload_vec(thz_ctx* c, float** d, const float* h, size_t n) {
   if (*d) {
     cudaFree(*d);
@@ -148,6 +165,8 @@ void thz_ctx_destroy(thz_ctx* c) {
   if (c->plan.d_band) cudaFree(c->plan.d_band);
   if (c->plan.d_hq) cudaFree(c->plan.d_hq);
   if (c->d_scratch) cudaFree(c->d_scratch);
+  for (auto& kv : c->ws)
+    if (kv.second.first) cudaFree(kv.second.first);
   for (int i = 0; i < kHostStreams; ++i) {
     if (c->d_stage[i]) cudaFree(c->d_stage[i]);
     if (c->hstream[i]) cudaStreamDestroy(c->hstream[i]);

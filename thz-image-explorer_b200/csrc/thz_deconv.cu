@@ -512,23 +512,42 @@ static int build_fir_hq(int m, const float* fir, std::vector<float>& hq) {
 
 struct FirTables {
   int m = 0, B = 0;
-  float* d_hq = nullptr;
+  float* d_hq = nullptr;   // workspace slot WS_FIR, cached across calls while the taps do not change
 };
+
+static uint64_t fnv1a(const void* p, size_t n, uint64_t h) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) {
+    h ^= b[i];
+    h *= 0x100000001B3ull;
+  }
+  return h;
+}
 
 static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_plan* bands, int B, FirTables& ft) {
   const int m = fir_fft_size(n);
   int ns, r[4];
   if (!plan_of_m(m, ns, r)) return set_err(c, THZ_EINVAL, "trace too long for the FIR transform (n + 249 must be <= 8192)");
+  uint64_t key = 0xcbf29ce484222325ull;
+  for (int b = 0; b < B; ++b) key = fnv1a(bands[b].fir, sizeof(bands[b].fir), key);
+  key = fnv1a(&m, sizeof m, key);
+  void* dp = nullptr;
+  int rc = ws_get(c, WS_FIR, (size_t)B * m * sizeof(float), &dp);
+  if (rc != THZ_OK) return rc;
+  ft.d_hq = (float*)dp;
+  ft.m = m;
+  ft.B = B;
+  if (c->fir_key == key && c->fir_m == m) return THZ_OK;
   std::vector<float> all((size_t)B * m), one;
   for (int b = 0; b < B; ++b) {
     if (build_fir_hq(m, bands[b].fir, one) != THZ_OK) return set_err(c, THZ_EINVAL, "bad FIR transform size");
     std::copy(one.begin(), one.end(), all.begin() + (size_t)b * m);
   }
-  THZ_CUDA(c, cudaMalloc((void**)&ft.d_hq, all.size() * sizeof(float)));
+  THZ_CUDA(c, cudaStreamSynchronize(s));   // no kernel still reads the previous spectra
   THZ_CUDA(c, cudaMemcpyAsync(ft.d_hq, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   THZ_CUDA(c, cudaStreamSynchronize(s));
-  ft.m = m;
-  ft.B = B;
+  c->fir_key = key;
+  c->fir_m = m;
   return THZ_OK;
 }
 
@@ -597,8 +616,6 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
     a.x = d_cube; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.energy = d_energy; a.tw = tb->d_tw;
     rc = dispatch_energy(c, s, ft.m, a);
   }
-  cudaStreamSynchronize(s);
-  cudaFree(ft.d_hq);
   return rc;
 }
 
@@ -618,8 +635,6 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
     a.tw = tb->d_tw;
     rc = dispatch_apply(c, s, ft.m, a);
   }
-  cudaStreamSynchronize(s);
-  cudaFree(ft.d_hq);
   return rc;
 }
 
@@ -710,7 +725,11 @@ static int make_conv_plan(thz_ctx* c, cudaStream_t s, int Hp, int Wp, int pitch,
     }
   }
   if (cp.smem > 227 * 1024) return set_err(c, THZ_EINVAL, "PSF too large for the shared-memory tile");
-  THZ_CUDA(c, cudaMalloc((void**)&cp.d_w, w.size() * sizeof(float)));
+  void* dp = nullptr;
+  int rc = ws_get(c, WS_RL_TAPS, w.size() * sizeof(float), &dp);
+  if (rc != THZ_OK) return rc;
+  cp.d_w = (float*)dp;
+  THZ_CUDA(c, cudaStreamSynchronize(s));   // the previous band's kernels are done with the taps
   THZ_CUDA(c, cudaMemcpyAsync(cp.d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   THZ_CUDA(c, cudaStreamSynchronize(s));
   return THZ_OK;
@@ -730,15 +749,15 @@ static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUt
   a.out = out;
   dim3 grid((a.Wp - a.col_shift + kTW - 1) / kTW, (a.Hp + kTH - 1) / kTH);
   cudaError_t e;
-  if (cp.dense) {
-    e = cudaFuncSetAttribute(k_rl_conv<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);
-    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl dense)");
-    k_rl_conv<MODE, true><<<grid, 256, cp.smem, s>>>(map, a);
-  } else {
-    e = cudaFuncSetAttribute(k_rl_conv<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);
+  const void* key = cp.dense ? (const void*)k_rl_conv<MODE, true> : (const void*)k_rl_conv<MODE, false>;
+  size_t& have = c->smem_set[key];
+  if (have < cp.smem) {
+    e = cudaFuncSetAttribute(key, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);
     if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl)");
-    k_rl_conv<MODE, false><<<grid, 256, cp.smem, s>>>(map, a);
+    have = cp.smem;
   }
+  if (cp.dense) k_rl_conv<MODE, true><<<grid, 256, cp.smem, s>>>(map, a);
+  else k_rl_conv<MODE, false><<<grid, 256, cp.smem, s>>>(map, a);
   c->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_conv launch");
@@ -755,9 +774,11 @@ int conv2d_once(thz_ctx* c, cudaStream_t s, const float* d_in, int rows, int col
                 const float* psf_y, int ky, const float* dense, int direct, float* d_out) {
   if (!d_in || !d_out || rows < 1 || cols < 1) return set_err(c, THZ_EINVAL, "bad image");
   const int pitch = round_up(cols, 4);
-  float *d_a = nullptr, *d_b = nullptr;
-  THZ_CUDA(c, cudaMalloc((void**)&d_a, (size_t)rows * pitch * sizeof(float)));
-  THZ_CUDA(c, cudaMalloc((void**)&d_b, (size_t)rows * pitch * sizeof(float)));
+  void *pa = nullptr, *pb = nullptr;
+  int rcw = ws_get(c, WS_CONV_A, (size_t)rows * pitch * sizeof(float), &pa);
+  if (rcw == THZ_OK) rcw = ws_get(c, WS_CONV_B, (size_t)rows * pitch * sizeof(float), &pb);
+  if (rcw != THZ_OK) return rcw;
+  float *d_a = (float*)pa, *d_b = (float*)pb;
   k_copy2d<<<grid_for(c, (int64_t)rows * cols), 256, 0, s>>>(d_in, rows, cols, cols, d_a, pitch);
   c->launches++;
   ConvPlan cp;
@@ -772,9 +793,6 @@ int conv2d_once(thz_ctx* c, cudaStream_t s, const float* d_in, int rows, int col
   }
   cudaStreamSynchronize(s);
   cudaError_t e = cudaGetLastError();
-  cudaFree(d_a);
-  cudaFree(d_b);
-  if (cp.d_w) cudaFree(cp.d_w);
   if (rc == THZ_OK && e != cudaSuccess) return cuda_fail(c, e, "conv2d");
   return rc;
 }
@@ -788,10 +806,12 @@ int richardson_lucy(thz_ctx* c, cudaStream_t s, const float* d_image, int rows, 
   if (pad_y >= rows - 1 || pad_x >= cols - 1) return set_err(c, THZ_EINVAL, "PSF larger than the image");
   const int Hp = rows + 2 * pad_y, Wp = cols + 2 * pad_x, pitch = round_up(Wp, 4);
   const size_t img_bytes = (size_t)Hp * pitch * sizeof(float);
-  float *d_d = nullptr, *d_u = nullptr, *d_r = nullptr;
-  THZ_CUDA(c, cudaMalloc((void**)&d_d, img_bytes));
-  THZ_CUDA(c, cudaMalloc((void**)&d_u, img_bytes));
-  THZ_CUDA(c, cudaMalloc((void**)&d_r, img_bytes));
+  void *pd = nullptr, *pu = nullptr, *pr = nullptr;
+  int rcw = ws_get(c, WS_RL_D, img_bytes, &pd);
+  if (rcw == THZ_OK) rcw = ws_get(c, WS_RL_U, img_bytes, &pu);
+  if (rcw == THZ_OK) rcw = ws_get(c, WS_RL_R, img_bytes, &pr);
+  if (rcw != THZ_OK) return rcw;
+  float *d_d = (float*)pd, *d_u = (float*)pu, *d_r = (float*)pr;
   THZ_CUDA(c, cudaMemsetAsync(d_d, 0, img_bytes, s));
   k_reflect_pad<<<grid_for(c, (int64_t)Hp * Wp), 256, 0, s>>>(d_image, rows, cols, pad_y, pad_x, d_d, pitch);
   c->launches++;
@@ -821,10 +841,6 @@ int richardson_lucy(thz_ctx* c, cudaStream_t s, const float* d_image, int rows, 
     c->launches++;
   }
   cudaError_t e = cudaStreamSynchronize(s);
-  cudaFree(d_d);
-  cudaFree(d_u);
-  cudaFree(d_r);
-  if (cp.d_w) cudaFree(cp.d_w);
   if (rc == THZ_OK && e != cudaSuccess) return cuda_fail(c, e, "richardson_lucy");
   if (rc == THZ_OK && aborted) return THZ_ABORTED;
   return rc;
@@ -895,10 +911,16 @@ int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, i
   const int64_t P = (int64_t)rows * cols;
   if (P == 0) return THZ_OK;
   if (progress) progress(0.0f, progress_user);
-  float *d_energy = nullptr, *d_gain = nullptr;
-  THZ_CUDA(c, cudaMalloc((void**)&d_energy, (size_t)n_bands * P * sizeof(float)));
-  THZ_CUDA(c, cudaMalloc((void**)&d_gain, (size_t)n_bands * P * sizeof(float)));
+  void *pe = nullptr, *pg = nullptr;
+  int rcw = ws_get(c, WS_ENERGY, (size_t)n_bands * P * sizeof(float), &pe);
+  if (rcw == THZ_OK) rcw = ws_get(c, WS_GAIN, (size_t)n_bands * P * sizeof(float), &pg);
+  if (rcw != THZ_OK) return rcw;
+  float *d_energy = (float*)pe, *d_gain = (float*)pg;
+  cudaEvent_t ev[4];
+  for (auto& e : ev) cudaEventCreate(&e);
+  cudaEventRecord(ev[0], c->stream);
   int rc = deconv_energies(c, c->stream, d_cube, P, n, bands, n_bands, d_energy);
+  cudaEventRecord(ev[1], c->stream);
   long total_iter = 0, done_iter = 0;
   for (int b = 0; b < n_bands; ++b) total_iter += std::max(bands[b].n_iter, 1);
   for (int b = 0; rc == THZ_OK && b < n_bands; ++b) {
@@ -910,12 +932,21 @@ int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, i
                          d_gain + (size_t)b * P, abort_flag, progress, progress_user, base, span);
     done_iter += std::max(bands[b].n_iter, 1);
   }
+  cudaEventRecord(ev[2], c->stream);
   if (rc == THZ_OK) rc = deconv_apply(c, c->stream, d_cube, d_gain, P, n, bands, n_bands, d_out, d_img);
+  cudaEventRecord(ev[3], c->stream);
   cudaStreamSynchronize(c->stream);
-  cudaFree(d_energy);
-  cudaFree(d_gain);
+  for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&c->stage_ms[i], ev[i], ev[i + 1]);
+  c->stage_ms[3] = (float)done_iter;
+  for (auto& e : ev) cudaEventDestroy(e);
   if (rc == THZ_OK && progress) progress(1.0f, progress_user);
   return rc;
+}
+
+int thz_deconv_stage_ms(const thz_ctx* c, float* ms4) {
+  if (!c || !ms4) return THZ_EINVAL;
+  for (int i = 0; i < 4; ++i) ms4[i] = c->stage_ms[i];
+  return THZ_OK;
 }
 
 int thz_deconvolution_host(thz_ctx* c, const float* cube, int rows, int cols, int n, const thz_band_plan* bands,
@@ -925,9 +956,11 @@ int thz_deconvolution_host(thz_ctx* c, const float* cube, int rows, int cols, in
   const int64_t P = (int64_t)rows * cols;
   if (P == 0) return THZ_OK;
   if (!cube || !out) return set_err(c, THZ_EINVAL, "null pointer");
-  float *d_cube = nullptr, *d_img = nullptr;
-  THZ_CUDA(c, cudaMalloc((void**)&d_cube, (size_t)P * n * sizeof(float)));
-  THZ_CUDA(c, cudaMalloc((void**)&d_img, (size_t)P * sizeof(float)));
+  void *pc = nullptr, *pi = nullptr;
+  int rcw = ws_get(c, WS_HOST_CUBE, (size_t)P * n * sizeof(float), &pc);
+  if (rcw == THZ_OK) rcw = ws_get(c, WS_HOST_IMG, (size_t)P * sizeof(float), &pi);
+  if (rcw != THZ_OK) return rcw;
+  float *d_cube = (float*)pc, *d_img = (float*)pi;
   THZ_CUDA(c, cudaMemcpyAsync(d_cube, cube, (size_t)P * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   int rc = thz_deconvolution_dev(c, d_cube, rows, cols, n, bands, n_bands, d_cube, d_img, abort_flag, progress,
                                  progress_user);
@@ -936,8 +969,6 @@ int thz_deconvolution_host(thz_ctx* c, const float* cube, int rows, int cols, in
     if (img) cudaMemcpyAsync(img, d_img, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
   }
   cudaError_t e = cudaStreamSynchronize(c->stream);
-  cudaFree(d_cube);
-  cudaFree(d_img);
   if (rc == THZ_OK && e != cudaSuccess) return cuda_fail(c, e, "thz_deconvolution_host");
   return rc;
 }

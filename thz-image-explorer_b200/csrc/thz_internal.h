@@ -41,6 +41,11 @@ struct thz_ctx {
   thz::TracePlan plan;
   std::string err;
   int64_t launches = 0;
+  std::map<int, std::pair<void*, size_t>> ws;    // grow-only device workspace slots (freed at destroy)
+  std::map<const void*, size_t> smem_set;        // largest dynamic smem opted in per kernel
+  uint64_t fir_key = 0;                          // cache key of the uploaded FIR spectra (slot WS_FIR)
+  int fir_m = 0;
+  float stage_ms[4] = {0, 0, 0, 0};              // last thz_deconvolution_dev: energies, RL, apply, RL iterations
   float* d_scratch = nullptr;                    // reductions
   size_t scratch_bytes = 0;
 };
@@ -57,6 +62,9 @@ int cuda_fail(thz_ctx* c, cudaError_t e, const char* what);
 
 int get_tables(thz_ctx* c, int n, const FftTables** out);
 int ensure_scratch(thz_ctx* c, size_t bytes);
+// grow-only workspace: returns a device buffer of at least `bytes` for `slot`
+int ws_get(thz_ctx* c, int slot, size_t bytes, void** out);
+enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG };
 
 // thz_trace.cu
 int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P);

@@ -1,0 +1,65 @@
+"""Row-slab sharding of the filter chain over the ranks of one node (one process per GPU).
+
+The cube is C-contiguous (x, y, t) with x slowest, the axis the reference parallelises over
+(src/math_tools.rs:333-340), so rank r owns the contiguous rows x in [x0, x1).  The trace
+passes (fused chain, band energies, gain application) are slab-local and need no
+communication.  The Richardson-Lucy images are W x H (tiny next to the cube): the B
+band-energy images are all-gathered, the bands are dealt round-robin to the ranks (band b on
+rank b % world, each running the full-image iteration), and the gains are summed back with
+one all-reduce.  Collectives go through torch.distributed (NCCL on GPUs, gloo in the CPU
+tests); the compute is injected through `ops` so that the same orchestration runs with
+libthzgpu on device tensors and with the oracle in the world_size-2 CPU test.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def slab_bounds(width: int, world: int, rank: int):
+    """Contiguous rows [x0, x1) of rank `rank`; the first `width % world` ranks get one more row."""
+    base, rem = divmod(width, world)
+    x0 = rank * base + min(rank, rem)
+    return x0, x0 + base + (1 if rank < rem else 0)
+
+
+def band_owner(band: int, world: int) -> int:
+    return band % world
+
+
+def gather_band_images(e_slab: torch.Tensor, width: int, height: int, dist, world: int) -> torch.Tensor:
+    """e_slab [B][rows_r * H] on every rank -> [B][W * H] on every rank (uneven slabs allowed)."""
+    B = e_slab.shape[0]
+    if world == 1:
+        return e_slab
+    counts = [(slab_bounds(width, world, r)[1] - slab_bounds(width, world, r)[0]) * height for r in range(world)]
+    mx = max(counts)
+    padded = e_slab.new_zeros((B, mx))
+    padded[:, : e_slab.shape[1]] = e_slab
+    parts = [e_slab.new_empty((B, mx)) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    full = e_slab.new_empty((B, width * height))
+    off = 0
+    for r in range(world):
+        full[:, off: off + counts[r]] = parts[r][:, : counts[r]]
+        off += counts[r]
+    return full
+
+
+def sharded_deconvolution(ops, slab, width: int, height: int, n_bands: int, dist, world: int, rank: int):
+    """Deconvolution of this rank's slab.
+
+    ops.energies(slab)            -> tensor [B][rows_r * H]
+    ops.rl_gain(band, image_WxH)  -> tensor [W * H]  (gain image of one band)
+    ops.apply(slab, gains_slab)   -> whatever the backend returns for the filtered slab
+    """
+    e_slab = ops.energies(slab)
+    e_full = gather_band_images(e_slab, width, height, dist, world)
+    g_full = torch.zeros_like(e_full)
+    for b in range(n_bands):
+        if band_owner(b, world) == rank:
+            g_full[b] = ops.rl_gain(b, e_full[b].reshape(width, height)).reshape(-1)
+    if world > 1:
+        dist.all_reduce(g_full)
+    x0, x1 = slab_bounds(width, world, rank)
+    g_slab = g_full[:, x0 * height: x1 * height].contiguous()
+    return ops.apply(slab, g_slab)
