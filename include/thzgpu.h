@@ -134,6 +134,12 @@ int thz_band_apply_dev(thz_ctx* ctx, float* d_fft, float* d_amp, int64_t P);
 int thz_trace_inverse_dev(thz_ctx* ctx, const float* d_fft, int use_band, int use_post,
                           float* d_out, float* d_img, int64_t P);
 
+/* A time-domain filter that is a pixel-independent multiplier applied on its own stage
+ * (`TiltCompensation` at 0 deg, src/filters/tilt_compensation.rs:188; the time gates,
+ * src/filters/band_pass_td_before_fft.rs:155-174): out[p][t] = in[p][t] * mult[t].  mult is a
+ * host vector of n floats; d_out may alias d_in. */
+int thz_time_multiply_dev(thz_ctx* ctx, const float* d_in, const float* mult, int n, float* d_out, int64_t P);
+
 /* Pixel means that `ifft` computes first (src/math_tools.rs:421-440): mean over all P traces
  * of fft (2F floats), amplitudes (F), phases (F).  Host outputs, any may be NULL. */
 int thz_spectral_means(thz_ctx* ctx, const float* d_fft, const float* d_amp, const float* d_phase,
@@ -206,16 +212,17 @@ int thz_deconv_energies_dev(thz_ctx* ctx, const float* d_cube, int64_t P, int n,
  * separable PSF: reflect pad, n_iter x { c = u (*) psf; r = d / (c + 1e-12); u *= r (*) mirror },
  * crop; then clamp >= 0 and, when d_gain != NULL, gain = sqrt(u / d) (:975, 990-993).
  * `direct` selects the correlation / convolution orientation of `convolve2d` (:484).
- * abort (nullable) is polled between launches; progress (nullable) is called with
+ * abort_flag (nullable) has the layout of Rust's `AtomicBool` (one byte, `abort_flag.as_ptr()`),
+ * polled between launches like the cancellable loops poll it; progress (nullable) is called with
  * progress_base + progress_span * done/n_iter. */
 int thz_rl_separable_dev(thz_ctx* ctx, const float* d_image, int rows, int cols, const float* psf_x, int kx,
                          const float* psf_y, int ky, int direct, int n_iter, float* d_deconvolved,
-                         float* d_gain, const volatile int32_t* abort_flag, thz_progress_fn progress,
+                         float* d_gain, const volatile uint8_t* abort_flag, thz_progress_fn progress,
                          void* progress_user, float progress_base, float progress_span);
 /* Same iteration for an arbitrary dense PSF psf[kx][ky] (odd extents), tiled 2-D filtering. */
 int thz_rl_dense_dev(thz_ctx* ctx, const float* d_image, int rows, int cols, const float* psf, int kx, int ky,
                      int direct, int n_iter, float* d_deconvolved, float* d_gain,
-                     const volatile int32_t* abort_flag);
+                     const volatile uint8_t* abort_flag);
 /* One "same" 2-D filtering with zero boundary, exposed for tests: out = correlate(in, psf)
  * (direct != 0, src/filters/deconvolution.rs:432-458) or convolve(in, psf) (direct == 0, :489-544). */
 int thz_conv2d_separable_dev(thz_ctx* ctx, const float* d_in, int rows, int cols, const float* psf_x, int kx,
@@ -230,7 +237,7 @@ int thz_deconv_apply_dev(thz_ctx* ctx, const float* d_cube, const float* d_gain,
  * alias d_cube.  Returns THZ_ABORTED when abort_flag became non-zero. */
 int thz_deconvolution_dev(thz_ctx* ctx, const float* d_cube, int rows, int cols, int n,
                           const thz_band_plan* bands, int n_bands, float* d_out, float* d_img,
-                          const volatile int32_t* abort_flag, thz_progress_fn progress, void* progress_user);
+                          const volatile uint8_t* abort_flag, thz_progress_fn progress, void* progress_user);
 /* CUDA-event timings of the last thz_deconvolution_dev call on this context, the per-filter
  * wall time the reference shows beside the filter header (src/data_thread.rs:1107, 1169-1184):
  * ms4 = {band energies, Richardson-Lucy, gain application, number of RL iterations run}. */
@@ -238,7 +245,7 @@ int thz_deconv_stage_ms(const thz_ctx* ctx, float* ms4);
 /* Host-pointer drop-in for `Deconvolution::filter`. */
 int thz_deconvolution_host(thz_ctx* ctx, const float* cube, int rows, int cols, int n,
                            const thz_band_plan* bands, int n_bands, float* out, float* img,
-                           const volatile int32_t* abort_flag, thz_progress_fn progress, void* progress_user);
+                           const volatile uint8_t* abort_flag, thz_progress_fn progress, void* progress_user);
 
 /* ------------------------------------------------------- trace pass, host pointers ----- */
 /* Same operators on host arrays (the reference's `ScannedImageFilterData` lives in host
@@ -248,6 +255,40 @@ int thz_trace_forward_host(thz_ctx* ctx, const float* in, float* windowed, float
                            float* phase, int64_t P);
 int thz_trace_inverse_host(thz_ctx* ctx, const float* fft, int use_band, int use_post, float* out,
                            float* img, int64_t P);
+int thz_time_multiply_host(thz_ctx* ctx, const float* in, const float* mult, int n, float* out, int64_t P);
+int thz_band_apply_host(thz_ctx* ctx, float* fft, float* amp, int64_t P);   /* in place */
+int thz_spectral_means_host(thz_ctx* ctx, const float* fft, const float* amp, const float* phase, int64_t P,
+                            float* avg_fft, float* avg_amp, float* avg_phase);
+/* img[p] = sum_t data[p][t]^2 (src/data_thread.rs:1288-1307) of a host cube */
+int thz_intensity_host(thz_ctx* ctx, const float* data, int n, float* img, int64_t P);
+
+/* ------------------------------------------------ chain driver (C++ host layer) -------- */
+/* C handle over thzhost::ChainDriver (csrc/host/thz_host.hpp), the C++ mirror of the
+ * reference's chain assembly (src/main.rs:194-268) and driver loop
+ * (src/data_thread.rs:1090-1316) with the five shipped filters registered through the
+ * `Filter` / `FilterRegistry` mirror.  Used by the Python tests to drive the chain exactly as
+ * `data_thread` does; slots follow `filter_data_pipeline` (0 = loaded scan, i + 1 = output of
+ * chain stage i). */
+typedef struct thz_chain thz_chain;
+int thz_chain_create(thz_ctx* ctx, thz_chain** out);
+void thz_chain_destroy(thz_chain* chain);
+int thz_chain_length(const thz_chain* chain);
+const char* thz_chain_stage_name(thz_chain* chain, int i);
+int thz_chain_set_config(thz_chain* chain, float window_lo, float window_hi, int window_type, int scale_factor);
+int thz_chain_set_psf(thz_chain* chain, const thz_psf* psf);               /* ConfigCommand::ApplyPSF */
+int thz_chain_set_param(thz_chain* chain, const char* filter_name, const char* param, double value);
+int thz_chain_get_param(thz_chain* chain, const char* filter_name, const char* param, double* value);
+int thz_chain_set_active(thz_chain* chain, const char* filter_name, int active);
+int thz_chain_open(thz_chain* chain, const float* time, int n, const float* data, int width, int height,
+                   int has_dxdy, float dx, float dy);                      /* ConfigCommand::OpenFile */
+int thz_chain_run(thz_chain* chain, int start_idx, int run_deconvolution); /* UpdateType::Filter(start_idx) */
+int thz_chain_run_fused(thz_chain* chain, int run_deconvolution);          /* same chain, one fused kernel */
+void thz_chain_abort(thz_chain* chain, int value);                         /* the GUI's abort button */
+int thz_chain_slot(thz_chain* chain, int slot, const float** data, const float** fft, const float** amp,
+                   const float** phase, const float** img, const float** avg_fft, const float** avg_amp,
+                   const float** avg_phase, int* n, int* f);
+int thz_chain_fused_result(thz_chain* chain, const float** data, const float** img);
+double thz_chain_filter_ms(thz_chain* chain, const char* filter_name);     /* filter_computation_time */
 
 #ifdef __cplusplus
 }

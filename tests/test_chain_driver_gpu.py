@@ -1,0 +1,118 @@
+"""The C++ host layer (thzhost::ChainDriver, the mirror of src/main.rs:194-268 chain assembly and
+the data_thread.rs:1090-1316 driver loop) against the oracle's stage-by-stage pipeline slots."""
+import numpy as np
+import pytest
+
+from helpers import (F32, TOL_MAP, TOL_TRACE, check_unwrapped_phase, orc, pkg, rel_err, slot0, synthetic_cube,
+                     time_axis)
+
+pytestmark = pytest.mark.gpu
+
+EXPECTED_ORDER = ["scaling", "Tilt Compensation", "Time Domain Band Pass (before FFT)", "fft",
+                  "Frequency Domain Band Pass", "ifft", "Time Domain Band Pass (after FFT)", "Deconvolution"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pkg().Context(0)
+    yield c
+    c.close()
+
+
+def test_chain_order_matches_reference(ctx):
+    ch = pkg().Chain(ctx)
+    assert ch.stages() == EXPECTED_ORDER     # 8 stages -> 9 pipeline slots
+    assert ch.get_param("Frequency Domain Band Pass", "low") == pytest.approx(0.2)
+    assert ch.get_param("Time Domain Band Pass (before FFT)", "window_width") == 2.0
+    assert ch.get_param("Time Domain Band Pass (after FFT)", "window_width") == pytest.approx(0.1)
+    assert ch.get_param("Deconvolution", "n_filters") == 25
+
+
+@pytest.mark.parametrize("n,dxdy", [(1024, True), (2048, False)])
+def test_stage_by_stage_slots_match_oracle(ctx, n, dxdy):
+    w, h = 6, 9
+    cube = synthetic_cube(w, h, n, seed=n)
+    t = time_axis(n)
+    slots = orc.run_default_chain(slot0(cube, t, dx=0.5 if dxdy else None, dy=0.5 if dxdy else None))
+    ch = pkg().Chain(ctx)
+    ch.open(t, cube, dx=0.5 if dxdy else None, dy=0.5 if dxdy else None)
+    ch.run(start_idx=1)
+    assert np.array_equal(ch.slot(0)["img"].shape, (w, h))
+    assert rel_err(ch.slot(0)["img"], slots[0].img) <= 1e-6
+    for i in (1, 2, 3):                       # scaling, tilt taper, gate before FFT: one f32 multiply each
+        assert np.array_equal(ch.slot(i)["data"], slots[i].data), i
+    s4 = ch.slot(4)                           # fft
+    assert np.array_equal(s4["data"], slots[4].data)
+    assert rel_err(s4["fft"], slots[4].fft) <= TOL_TRACE
+    assert rel_err(s4["amplitudes"], slots[4].amplitudes) <= TOL_TRACE
+    tol_rad = max(TOL_TRACE * float(np.abs(slots[4].phases).max()), 2e-3)
+    check_unwrapped_phase(s4["phases"], slots[4].phases, slots[4].fft, tol_rad)
+    s5 = ch.slot(5)                           # FD band-pass: fft and amplitudes scaled, phases untouched
+    assert rel_err(s5["fft"], slots[5].fft) <= TOL_TRACE
+    assert rel_err(s5["amplitudes"], slots[5].amplitudes) <= TOL_TRACE
+    assert np.array_equal(s5["phases"], s4["phases"])
+    s6 = ch.slot(6)                           # ifft (+ pixel means)
+    assert rel_err(s6["data"], slots[6].data) <= TOL_TRACE
+    assert rel_err(s6["avg_fft"], slots[6].avg_fft) <= TOL_TRACE
+    assert rel_err(s6["avg_signal_fft"], slots[6].avg_signal_fft) <= TOL_TRACE
+    s7 = ch.slot(7)                           # gate after iFFT
+    assert rel_err(s7["data"], slots[7].data) <= TOL_TRACE
+    s8 = ch.slot(8)                           # deconvolution inactive: clone of slot 7, driver's intensity image
+    assert np.array_equal(s8["data"], s7["data"])
+    assert rel_err(s8["img"], slots[7].img) <= TOL_TRACE
+    # the fused kernel gives the same last slot
+    fused, img = ch.run_fused()
+    assert rel_err(fused, s7["data"]) <= 2e-6 and rel_err(img, s8["img"]) <= 1e-5
+
+
+def test_partial_update_and_inactive_filter(ctx):
+    """UpdateType::Filter(idx) recomputes from that stage on; an inactive filter clones its input
+    (data_thread.rs:1186-1187)."""
+    n, w, h = 512, 4, 5
+    cube = synthetic_cube(w, h, n, seed=1)
+    t = time_axis(n)
+    ch = pkg().Chain(ctx)
+    ch.open(t, cube, 0.5, 0.5)
+    ch.run(1)
+    before = ch.slot(7)["data"]
+    ch.set_param("Frequency Domain Band Pass", "high", 2.0)
+    ch.run(start_idx=ch.slot_of("Frequency Domain Band Pass"))
+    after = ch.slot(7)["data"]
+    assert not np.array_equal(before, after)
+    p = orc.ChainParams()
+    p.band.high = 2.0
+    ref = orc.run_default_chain(slot0(cube, t), p)
+    assert rel_err(after, ref[7].data) <= TOL_TRACE
+    ch.set_active("Time Domain Band Pass (after FFT)", False)
+    ch.run(start_idx=ch.slot_of("Time Domain Band Pass (after FFT)"))
+    assert np.array_equal(ch.slot(7)["data"], ch.slot(6)["data"])
+
+
+def test_deconvolution_only_on_apply(ctx, psf_npz_path):
+    """The deconvolution runs only when the update starts at it (its Apply button,
+    data_thread.rs:1139-1150) and needs the filter to be active and a PSF to be loaded."""
+    m = pkg()
+    n, w, h = 256, 36, 32
+    cube = synthetic_cube(w, h, n, seed=2, noise=0.02)
+    t = time_axis(n)
+    ch = m.Chain(ctx)
+    ch.open(t, cube, 1.0, 1.0)
+    ch.set_active("Deconvolution", True)
+    ch.set_param("Deconvolution", "n_filters", 4)
+    ch.set_param("Deconvolution", "n_iterations", 10)
+    ch.run(1, run_deconvolution=True)      # an earlier filter ran first -> deconvolution is skipped
+    assert np.array_equal(ch.slot(8)["data"], ch.slot(7)["data"])
+    ch.run(ch.slot_of("Deconvolution"), run_deconvolution=True)   # no PSF loaded -> input returned
+    assert np.array_equal(ch.slot(8)["data"], ch.slot(7)["data"])
+    psf = m.host.PSF.load(psf_npz_path)
+    ch.set_psf(psf)
+    ch.run(ch.slot_of("Deconvolution"), run_deconvolution=True)
+    s7, s8 = ch.slot(7), ch.slot(8)
+    assert not np.array_equal(s8["data"], s7["data"])
+    assert ch.filter_ms("Deconvolution") > 0
+    opsf = orc.load_psf(psf_npz_path)
+    f = orc.frequency_axis(t)
+    sin = orc.ScannedImageFilterData(time=t, data=s7["data"], frequency=f, img=orc.intensity_image(s7["data"]),
+                                     dx=1.0, dy=1.0, width=w, height=h)
+    ref = orc.Deconvolution(n_filters=4, n_iterations=10).filter(sin, opsf)
+    assert rel_err(s8["data"], ref.data) <= TOL_MAP and rel_err(s8["img"], ref.img) <= TOL_MAP

@@ -137,6 +137,6 @@ def test_abort_flag_stops_the_filter(ctx, psfs):
     w, h, n = 32, 32, 256
     cube = synthetic_cube(w, h, n, seed=5)
     bands, _ = pkg().host.Deconvolution(n_filters=4, n_iterations=500).plan(time_axis(n), (w, h), 1.0, 1.0, psf)
-    flag = ctypes.c_int32(1)
+    flag = ctypes.c_uint8(1)   # layout of Rust AtomicBool
     out, img, rc = ctx.deconvolution(cube, bands, abort_flag=flag)
     assert rc == 1   # THZ_ABORTED: the shim keeps the previous slot, like the cancellable loops

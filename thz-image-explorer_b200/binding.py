@@ -35,6 +35,14 @@ def declared_symbols(header: str = HEADER):
     return sorted(set(re.findall(r"\b(thz_[a-z0-9_]+)\s*\(", txt)) - {"thz_progress_fn"})
 
 
+def _as_np(ptr, shape, dtype=np.float32):
+    n = int(np.prod(shape))
+    if n == 0 or not ptr:
+        return np.zeros(shape, dtype)
+    buf = (C.c_byte * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape).copy()
+
+
 DECLARED_SYMBOLS = declared_symbols() if os.path.exists(HEADER) else []
 
 THZ_MAX_PSF = 255
@@ -138,6 +146,27 @@ def load_library():
         "thz_deconvolution_dev": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_deconv_stage_ms": (i32, [vp, fp]),
         "thz_deconvolution_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
+        "thz_time_multiply_dev": (i32, [vp, fp, fp, i32, fp, i64]),
+        "thz_time_multiply_host": (i32, [vp, fp, fp, i32, fp, i64]),
+        "thz_band_apply_host": (i32, [vp, fp, fp, i64]),
+        "thz_spectral_means_host": (i32, [vp, fp, fp, fp, i64, fp, fp, fp]),
+        "thz_intensity_host": (i32, [vp, fp, i32, fp, i64]),
+        "thz_chain_create": (i32, [vp, C.POINTER(vp)]),
+        "thz_chain_destroy": (None, [vp]),
+        "thz_chain_length": (i32, [vp]),
+        "thz_chain_stage_name": (C.c_char_p, [vp, i32]),
+        "thz_chain_set_config": (i32, [vp, f32, f32, i32, i32]),
+        "thz_chain_set_psf": (i32, [vp, C.POINTER(PsfC)]),
+        "thz_chain_set_param": (i32, [vp, C.c_char_p, C.c_char_p, C.c_double]),
+        "thz_chain_get_param": (i32, [vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]),
+        "thz_chain_set_active": (i32, [vp, C.c_char_p, i32]),
+        "thz_chain_open": (i32, [vp, fp, i32, fp, i32, i32, i32, f32, f32]),
+        "thz_chain_run": (i32, [vp, i32, i32]),
+        "thz_chain_run_fused": (i32, [vp, i32]),
+        "thz_chain_abort": (None, [vp, i32]),
+        "thz_chain_slot": (i32, [vp, i32] + [C.POINTER(vp)] * 8 + [C.POINTER(i32), C.POINTER(i32)]),
+        "thz_chain_fused_result": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "thz_chain_filter_ms": (C.c_double, [vp, C.c_char_p]),
         "thz_trace_fused_host": (i32, [vp, fp, fp, fp, i64]),
         "thz_trace_forward_host": (i32, [vp, fp, fp, fp, fp, fp, i64]),
         "thz_trace_inverse_host": (i32, [vp, fp, i32, i32, fp, fp, i64]),
@@ -418,3 +447,89 @@ class Context:
         ms = np.zeros(4, np.float32)
         self._check(lib.thz_deconv_stage_ms(self.handle, ms.ctypes.data))
         return {"energies_ms": float(ms[0]), "rl_ms": float(ms[1]), "apply_ms": float(ms[2]), "rl_iterations": int(ms[3])}
+
+
+class Chain:
+    """Python handle over the C++ ChainDriver (the mirror of data_thread's chain loop)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._check(lib.thz_chain_create(ctx.handle, C.byref(h)))
+        self.handle = h.value
+        self.shape = (0, 0, 0)
+
+    def close(self):
+        if self.handle:
+            lib.thz_chain_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stages(self):
+        return [lib.thz_chain_stage_name(self.handle, i).decode() for i in range(lib.thz_chain_length(self.handle))]
+
+    def slot_of(self, stage_name):
+        return self.stages().index(stage_name) + 1
+
+    def set_param(self, filt, param, value):
+        self.ctx._check(lib.thz_chain_set_param(self.handle, filt.encode(), param.encode(), float(value)))
+
+    def get_param(self, filt, param):
+        v = C.c_double()
+        self.ctx._check(lib.thz_chain_get_param(self.handle, filt.encode(), param.encode(), C.byref(v)))
+        return v.value
+
+    def set_active(self, filt, active):
+        self.ctx._check(lib.thz_chain_set_active(self.handle, filt.encode(), int(active)))
+
+    def set_config(self, fft_window=(1.0, 7.0), window_type=0, scale_factor=1):
+        self.ctx._check(lib.thz_chain_set_config(self.handle, float(fft_window[0]), float(fft_window[1]),
+                                                 int(window_type), int(scale_factor)))
+
+    def set_psf(self, psf):
+        self.ctx._check(lib.thz_chain_set_psf(self.handle, C.byref(psf.c)))
+
+    def open(self, time, cube, dx=None, dy=None):
+        t = np.ascontiguousarray(time, np.float32)
+        cube = _f32c(cube)
+        w, h, n = cube.shape
+        self.shape = (w, h, n)
+        self.ctx._check(lib.thz_chain_open(self.handle, t.ctypes.data, n, cube.ctypes.data, w, h,
+                                           int(dx is not None and dy is not None), float(dx or 0), float(dy or 0)))
+
+    def run(self, start_idx=1, run_deconvolution=False):
+        self.ctx._check(lib.thz_chain_run(self.handle, int(start_idx), int(run_deconvolution)))
+
+    def run_fused(self, run_deconvolution=False):
+        self.ctx._check(lib.thz_chain_run_fused(self.handle, int(run_deconvolution)))
+        d, i = C.c_void_p(), C.c_void_p()
+        lib.thz_chain_fused_result(self.handle, C.byref(d), C.byref(i))
+        w, h, n = self.shape
+        return _as_np(d.value, (w, h, n)), _as_np(i.value, (w, h))
+
+    def abort(self, value=True):
+        lib.thz_chain_abort(self.handle, int(value))
+
+    def filter_ms(self, filt):
+        return float(lib.thz_chain_filter_ms(self.handle, filt.encode()))
+
+    def slot(self, idx):
+        p = [C.c_void_p() for _ in range(8)]
+        n, f = C.c_int(), C.c_int()
+        self.ctx._check(lib.thz_chain_slot(self.handle, int(idx), *[C.byref(x) for x in p], C.byref(n), C.byref(f)))
+        w, h, _ = self.shape
+        N, F = n.value, f.value
+        names = ["data", "fft", "amplitudes", "phases", "img", "avg_fft", "avg_signal_fft", "avg_phase_fft"]
+        shapes = [(w, h, N), (w, h, F), (w, h, F), (w, h, F), (w, h), (F,), (F,), (F,)]
+        out = {}
+        for nm, ptr, shp in zip(names, p, shapes):
+            if nm in ("fft", "avg_fft"):
+                out[nm] = _as_np(ptr.value, shp + (2,)).view(np.complex64).reshape(shp)
+            else:
+                out[nm] = _as_np(ptr.value, shp)
+        return out

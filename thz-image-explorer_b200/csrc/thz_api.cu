@@ -298,6 +298,29 @@ int thz_trace_inverse_dev(thz_ctx* c, const float* d_fft, int use_band, int use_
   return launch_trace_inverse(c, c->stream, (const float2*)d_fft, use_band != 0, use_post != 0, d_out, d_img, P);
 }
 
+static int upload_mult(thz_ctx* c, cudaStream_t s, const float* mult, int n, float** d) {
+  *d = nullptr;
+  if (!mult) return THZ_OK;
+  void* p = nullptr;
+  int rc = ws_get(c, WS_MULT, (size_t)n * sizeof(float), &p);
+  if (rc != THZ_OK) return rc;
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < kHostStreams; ++i) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[i]));
+  THZ_CUDA(c, cudaMemcpyAsync(p, mult, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s));
+  THZ_CUDA(c, cudaStreamSynchronize(s));
+  *d = (float*)p;
+  return THZ_OK;
+}
+
+int thz_time_multiply_dev(thz_ctx* c, const float* d_in, const float* mult, int n, float* d_out, int64_t P) {
+  CHECK_CTX(c);
+  if (!d_in || !d_out || n <= 0) return set_err(c, THZ_EINVAL, "bad argument");
+  float* d_m = nullptr;
+  int rc = upload_mult(c, c->stream, mult, n, &d_m);
+  if (rc != THZ_OK) return rc;
+  return launch_time_multiply(c, c->stream, d_in, d_m, n, d_out, P, nullptr);
+}
+
 int thz_spectral_means(thz_ctx* c, const float* d_fft, const float* d_amp, const float* d_phase, int64_t P,
                        float* avg_fft, float* avg_amp, float* avg_phase) {
   CHECK_CTX(c);
@@ -428,6 +451,107 @@ int thz_trace_inverse_host(thz_ctx* c, const float* fft, int use_band, int use_p
     if (img) THZ_CUDA(c, cudaMemcpyAsync(img + p, d_img, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
   for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
+  return THZ_OK;
+}
+
+// elementwise stages on host arrays: chunked over the three pipeline streams
+static int elementwise_host(thz_ctx* c, const float* in, float* out, float* img, int64_t P, int n, const float* d_mult) {
+  const int64_t ct = chunk_traces(n, n + 1);
+  int rc = ensure_stage(c, (size_t)ct * (n + 1) * sizeof(float));
+  if (rc != THZ_OK) return rc;
+  int i = 0;
+  for (int64_t p = 0; p < P; p += ct, ++i) {
+    const int64_t np = std::min(ct, P - p);
+    const int k = i % kHostStreams;
+    cudaStream_t s = c->hstream[k];
+    float* d_buf = (float*)c->d_stage[k];
+    float* d_img = d_buf + (size_t)ct * n;
+    THZ_CUDA(c, cudaMemcpyAsync(d_buf, in + p * n, (size_t)np * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = launch_time_multiply(c, s, d_buf, d_mult, n, out ? d_buf : nullptr, np, img ? d_img : nullptr);
+    if (rc != THZ_OK) return rc;
+    if (out) THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d_buf, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (img) THZ_CUDA(c, cudaMemcpyAsync(img + p, d_img, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
+  return THZ_OK;
+}
+
+int thz_time_multiply_host(thz_ctx* c, const float* in, const float* mult, int n, float* out, int64_t P) {
+  CHECK_CTX(c);
+  if (P == 0) return THZ_OK;
+  if (!in || !out || n <= 0 || n % 4) return set_err(c, THZ_EINVAL, "bad argument");
+  float* d_m = nullptr;
+  int rc = upload_mult(c, c->stream, mult, n, &d_m);
+  if (rc != THZ_OK) return rc;
+  return elementwise_host(c, in, out, nullptr, P, n, d_m);
+}
+
+int thz_intensity_host(thz_ctx* c, const float* data, int n, float* img, int64_t P) {
+  CHECK_CTX(c);
+  if (P == 0) return THZ_OK;
+  if (!data || !img || n <= 0 || n % 4) return set_err(c, THZ_EINVAL, "bad argument");
+  return elementwise_host(c, data, nullptr, img, P, n, nullptr);
+}
+
+int thz_band_apply_host(thz_ctx* c, float* fft, float* amp, int64_t P) {
+  CHECK_CTX(c);
+  if (c->plan.n == 0) return set_err(c, THZ_ESTATE, "thz_plan_trace has not been called");
+  if (P == 0) return THZ_OK;
+  const int F = c->plan.n / 2 + 1;
+  const int per = 3 * F;
+  const int64_t ct = chunk_traces(c->plan.n, per);
+  int rc = ensure_stage(c, (size_t)ct * per * sizeof(float));
+  if (rc != THZ_OK) return rc;
+  int i = 0;
+  for (int64_t p = 0; p < P; p += ct, ++i) {
+    const int64_t np = std::min(ct, P - p);
+    const int k = i % kHostStreams;
+    cudaStream_t s = c->hstream[k];
+    float* d_fft = (float*)c->d_stage[k];
+    float* d_amp = d_fft + (size_t)ct * 2 * F;
+    if (fft) THZ_CUDA(c, cudaMemcpyAsync(d_fft, fft + p * 2 * F, (size_t)np * 2 * F * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (amp) THZ_CUDA(c, cudaMemcpyAsync(d_amp, amp + p * F, (size_t)np * F * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = launch_band_apply(c, s, fft ? (float2*)d_fft : nullptr, amp ? d_amp : nullptr, np);
+    if (rc != THZ_OK) return rc;
+    if (fft) THZ_CUDA(c, cudaMemcpyAsync(fft + p * 2 * F, d_fft, (size_t)np * 2 * F * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (amp) THZ_CUDA(c, cudaMemcpyAsync(amp + p * F, d_amp, (size_t)np * F * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
+  return THZ_OK;
+}
+
+int thz_spectral_means_host(thz_ctx* c, const float* fft, const float* amp, const float* phase, int64_t P,
+                            float* avg_fft, float* avg_amp, float* avg_phase) {
+  CHECK_CTX(c);
+  if (c->plan.n == 0) return set_err(c, THZ_ESTATE, "thz_plan_trace has not been called");
+  if (P <= 0) return set_err(c, THZ_EINVAL, "P must be positive");
+  const int F = c->plan.n / 2 + 1;
+  const int nb = c->sm_count * 2;
+  struct Job { const float* h; int cols; float* out; };
+  Job jobs[3] = {{fft, 2 * F, avg_fft}, {amp, F, avg_amp}, {phase, F, avg_phase}};
+  int rc = ensure_scratch(c, (size_t)nb * 2 * F * sizeof(float));
+  if (rc != THZ_OK) return rc;
+  std::vector<float> part((size_t)nb * 2 * F);
+  for (const Job& j : jobs) {
+    if (!j.h || !j.out) continue;
+    const int64_t ct = chunk_traces(c->plan.n, j.cols);
+    rc = ensure_stage(c, (size_t)ct * j.cols * sizeof(float));
+    if (rc != THZ_OK) return rc;
+    std::vector<double> acc(j.cols, 0.0);
+    for (int64_t p = 0; p < P; p += ct) {
+      const int64_t np = std::min(ct, P - p);
+      float* d_buf = (float*)c->d_stage[0];
+      THZ_CUDA(c, cudaMemcpyAsync(d_buf, j.h + p * j.cols, (size_t)np * j.cols * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      const int nbb = (int)std::min<int64_t>(nb, np);
+      rc = launch_column_sums(c, c->stream, d_buf, np, j.cols, c->d_scratch, nbb);
+      if (rc != THZ_OK) return rc;
+      THZ_CUDA(c, cudaMemcpyAsync(part.data(), c->d_scratch, (size_t)nbb * j.cols * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+      for (int b = 0; b < nbb; ++b)
+        for (int col = 0; col < j.cols; ++col) acc[col] += (double)part[(size_t)b * j.cols + col];
+    }
+    for (int col = 0; col < j.cols; ++col) j.out[col] = (float)(acc[col] / (double)P);
+  }
   return THZ_OK;
 }
 

@@ -799,7 +799,7 @@ int conv2d_once(thz_ctx* c, cudaStream_t s, const float* d_in, int rows, int col
 
 int richardson_lucy(thz_ctx* c, cudaStream_t s, const float* d_image, int rows, int cols, const float* psf_x, int kx,
                     const float* psf_y, int ky, const float* dense, int direct, int n_iter, float* d_deconv,
-                    float* d_gain, const volatile int32_t* abort_flag, thz_progress_fn progress, void* puser,
+                    float* d_gain, const volatile uint8_t* abort_flag, thz_progress_fn progress, void* puser,
                     float pbase, float pspan) {
   if (!d_image || rows < 2 || cols < 2) return set_err(c, THZ_EINVAL, "bad image");
   const int pad_y = kx / 2, pad_x = ky / 2;   // psf.nrows()/2 pads axis 0 (deconvolution.rs:629-631)
@@ -873,7 +873,7 @@ int thz_deconv_apply_dev(thz_ctx* c, const float* d_cube, const float* d_gain, i
 
 int thz_rl_separable_dev(thz_ctx* c, const float* d_image, int rows, int cols, const float* psf_x, int kx,
                          const float* psf_y, int ky, int direct, int n_iter, float* d_deconvolved, float* d_gain,
-                         const volatile int32_t* abort_flag, thz_progress_fn progress, void* progress_user,
+                         const volatile uint8_t* abort_flag, thz_progress_fn progress, void* progress_user,
                          float progress_base, float progress_span) {
   CHECK_CTX(c);
   if (!psf_x || !psf_y) return set_err(c, THZ_EINVAL, "null PSF");
@@ -882,7 +882,7 @@ int thz_rl_separable_dev(thz_ctx* c, const float* d_image, int rows, int cols, c
 }
 
 int thz_rl_dense_dev(thz_ctx* c, const float* d_image, int rows, int cols, const float* psf, int kx, int ky, int direct,
-                     int n_iter, float* d_deconvolved, float* d_gain, const volatile int32_t* abort_flag) {
+                     int n_iter, float* d_deconvolved, float* d_gain, const volatile uint8_t* abort_flag) {
   CHECK_CTX(c);
   if (!psf) return set_err(c, THZ_EINVAL, "null PSF");
   return richardson_lucy(c, c->stream, d_image, rows, cols, nullptr, kx, nullptr, ky, psf, direct, n_iter,
@@ -904,7 +904,7 @@ int thz_conv2d_dense_dev(thz_ctx* c, const float* d_in, int rows, int cols, cons
 }
 
 int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, int n, const thz_band_plan* bands,
-                          int n_bands, float* d_out, float* d_img, const volatile int32_t* abort_flag,
+                          int n_bands, float* d_out, float* d_img, const volatile uint8_t* abort_flag,
                           thz_progress_fn progress, void* progress_user) {
   CHECK_CTX(c);
   if (!bands || n_bands < 1 || n_bands > THZ_MAX_BANDS) return set_err(c, THZ_EINVAL, "bad band count");
@@ -950,7 +950,7 @@ int thz_deconv_stage_ms(const thz_ctx* c, float* ms4) {
 }
 
 int thz_deconvolution_host(thz_ctx* c, const float* cube, int rows, int cols, int n, const thz_band_plan* bands,
-                           int n_bands, float* out, float* img, const volatile int32_t* abort_flag,
+                           int n_bands, float* out, float* img, const volatile uint8_t* abort_flag,
                            thz_progress_fn progress, void* progress_user) {
   CHECK_CTX(c);
   const int64_t P = (int64_t)rows * cols;

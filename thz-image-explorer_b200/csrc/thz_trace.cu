@@ -406,6 +406,34 @@ __global__ void k_band_apply(float2* __restrict__ fft, float* __restrict__ amp, 
   }
 }
 
+// out[p][t] = in[p][t] * mult[t] (mult may be null = ones); optional img[p] = sum_t out^2.
+// One warp per trace, 128-bit accesses.
+__global__ void k_time_multiply(const float* __restrict__ in, const float* __restrict__ mult, int n,
+                                float* __restrict__ out, int64_t P, float* __restrict__ img) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < P; p += nwarps) {
+    const float4* src = reinterpret_cast<const float4*>(in + p * n);
+    float4* dst = out ? reinterpret_cast<float4*>(out + p * n) : nullptr;
+    float acc = 0.f;
+    for (int q = lane; q < n / 4; q += 32) {
+      float4 v = __ldcs(src + q);
+      if (mult) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mult) + q);
+        v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+      }
+      if (dst) __stcs(dst + q, v);
+      acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    }
+    if (img) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) img[p] = acc;
+    }
+  }
+}
+
 // partial column sums of x[rows][cols]: block b sums rows [b*rpb, (b+1)*rpb) sequentially
 __global__ void k_column_sums(const float* __restrict__ x, int64_t rows, int cols, float* __restrict__ partials) {
   const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
@@ -672,6 +700,20 @@ int launch_band_apply(thz_ctx* c, cudaStream_t s, float2* d_fft, float* d_amp, i
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(c, e, "k_band_apply launch");
+  return THZ_OK;
+}
+
+int launch_time_multiply(thz_ctx* c, cudaStream_t s, const float* d_in, const float* d_mult, int n, float* d_out,
+                         int64_t P, float* d_img) {
+  if (n % 4 != 0) return set_err(c, THZ_EINVAL, "n must be a multiple of 4");
+  if (P == 0) return THZ_OK;
+  int64_t blocks = (P * 32 + 255) / 256;
+  const int64_t cap = (int64_t)c->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  k_time_multiply<<<(unsigned)blocks, 256, 0, s>>>(d_in, d_mult, n, d_out, P, d_img);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_time_multiply launch");
   return THZ_OK;
 }
 
