@@ -39,10 +39,11 @@ def test_stage_by_stage_slots_match_oracle(ctx, n, dxdy):
     ch.run(start_idx=1)
     assert np.array_equal(ch.slot(0)["img"].shape, (w, h))
     assert rel_err(ch.slot(0)["img"], slots[0].img) <= 1e-6
-    for i in (1, 2, 3):                       # scaling, tilt taper, gate before FFT: one f32 multiply each
-        assert np.array_equal(ch.slot(i)["data"], slots[i].data), i
+    assert np.array_equal(ch.slot(1)["data"], slots[1].data)   # scaling (s = 1): clone
+    for i in (2, 3):                          # tilt taper, gate before FFT: one f32 multiply each; the taper
+        assert rel_err(ch.slot(i)["data"], slots[i].data) <= 1e-6, i   # vectors may differ by 1 ulp (cosf)
     s4 = ch.slot(4)                           # fft
-    assert np.array_equal(s4["data"], slots[4].data)
+    assert rel_err(s4["data"], slots[4].data) <= 1e-6
     assert rel_err(s4["fft"], slots[4].fft) <= TOL_TRACE
     assert rel_err(s4["amplitudes"], slots[4].amplitudes) <= TOL_TRACE
     tol_rad = max(TOL_TRACE * float(np.abs(slots[4].phases).max()), 2e-3)
