@@ -48,6 +48,10 @@ struct FirArgs {
   float* out;            // [P][N]                 (pass C)
   float* img;            // [P] or null            (pass C)
   const float2* tw;
+  const float* wq;       // [B][M/2] |H_b|^2 / M for the lower-half bins, register order   (pass A, Parseval)
+  const float* wnyq;     // [B]      |H_b[M/2]|^2 / M
+  const float2* edge;    // [2][B][512] spectra / 512 of the first / last 249 taps, register order (edges)
+  const float2* tw512;
 };
 
 template <int M>
@@ -148,6 +152,216 @@ __global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_energy
         // an all-zero trace has exactly zero band energy in the reference (-> NaN gain, quirk 10)
         if (act0) a.energy[(size_t)b * a.P + p0] = z0 ? 0.f : s0;
         if (act1) a.energy[(size_t)b * a.P + p0 + 1] = z1 ? 0.f : s1;
+      }
+    }
+  }
+}
+
+
+// ---- pass A, fast form: Parseval total energy ------------------------------------------------
+// E_b = sum_{k in [249, N+249)} y_b[k]^2 with y_b = h_b * x the FULL linear convolution (N + 498
+// samples).  For M >= N + 498 the total energy is (1/M) sum_f |H_b[f]|^2 |X[f]|^2 (no circular
+// aliasing), so one forward transform per pair and B weighted sums replace B inverse transforms;
+// the 2 x 249 excluded samples are subtracted by k_fir_edges.  With two traces packed as
+// Z = X1 + i X2 and W symmetric: for 0 < f < M/2, p = (|Z[f]|^2 + |Z[M-f]|^2)/2, c = Re(Z[f] Z[M-f]);
+// for f in {0, M/2}, p = |Z|^2/2, c = (Re^2 - Im^2)/2; then E1 += W[f] (p + c), E2 += W[f] (p - c).
+template <int M>
+__global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_energy_total(const FirArgs a) {
+  using GEO = DGeo<M>;
+  constexpr int T = GEO::T, G = GEO::G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(M));
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(M);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<M>::ns - 1;
+  constexpr int RL = Plan<M>::r[LAST];
+  constexpr int UL = kE / RL;
+  constexpr int NLOW = kE / 2;            // registers with last-stage digit m < RL/2 hold bins < M/2
+  constexpr int W = (T < 32) ? T : 32;
+  constexpr int NW = (T + 31) / 32;
+  static_assert(RL >= 2, "last stage radix");
+  unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
+  float* red = reinterpret_cast<float*>(sm);   // the transform buffer is free during the reduction
+  int parity = 0;
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
+    const int64_t p0 = (item * G + g) * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    float2 z[kE];
+    bool nz0, nz1, z0, z1;
+    load_padded_pair<M>(z, a, t, act0, act1, p0, nz0, nz1);
+    nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
+    fft_forward<M>(z, t, sm, a.tw);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<M>(stage_elem<M, LAST>(t, i)))] = z[i];
+    __syncthreads();
+    nz_resolve<T>(g, parity, nzbuf, z0, z1);
+    // per lower-half register: q1 = p + c, q2 = p - c
+    float q1[NLOW], q2[NLOW];
+#pragma unroll
+    for (int j = 0; j < NLOW; ++j) {
+      // lower-half registers are i = u + UL * m with m < RL/2, enumerated as j = u + UL * m
+      const int i = j;                      // (u, m) -> u + UL*m keeps the same numbering for m < RL/2
+      const int f = pos_to_bin<M>(stage_elem<M, LAST>(t, i));
+      const float2 zz = z[i];
+      if (f == 0) {
+        q1[j] = zz.x * zz.x;
+        q2[j] = zz.y * zz.y;
+      } else {
+        const float2 zp = sm[pad_idx(M - f)];
+        const float p = 0.5f * (zz.x * zz.x + zz.y * zz.y + zp.x * zp.x + zp.y * zp.y);
+        const float c = zz.x * zp.x - zz.y * zp.y;
+        q1[j] = p + c;
+        q2[j] = p - c;
+      }
+    }
+    // Nyquist bin M/2 lives in register (u = 0, m = RL/2) of thread beta = 0
+    float ny1 = 0.f, ny2 = 0.f;
+    if (t == 0) {
+      const float2 zz = z[UL * (RL / 2)];
+      ny1 = zz.x * zz.x;
+      ny2 = zz.y * zz.y;
+    }
+    __syncthreads();   // all partner reads done: the buffer becomes reduction scratch
+    for (int b0 = 0; b0 < a.B; b0 += 4) {
+      float e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const int b = b0 + bb;
+        if (b < a.B) {
+          const float* wq = a.wq + (size_t)b * (M / 2);
+#pragma unroll
+          for (int j = 0; j < NLOW; ++j) {
+            const int u = j % UL, m = j / UL;
+            const float w = __ldg(wq + m * (M / RL) + t + u * T);
+            e1[bb] = fmaf(w, q1[j], e1[bb]);
+            e2[bb] = fmaf(w, q2[j], e2[bb]);
+          }
+          if (t == 0) {
+            const float w = __ldg(a.wnyq + b);
+            e1[bb] = fmaf(w, ny1, e1[bb]);
+            e2[bb] = fmaf(w, ny2, e2[bb]);
+          }
+        }
+      }
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) {
+          e1[bb] += __shfl_xor_sync(0xffffffffu, e1[bb], o);
+          e2[bb] += __shfl_xor_sync(0xffffffffu, e2[bb], o);
+        }
+      }
+      if constexpr (T > 32) {
+        if ((t & 31) == 0) {
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            red[((t >> 5) * 4 + bb) * 2] = e1[bb];
+            red[((t >> 5) * 4 + bb) * 2 + 1] = e2[bb];
+          }
+        }
+        __syncthreads();
+        if (t < 8) {   // thread t sums (band t/2, trace t%2) over the warps
+          float acc = 0.f;
+          for (int w = 0; w < NW; ++w) acc += red[(w * 4 + (t >> 1)) * 2 + (t & 1)];
+          const int b = b0 + (t >> 1);
+          const bool second = (t & 1) != 0;
+          if (b < a.B && (second ? act1 : act0))
+            a.energy[(size_t)b * a.P + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : acc;
+        }
+        __syncthreads();
+      } else {
+        if (t == 0) {
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            const int b = b0 + bb;
+            if (b < a.B) {
+              if (act0) a.energy[(size_t)b * a.P + p0] = z0 ? 0.f : e1[bb];
+              if (act1) a.energy[(size_t)b * a.P + p0 + 1] = z1 ? 0.f : e2[bb];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- pass A, edges: subtract the energy of the 2 x 249 samples outside the "same" window -----------
+// head: y[k], k < 249 = first 249 outputs of conv(x[0..249), h_b[0..249)); tail: last 249 outputs of
+// conv(x[N-249..N), h_b[250..499)).  Both are length-497 linear convolutions: exact in a 512-point
+// circular transform.  One group of 32 threads (one warp) per trace pair; both edges in sequence.
+__global__ void __launch_bounds__(256, 2) k_fir_edges(const FirArgs a) {
+  constexpr int M = 512;
+  using GEO = DGeo<M>;
+  constexpr int T = GEO::T, G = GEO::G;   // 32 threads per pair, 8 pairs per CTA
+  static_assert(T == 32, "one warp per pair");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(M);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<M>::ns - 1;
+  constexpr int RL = Plan<M>::r[LAST];
+  constexpr int UL = kE / RL;
+  constexpr int kSeg = (THZ_FIR_TAPS - 1) / 2;   // 249
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t p0 = (item * G + g) * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    for (int edge = 0; edge < 2; ++edge) {
+      const int off = edge ? a.n - kSeg : 0;
+      const float* r0 = a.x + p0 * a.n + off;
+      const float* r1 = r0 + a.n;
+      float2 z[kE];
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        const int e = t + i * T;
+        const bool in = e < kSeg;
+        z[i].x = (act0 && in) ? __ldg(r0 + e) : 0.f;
+        z[i].y = (act1 && in) ? __ldg(r1 + e) : 0.f;
+      }
+      fft_forward<M>(z, t, sm, a.tw512);
+      const int lo = edge ? kSeg - 1 : 0, hi = edge ? 2 * kSeg - 1 : kSeg;   // kept outputs [lo, hi)
+      for (int b = 0; b < a.B; ++b) {
+        const float2* hq = a.edge + ((size_t)edge * a.B + b) * M;
+        float2 w[kE];
+#pragma unroll
+        for (int i = 0; i < kE; ++i) {
+          const int u = i % UL, m = i / UL;
+          w[i] = cmul(z[i], __ldg(hq + m * (M / RL) + t + u * T));
+        }
+        fft_inverse<M>(w, t, sm, a.tw512);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kE; ++i) {
+          const int e = t + i * T;
+          if (e >= lo && e < hi) {
+            s0 = fmaf(w[i].x, w[i].x, s0);
+            s1 = fmaf(w[i].y, w[i].y, s1);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (t == 0) {   // only this warp touches the pair's entries; exact zeros (dead pixels) stay zero
+          if (act0) {
+            float* e = a.energy + (size_t)b * a.P + p0;
+            const float v = *e;
+            if (v != 0.f) *e = fmaxf(v - s0, 0.f);
+          }
+          if (act1) {
+            float* e = a.energy + (size_t)b * a.P + p0 + 1;
+            const float v = *e;
+            if (v != 0.f) *e = fmaxf(v - s1, 0.f);
+          }
+        }
       }
     }
   }
@@ -513,7 +727,48 @@ static int build_fir_hq(int m, const float* fir, std::vector<float>& hq) {
 struct FirTables {
   int m = 0, B = 0;
   float* d_hq = nullptr;   // workspace slot WS_FIR, cached across calls while the taps do not change
+  float* d_wq = nullptr;   // [B][m/2]
+  float* d_wnyq = nullptr; // [B]
+  float2* d_edge = nullptr;// [2][B][512]
 };
+
+// spectra / 512 of the first (edge 0) and last (edge 1) 249 taps at 512 points, register order of Plan<512>
+static void build_edge_tables(const float* fir, std::vector<float2>& head, std::vector<float2>& tail) {
+  const int M = 512, seg = (THZ_FIR_TAPS - 1) / 2;
+  int ns, r[4];
+  plan_of_m(M, ns, r);
+  const int RLs = r[ns - 1];
+  std::vector<double> ct(M), st(M);
+  for (int i = 0; i < M; ++i) {
+    ct[i] = cos(2.0 * M_PI * i / M);
+    st[i] = sin(2.0 * M_PI * i / M);
+  }
+  head.assign(M, make_float2(0.f, 0.f));
+  tail.assign(M, make_float2(0.f, 0.f));
+  for (int beta = 0; beta < M / RLs; ++beta)
+    for (int mm = 0; mm < RLs; ++mm) {
+      int p = beta * RLs + mm, k = 0, w = 1, L = M;
+      for (int s2 = 0; s2 < ns; ++s2) {
+        const int S = L / r[s2];
+        const int q = p / S;
+        p -= q * S;
+        k += q * w;
+        w *= r[s2];
+        L = S;
+      }
+      double hr = 0, hi = 0, tr = 0, ti = 0;
+      for (int j = 0; j < seg; ++j) {
+        const int idx = (int)(((long)j * k) & (M - 1));
+        hr += (double)fir[j] * ct[idx];
+        hi -= (double)fir[j] * st[idx];
+        tr += (double)fir[seg + 1 + j] * ct[idx];
+        ti -= (double)fir[seg + 1 + j] * st[idx];
+      }
+      const size_t o = (size_t)mm * (M / RLs) + beta;
+      head[o] = make_float2((float)(hr / M), (float)(hi / M));
+      tail[o] = make_float2((float)(tr / M), (float)(ti / M));
+    }
+}
 
 static uint64_t fnv1a(const void* p, size_t n, uint64_t h) {
   const unsigned char* b = (const unsigned char*)p;
@@ -532,16 +787,35 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
   for (int b = 0; b < B; ++b) key = fnv1a(bands[b].fir, sizeof(bands[b].fir), key);
   key = fnv1a(&m, sizeof m, key);
   void* dp = nullptr;
-  int rc = ws_get(c, WS_FIR, (size_t)B * m * sizeof(float), &dp);
+  // layout (floats): hq [B][m] | wq [B][m/2] | wnyq [B, padded to 4] | edge [2][B][512] float2
+  const size_t n_hq = (size_t)B * m, n_wq = (size_t)B * (m / 2), n_ny = (size_t)((B + 3) & ~3);
+  const size_t n_edge = (size_t)2 * B * 512 * 2;
+  int rc = ws_get(c, WS_FIR, (n_hq + n_wq + n_ny + n_edge) * sizeof(float), &dp);
   if (rc != THZ_OK) return rc;
   ft.d_hq = (float*)dp;
+  ft.d_wq = ft.d_hq + n_hq;
+  ft.d_wnyq = ft.d_wq + n_wq;
+  ft.d_edge = reinterpret_cast<float2*>(ft.d_wnyq + n_ny);
   ft.m = m;
   ft.B = B;
   if (c->fir_key == key && c->fir_m == m) return THZ_OK;
-  std::vector<float> all((size_t)B * m), one;
+  std::vector<float> all(n_hq + n_wq + n_ny + n_edge, 0.f), one;
+  const int RLs = r[ns - 1];
   for (int b = 0; b < B; ++b) {
     if (build_fir_hq(m, bands[b].fir, one) != THZ_OK) return set_err(c, THZ_EINVAL, "bad FIR transform size");
     std::copy(one.begin(), one.end(), all.begin() + (size_t)b * m);
+    // Parseval weights |H|^2 / m = (H/m)^2 * m for the lower-half registers (last-stage digit < RL/2):
+    // they are the first m/2 entries of the [digit][beta] register-order table
+    for (int i = 0; i < m / 2; ++i) all[n_hq + (size_t)b * (m / 2) + i] = one[i] * one[i] * (float)m;
+    // Nyquist bin: register (digit RL/2, beta 0)
+    const float hn = one[(size_t)(RLs / 2) * (m / RLs)];
+    all[n_hq + n_wq + b] = hn * hn * (float)m;
+    std::vector<float2> head, tail;
+    build_edge_tables(bands[b].fir, head, tail);
+    float* eh = all.data() + n_hq + n_wq + n_ny + ((size_t)0 * B + b) * 512 * 2;
+    float* et = all.data() + n_hq + n_wq + n_ny + ((size_t)1 * B + b) * 512 * 2;
+    memcpy(eh, head.data(), 512 * sizeof(float2));
+    memcpy(et, tail.data(), 512 * sizeof(float2));
   }
   THZ_CUDA(c, cudaStreamSynchronize(s));   // no kernel still reads the previous spectra
   THZ_CUDA(c, cudaMemcpyAsync(ft.d_hq, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -584,6 +858,9 @@ template <int M> static int do_energy(thz_ctx* c, cudaStream_t s, const FirArgs&
 template <int M> static int do_apply(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
   return launch_fir<M>(c, s, k_fir_apply<M>, a);
 }
+template <int M> static int do_energy_total(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
+  return launch_fir<M>(c, s, k_fir_energy_total<M>, a);
+}
 
 #define THZ_DISPATCH_M(m, FN, ...)                 \
   switch (m) {                                     \
@@ -600,6 +877,9 @@ template <int M> static int do_apply(thz_ctx* c, cudaStream_t s, const FirArgs& 
 
 static int dispatch_energy(thz_ctx* c, cudaStream_t s, int m, const FirArgs& a) { THZ_DISPATCH_M(m, do_energy, c, s, a); }
 static int dispatch_apply(thz_ctx* c, cudaStream_t s, int m, const FirArgs& a) { THZ_DISPATCH_M(m, do_apply, c, s, a); }
+static int dispatch_energy_total(thz_ctx* c, cudaStream_t s, int m, const FirArgs& a) {
+  THZ_DISPATCH_M(m, do_energy_total, c, s, a);
+}
 
 int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
                     int B, float* d_energy) {
@@ -614,7 +894,18 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
   if (rc == THZ_OK) {
     FirArgs a{};
     a.x = d_cube; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.energy = d_energy; a.tw = tb->d_tw;
-    rc = dispatch_energy(c, s, ft.m, a);
+    a.wq = ft.d_wq; a.wnyq = ft.d_wnyq; a.edge = ft.d_edge;
+    if (n >= 512 && ft.m >= n + THZ_FIR_TAPS - 1) {
+      // Parseval total energy of the full linear convolution minus the two excluded edge segments
+      const FftTables* tb512 = nullptr;
+      rc = get_tables(c, 512, &tb512);
+      if (rc != THZ_OK) return rc;
+      a.tw512 = tb512->d_tw;
+      rc = dispatch_energy_total(c, s, ft.m, a);
+      if (rc == THZ_OK) rc = launch_fir<512>(c, s, k_fir_edges, a);
+    } else {
+      rc = dispatch_energy(c, s, ft.m, a);   // short traces: B inverse transforms per pair
+    }
   }
   return rc;
 }
