@@ -52,6 +52,12 @@ struct FirArgs {
   const float* wnyq;     // [B]      |H_b[M/2]|^2 / M
   const float2* edge;    // [2][B][512] spectra / 512 of the first / last 249 taps, register order (edges)
   const float2* tw512;
+  // split form (M = 2N as two N-point sub-spectra, even and odd bins), all in Plan<N> register order
+  const float* he;       // [B][N]   H_b[2j]   / M
+  const float* ho;       // [B][N]   H_b[2j+1] / M
+  const float* we;       // [B][N/2] |H_b[2j]|^2   / M, lower-half registers
+  const float* wo;       // [B][N/2] |H_b[2j+1]|^2 / M
+  const float2* mod;     // [N] exp(-2 pi i n / M): modulation that selects the odd bins
 };
 
 template <int M>
@@ -285,6 +291,324 @@ __global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_energy
             }
           }
         }
+      }
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------
+// Split form of the zero-padded M = 2N transform.  The trace occupies [0, N) of the M-point
+// frame, so   X[2j]   = FFT_N(x)[j]               (even bins)
+//             X[2j+1] = FFT_N(x * w_M^n)[j]       (odd bins, w_M = exp(-2 pi i / M))
+// and for the outputs n < N:  y[n] = (inv_N(Y_even)[n] + conj(w_M^n) inv_N(Y_odd)[n]) / M.
+// Mirror bins stay inside each sub-spectrum: M - 2j = 2 ((N - j) mod N), M - (2j+1) = 2 (N-1-j) + 1.
+// Everything therefore runs in the 256-thread N-point geometry of the trace pass (2 CTAs per SM)
+// instead of one 512-thread CTA per SM for a monolithic 8192-point transform.
+// ------------------------------------------------------------------------------------
+template <int N> struct SGeo {
+  static constexpr int T = N / kE;
+  static constexpr int NT = (T >= 256) ? T : 256;
+  static constexpr int G = NT / T;
+  static constexpr int kScr = (32 + kNzWords) * G;
+  static constexpr size_t smem_bytes = (size_t)G * padded_len(N) * sizeof(float2) + kScr * sizeof(float);
+  static constexpr int kMinBlocks = (NT == 256) ? 2 : 1;
+};
+
+template <int N>
+__device__ __forceinline__ void load_pair_n(float2 (&v)[kE], const float* x, int t, bool act0, bool act1, int64_t p0,
+                                            bool& nz0, bool& nz1) {
+  constexpr int T = SGeo<N>::T;
+  const float* r0 = x + p0 * N + t;
+  const float* r1 = r0 + N;
+  nz0 = nz1 = false;
+#pragma unroll
+  for (int i = 0; i < kE; ++i) {
+    v[i].x = act0 ? __ldg(r0 + i * T) : 0.f;   // read twice per item (even and odd pass): keep it cacheable
+    v[i].y = act1 ? __ldg(r1 + i * T) : 0.f;
+    nz0 |= (v[i].x != 0.f);
+    nz1 |= (v[i].y != 0.f);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void modulate(float2 (&v)[kE], const float2* __restrict__ mod, int t) {
+  constexpr int T = SGeo<N>::T;
+#pragma unroll
+  for (int i = 0; i < kE; ++i) v[i] = cmul(v[i], __ldg(mod + t + i * T));
+}
+
+// q1 = p + c, q2 = p - c for the lower-half registers of one sub-spectrum (see k_fir_energy_total)
+template <int N, bool ODD>
+__device__ __forceinline__ void parseval_terms(const float2 (&z)[kE], const float2* sm, int t, float (&q1)[kE / 2],
+                                               float (&q2)[kE / 2]) {
+  constexpr int LAST = Plan<N>::ns - 1;
+#pragma unroll
+  for (int j = 0; j < kE / 2; ++j) {
+    const int f = pos_to_bin<N>(stage_elem<N, LAST>(t, j));
+    const float2 zz = z[j];
+    if (!ODD && f == 0) {
+      q1[j] = zz.x * zz.x;
+      q2[j] = zz.y * zz.y;
+    } else {
+      const float2 zp = sm[pad_idx(ODD ? (N - 1 - f) : (N - f))];
+      const float p = 0.5f * (zz.x * zz.x + zz.y * zz.y + zp.x * zp.x + zp.y * zp.y);
+      const float c = zz.x * zp.x - zz.y * zp.y;
+      q1[j] = p + c;
+      q2[j] = p - c;
+    }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy_split(const FirArgs a) {
+  using GEO = SGeo<N>;
+  constexpr int T = GEO::T, G = GEO::G;
+  constexpr int M = 2 * N;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(N));
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(N);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<N>::ns - 1;
+  constexpr int RL = Plan<N>::r[LAST];
+  constexpr int UL = kE / RL;
+  constexpr int NLOW = kE / 2;
+  constexpr int W = (T < 32) ? T : 32;
+  constexpr int NW = (T + 31) / 32;
+  unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
+  float* red = reinterpret_cast<float*>(sm);
+  int parity = 0;
+  (void)M;
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
+    const int64_t p0 = (item * G + g) * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    float2 z[kE];
+    bool nz0, nz1, z0, z1;
+    float q1e[NLOW], q2e[NLOW], q1o[NLOW], q2o[NLOW];
+    // even bins
+    load_pair_n<N>(z, a.x, t, act0, act1, p0, nz0, nz1);
+    nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
+    fft_forward<N>(z, t, sm, a.tw);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
+    __syncthreads();
+    nz_resolve<T>(g, parity, nzbuf, z0, z1);
+    parseval_terms<N, false>(z, sm, t, q1e, q2e);
+    float ny1 = 0.f, ny2 = 0.f;   // bin M/2 = even index N/2: register (u = 0, digit RL/2) of thread 0
+    if (t == 0) {
+      const float2 zz = z[UL * (RL / 2)];
+      ny1 = zz.x * zz.x;
+      ny2 = zz.y * zz.y;
+    }
+    // odd bins
+    bool d0, d1;
+    load_pair_n<N>(z, a.x, t, act0, act1, p0, d0, d1);
+    modulate<N>(z, a.mod, t);
+    fft_forward<N>(z, t, sm, a.tw);   // its first barrier orders the partner reads above before the exchange
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
+    __syncthreads();
+    parseval_terms<N, true>(z, sm, t, q1o, q2o);
+    __syncthreads();   // partner reads done: the buffer becomes reduction scratch
+    for (int b0 = 0; b0 < a.B; b0 += 4) {
+      float e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const int b = b0 + bb;
+        if (b < a.B) {
+          const float* we = a.we + (size_t)b * (N / 2);
+          const float* wo = a.wo + (size_t)b * (N / 2);
+#pragma unroll
+          for (int j = 0; j < NLOW; ++j) {
+            const int u = j % UL, m = j / UL;
+            const float w_e = __ldg(we + m * (N / RL) + t + u * T);
+            const float w_o = __ldg(wo + m * (N / RL) + t + u * T);
+            e1[bb] = fmaf(w_e, q1e[j], e1[bb]);
+            e2[bb] = fmaf(w_e, q2e[j], e2[bb]);
+            e1[bb] = fmaf(w_o, q1o[j], e1[bb]);
+            e2[bb] = fmaf(w_o, q2o[j], e2[bb]);
+          }
+          if (t == 0) {
+            const float w = __ldg(a.wnyq + b);
+            e1[bb] = fmaf(w, ny1, e1[bb]);
+            e2[bb] = fmaf(w, ny2, e2[bb]);
+          }
+        }
+      }
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) {
+          e1[bb] += __shfl_xor_sync(0xffffffffu, e1[bb], o);
+          e2[bb] += __shfl_xor_sync(0xffffffffu, e2[bb], o);
+        }
+      }
+      if constexpr (T > 32) {
+        if ((t & 31) == 0) {
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            red[((t >> 5) * 4 + bb) * 2] = e1[bb];
+            red[((t >> 5) * 4 + bb) * 2 + 1] = e2[bb];
+          }
+        }
+        __syncthreads();
+        if (t < 8) {
+          float acc = 0.f;
+          for (int w = 0; w < NW; ++w) acc += red[(w * 4 + (t >> 1)) * 2 + (t & 1)];
+          const int b = b0 + (t >> 1);
+          const bool second = (t & 1) != 0;
+          if (b < a.B && (second ? act1 : act0))
+            a.energy[(size_t)b * a.P + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : acc;
+        }
+        __syncthreads();
+      } else {
+        if (t == 0) {
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            const int b = b0 + bb;
+            if (b < a.B) {
+              if (act0) a.energy[(size_t)b * a.P + p0] = z0 ? 0.f : e1[bb];
+              if (act1) a.energy[(size_t)b * a.P + p0 + 1] = z1 ? 0.f : e2[bb];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// Y = S Z + D conj(Z_mirror) for one sub-spectrum, S = sum_b (g0+g1)/2 H_b, D = sum_b (g0-g1)/2 H_b,
+// in two batches of 8 registers to bound the register footprint
+template <int N, bool ODD>
+__device__ __forceinline__ void mix_subspectrum(float2 (&z)[kE], const float2* sm, int t, const FirArgs& a,
+                                                const float* __restrict__ htab, int64_t p0, bool act0, bool act1,
+                                                bool& bad0, bool& bad1) {
+  constexpr int T = SGeo<N>::T;
+  constexpr int LAST = Plan<N>::ns - 1;
+  constexpr int RL = Plan<N>::r[LAST];
+  constexpr int UL = kE / RL;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float sacc[8], dacc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sacc[j] = dacc[j] = 0.f;
+    for (int b = 0; b < a.B; ++b) {
+      float g0 = act0 ? __ldg(a.gain + (size_t)b * a.P + p0) : 0.f;
+      float g1 = act1 ? __ldg(a.gain + (size_t)b * a.P + p0 + 1) : 0.f;
+      if (!(fabsf(g0) <= 3.0e38f)) { bad0 = true; g0 = 0.f; }
+      if (!(fabsf(g1) <= 3.0e38f)) { bad1 = true; g1 = 0.f; }
+      const float gs = 0.5f * (g0 + g1), gd = 0.5f * (g0 - g1);
+      const float* hq = htab + (size_t)b * N;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = half * 8 + j;
+        const int u = i % UL, m = i / UL;
+        const float h = __ldg(hq + m * (N / RL) + t + u * T);
+        sacc[j] = fmaf(gs, h, sacc[j]);
+        dacc[j] = fmaf(gd, h, dacc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = half * 8 + j;
+      const int k = pos_to_bin<N>(stage_elem<N, LAST>(t, i));
+      const float2 zp = sm[pad_idx(ODD ? (N - 1 - k) : ((N - k) & (N - 1)))];
+      z[i] = make_float2(fmaf(sacc[j], z[i].x, dacc[j] * zp.x), fmaf(sacc[j], z[i].y, -dacc[j] * zp.y));
+    }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_split(const FirArgs a) {
+  using GEO = SGeo<N>;
+  constexpr int T = GEO::T, G = GEO::G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(N));
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(N);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<N>::ns - 1;
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t p0 = (item * G + g) * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    bool nz0, nz1, bad0 = false, bad1 = false;
+    float2 ye[kE];
+    {   // even bins
+      float2 z[kE];
+      load_pair_n<N>(z, a.x, t, act0, act1, p0, nz0, nz1);
+      fft_forward<N>(z, t, sm, a.tw);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
+      __syncthreads();
+      mix_subspectrum<N, false>(z, sm, t, a, a.he, p0, act0, act1, bad0, bad1);
+      fft_inverse<N>(z, t, sm, a.tw);
+#pragma unroll
+      for (int i = 0; i < kE; ++i) ye[i] = z[i];
+    }
+    float2 z[kE];
+    load_pair_n<N>(z, a.x, t, act0, act1, p0, nz0, nz1);
+    modulate<N>(z, a.mod, t);
+    fft_forward<N>(z, t, sm, a.tw);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
+    __syncthreads();
+    mix_subspectrum<N, true>(z, sm, t, a, a.ho, p0, act0, act1, bad0, bad1);
+    fft_inverse<N>(z, t, sm, a.tw);
+    // y[n] = ye[n] + conj(w_M^n) yo[n]   (1/M is folded into the H tables)
+    const float kNaN = __int_as_float(0x7fc00000);
+    float* r0 = a.out + p0 * N + t;
+    float* r1 = r0 + N;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      const float2 w = __ldg(a.mod + t + i * T);
+      const float2 yo = cmul_conj(z[i], w);
+      const float y0 = bad0 ? kNaN : ye[i].x + yo.x, y1 = bad1 ? kNaN : ye[i].y + yo.y;
+      if (act0) __stcs(r0 + i * T, y0);
+      if (act1) __stcs(r1 + i * T, y1);
+      s0 = fmaf(y0, y0, s0);
+      s1 = fmaf(y1, y1, s1);
+    }
+    if (a.img != nullptr) {
+      // group reduction (same scheme as the trace pass)
+      constexpr int W = (T < 32) ? T : 32;
+#pragma unroll
+      for (int o = W / 2; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      }
+      if constexpr (T > 32) {
+        float* sc = scr + g * 32;
+        if ((t & 31) == 0) {
+          sc[2 * (t >> 5)] = s0;
+          sc[2 * (t >> 5) + 1] = s1;
+        }
+        __syncthreads();
+        if (t == 0) {
+          float sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int w = 0; w < T / 32; ++w) {
+            sa += sc[2 * w];
+            sb += sc[2 * w + 1];
+          }
+          s0 = sa;
+          s1 = sb;
+        }
+      }
+      if (t == 0) {
+        if (act0) a.img[p0] = s0;
+        if (act1) a.img[p0 + 1] = s1;
       }
     }
   }
@@ -730,6 +1054,10 @@ struct FirTables {
   float* d_wq = nullptr;   // [B][m/2]
   float* d_wnyq = nullptr; // [B]
   float2* d_edge = nullptr;// [2][B][512]
+  // split form (n_half = m/2 = trace length): he, ho [B][n_half]; we, wo [B][n_half/2]; mod [n_half] float2
+  bool split = false;
+  float *d_he = nullptr, *d_ho = nullptr, *d_we = nullptr, *d_wo = nullptr;
+  float2* d_mod = nullptr;
 };
 
 // spectra / 512 of the first (edge 0) and last (edge 1) 249 taps at 512 points, register order of Plan<512>
@@ -790,16 +1118,28 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
   // layout (floats): hq [B][m] | wq [B][m/2] | wnyq [B, padded to 4] | edge [2][B][512] float2
   const size_t n_hq = (size_t)B * m, n_wq = (size_t)B * (m / 2), n_ny = (size_t)((B + 3) & ~3);
   const size_t n_edge = (size_t)2 * B * 512 * 2;
-  int rc = ws_get(c, WS_FIR, (n_hq + n_wq + n_ny + n_edge) * sizeof(float), &dp);
+  const int nh = m / 2;
+  int nsh, rh[4];
+  const bool split = (nh == n) && nh >= 256 && plan_of_m(nh, nsh, rh);
+  const size_t n_split = split ? ((size_t)2 * B * nh + (size_t)2 * B * (nh / 2) + (size_t)2 * nh) : 0;
+  int rc = ws_get(c, WS_FIR, (n_hq + n_wq + n_ny + n_edge + n_split) * sizeof(float), &dp);
   if (rc != THZ_OK) return rc;
   ft.d_hq = (float*)dp;
   ft.d_wq = ft.d_hq + n_hq;
   ft.d_wnyq = ft.d_wq + n_wq;
   ft.d_edge = reinterpret_cast<float2*>(ft.d_wnyq + n_ny);
+  ft.split = split;
+  if (split) {
+    ft.d_he = ft.d_wnyq + n_ny + n_edge;
+    ft.d_ho = ft.d_he + (size_t)B * nh;
+    ft.d_we = ft.d_ho + (size_t)B * nh;
+    ft.d_wo = ft.d_we + (size_t)B * (nh / 2);
+    ft.d_mod = reinterpret_cast<float2*>(ft.d_wo + (size_t)B * (nh / 2));
+  }
   ft.m = m;
   ft.B = B;
   if (c->fir_key == key && c->fir_m == m) return THZ_OK;
-  std::vector<float> all(n_hq + n_wq + n_ny + n_edge, 0.f), one;
+  std::vector<float> all(n_hq + n_wq + n_ny + n_edge + n_split, 0.f), one;
   const int RLs = r[ns - 1];
   for (int b = 0; b < B; ++b) {
     if (build_fir_hq(m, bands[b].fir, one) != THZ_OK) return set_err(c, THZ_EINVAL, "bad FIR transform size");
@@ -816,6 +1156,56 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
     float* et = all.data() + n_hq + n_wq + n_ny + ((size_t)1 * B + b) * 512 * 2;
     memcpy(eh, head.data(), 512 * sizeof(float2));
     memcpy(et, tail.data(), 512 * sizeof(float2));
+    if (split) {
+      // natural-order H / m from the register-order table of the m-point plan, then the even / odd
+      // sub-spectra in the register order of the (m/2)-point plan
+      std::vector<float> hnat(m);
+      for (int beta = 0; beta < m / RLs; ++beta)
+        for (int mm = 0; mm < RLs; ++mm) {
+          int pp = beta * RLs + mm, k = 0, w = 1, L = m;
+          for (int s2 = 0; s2 < ns; ++s2) {
+            const int S = L / r[s2];
+            const int q = pp / S;
+            pp -= q * S;
+            k += q * w;
+            w *= r[s2];
+            L = S;
+          }
+          hnat[k] = one[(size_t)mm * (m / RLs) + beta];
+        }
+      const int RLh = rh[nsh - 1];
+      float* he = all.data() + n_hq + n_wq + n_ny + n_edge + (size_t)b * nh;
+      float* ho = he + (size_t)B * nh;
+      float* we = all.data() + n_hq + n_wq + n_ny + n_edge + (size_t)2 * B * nh + (size_t)b * (nh / 2);
+      float* wo = we + (size_t)B * (nh / 2);
+      for (int beta = 0; beta < nh / RLh; ++beta)
+        for (int mm = 0; mm < RLh; ++mm) {
+          int pp = beta * RLh + mm, j = 0, w = 1, L = nh;
+          for (int s2 = 0; s2 < nsh; ++s2) {
+            const int S = L / rh[s2];
+            const int q = pp / S;
+            pp -= q * S;
+            j += q * w;
+            w *= rh[s2];
+            L = S;
+          }
+          const size_t o = (size_t)mm * (nh / RLh) + beta;
+          he[o] = hnat[2 * j];
+          ho[o] = hnat[2 * j + 1];
+          if (o < (size_t)(nh / 2)) {   // lower-half registers
+            we[o] = he[o] * he[o] * (float)m;
+            wo[o] = ho[o] * ho[o] * (float)m;
+          }
+        }
+    }
+  }
+  if (split) {
+    float2* mod = reinterpret_cast<float2*>(all.data() + n_hq + n_wq + n_ny + n_edge + (size_t)2 * B * nh +
+                                            (size_t)2 * B * (nh / 2));
+    for (int i = 0; i < nh; ++i) {
+      const double ang = -2.0 * M_PI * (double)i / (double)m;
+      mod[i] = make_float2((float)cos(ang), (float)sin(ang));
+    }
   }
   THZ_CUDA(c, cudaStreamSynchronize(s));   // no kernel still reads the previous spectra
   THZ_CUDA(c, cudaMemcpyAsync(ft.d_hq, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -861,6 +1251,13 @@ template <int M> static int do_apply(thz_ctx* c, cudaStream_t s, const FirArgs& 
 template <int M> static int do_energy_total(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
   return launch_fir<M>(c, s, k_fir_energy_total<M>, a);
 }
+// split kernels use the N-point geometry (identical to DGeo<N>)
+template <int N> static int do_energy_split(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
+  return launch_fir<N>(c, s, k_fir_energy_split<N>, a);
+}
+template <int N> static int do_apply_split(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
+  return launch_fir<N>(c, s, k_fir_apply_split<N>, a);
+}
 
 #define THZ_DISPATCH_M(m, FN, ...)                 \
   switch (m) {                                     \
@@ -879,6 +1276,12 @@ static int dispatch_energy(thz_ctx* c, cudaStream_t s, int m, const FirArgs& a) 
 static int dispatch_apply(thz_ctx* c, cudaStream_t s, int m, const FirArgs& a) { THZ_DISPATCH_M(m, do_apply, c, s, a); }
 static int dispatch_energy_total(thz_ctx* c, cudaStream_t s, int m, const FirArgs& a) {
   THZ_DISPATCH_M(m, do_energy_total, c, s, a);
+}
+static int dispatch_energy_split(thz_ctx* c, cudaStream_t s, int n, const FirArgs& a) {
+  THZ_DISPATCH_M(n, do_energy_split, c, s, a);
+}
+static int dispatch_apply_split(thz_ctx* c, cudaStream_t s, int n, const FirArgs& a) {
+  THZ_DISPATCH_M(n, do_apply_split, c, s, a);
 }
 
 int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
@@ -901,7 +1304,17 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
       rc = get_tables(c, 512, &tb512);
       if (rc != THZ_OK) return rc;
       a.tw512 = tb512->d_tw;
-      rc = dispatch_energy_total(c, s, ft.m, a);
+      if (ft.split) {
+        const FftTables* tbn = nullptr;
+        rc = get_tables(c, n, &tbn);
+        if (rc != THZ_OK) return rc;
+        FirArgs as = a;
+        as.tw = tbn->d_tw;
+        as.he = ft.d_he; as.ho = ft.d_ho; as.we = ft.d_we; as.wo = ft.d_wo; as.mod = ft.d_mod;
+        rc = dispatch_energy_split(c, s, n, as);
+      } else {
+        rc = dispatch_energy_total(c, s, ft.m, a);
+      }
       if (rc == THZ_OK) rc = launch_fir<512>(c, s, k_fir_edges, a);
     } else {
       rc = dispatch_energy(c, s, ft.m, a);   // short traces: B inverse transforms per pair
@@ -924,7 +1337,16 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
     FirArgs a{};
     a.x = d_cube; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.gain = d_gain; a.out = d_out; a.img = d_img;
     a.tw = tb->d_tw;
-    rc = dispatch_apply(c, s, ft.m, a);
+    if (ft.split) {
+      const FftTables* tbn = nullptr;
+      rc = get_tables(c, n, &tbn);
+      if (rc != THZ_OK) return rc;
+      a.tw = tbn->d_tw;
+      a.he = ft.d_he; a.ho = ft.d_ho; a.mod = ft.d_mod;
+      rc = dispatch_apply_split(c, s, n, a);
+    } else {
+      rc = dispatch_apply(c, s, ft.m, a);
+    }
   }
   return rc;
 }
