@@ -311,25 +311,64 @@ template <int N> struct SGeo {
   static constexpr int NT = (T >= 256) ? T : 256;
   static constexpr int G = NT / T;
   static constexpr int kScr = (32 + kNzWords) * G;
-  static constexpr size_t smem_bytes = (size_t)G * padded_len(N) * sizeof(float2) + kScr * sizeof(float);
+  static constexpr size_t base_bytes = (size_t)G * padded_len(N) * sizeof(float2) + kScr * sizeof(float);
+  // input slab of the work item, double buffered, filled by bulk copies (BulkStager): the even and the
+  // odd pass both read it from shared memory, the cube crosses HBM once per pass
+  static constexpr int kSlabFloats = 2 * G * N;
+  static constexpr size_t stage_off = (base_bytes + 127) & ~(size_t)127;
+  static constexpr size_t smem_bytes = stage_off + 2 * (size_t)kSlabFloats * sizeof(float) + 16;
   static constexpr int kMinBlocks = (NT == 256) ? 2 : 1;
 };
 
 template <int N>
-__device__ __forceinline__ void load_pair_n(float2 (&v)[kE], const float* x, int t, bool act0, bool act1, int64_t p0,
+__device__ __forceinline__ void load_pair_n(float2 (&v)[kE], const float* slab, int t, int g, bool act0, bool act1,
                                             bool& nz0, bool& nz1) {
   constexpr int T = SGeo<N>::T;
-  const float* r0 = x + p0 * N + t;
+  const float* r0 = slab + (size_t)(2 * g) * N + t;
   const float* r1 = r0 + N;
   nz0 = nz1 = false;
 #pragma unroll
   for (int i = 0; i < kE; ++i) {
-    v[i].x = act0 ? __ldg(r0 + i * T) : 0.f;   // read twice per item (even and odd pass): keep it cacheable
-    v[i].y = act1 ? __ldg(r1 + i * T) : 0.f;
+    v[i].x = act0 ? r0[i * T] : 0.f;
+    v[i].y = act1 ? r1[i * T] : 0.f;
     nz0 |= (v[i].x != 0.f);
     nz1 |= (v[i].y != 0.f);
   }
 }
+
+// common prologue / per-iteration staging of the split kernels
+template <int N> struct SlabPipe {
+  using GEO = SGeo<N>;
+  float* slab[2];
+  BulkStager stager;
+  uint32_t it_count = 0;
+  const float* x;
+  int64_t P, nitems;
+  __device__ __forceinline__ uint32_t bytes_of(int64_t it) const {
+    int64_t cnt = P - it * GEO::G * 2;
+    if (cnt > 2 * GEO::G) cnt = 2 * GEO::G;
+    return (uint32_t)(cnt * N * sizeof(float));
+  }
+  __device__ __forceinline__ void init(unsigned char* smem_raw, const float* x_, int64_t P_, int64_t nitems_) {
+    x = x_; P = P_; nitems = nitems_;
+    slab[0] = reinterpret_cast<float*>(smem_raw + GEO::stage_off);
+    slab[1] = slab[0] + GEO::kSlabFloats;
+    stager.init(reinterpret_cast<uint64_t*>(smem_raw + GEO::stage_off + 2 * (size_t)GEO::kSlabFloats * sizeof(float)));
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < nitems)
+      stager.issue(0, slab[0], x + (int64_t)blockIdx.x * GEO::G * 2 * N, bytes_of(blockIdx.x));
+  }
+  // top of an iteration: prefetch the next item, wait for this one; returns its slab
+  __device__ __forceinline__ const float* acquire(int64_t item) {
+    const int buf = it_count & 1;
+    const int64_t next = item + gridDim.x;
+    if constexpr (GEO::T <= 32) __syncthreads();
+    if (threadIdx.x == 0 && next < nitems)
+      stager.issue(buf ^ 1, slab[buf ^ 1], x + next * GEO::G * 2 * N, bytes_of(next));
+    stager.wait(buf, (it_count >> 1) & 1);
+    ++it_count;
+    return slab[buf];
+  }
+};
 
 template <int N>
 __device__ __forceinline__ void modulate(float2 (&v)[kE], const float2* __restrict__ mod, int t) {
@@ -382,15 +421,18 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
   float* red = reinterpret_cast<float*>(sm);
   int parity = 0;
   (void)M;
+  SlabPipe<N> pipe;
+  pipe.init(smem_raw, a.x, a.P, nitems);
 
   for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
     const int64_t p0 = (item * G + g) * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    const float* slab = pipe.acquire(item);
     float2 z[kE];
     bool nz0, nz1, z0, z1;
     float q1e[NLOW], q2e[NLOW], q1o[NLOW], q2o[NLOW];
     // even bins
-    load_pair_n<N>(z, a.x, t, act0, act1, p0, nz0, nz1);
+    load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
     nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
     fft_forward<N>(z, t, sm, a.tw);
     __syncthreads();
@@ -407,7 +449,7 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
     }
     // odd bins
     bool d0, d1;
-    load_pair_n<N>(z, a.x, t, act0, act1, p0, d0, d1);
+    load_pair_n<N>(z, slab, t, g, act0, act1, d0, d1);
     modulate<N>(z, a.mod, t);
     fft_forward<N>(z, t, sm, a.tw);   // its first barrier orders the partner reads above before the exchange
     __syncthreads();
@@ -536,15 +578,18 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_
   const int64_t npairs = (a.P + 1) >> 1;
   const int64_t nitems = (npairs + G - 1) / G;
   constexpr int LAST = Plan<N>::ns - 1;
+  SlabPipe<N> pipe;
+  pipe.init(smem_raw, a.x, a.P, nitems);
 
   for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int64_t p0 = (item * G + g) * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    const float* slab = pipe.acquire(item);
     bool nz0, nz1, bad0 = false, bad1 = false;
     float2 ye[kE];
     {   // even bins
       float2 z[kE];
-      load_pair_n<N>(z, a.x, t, act0, act1, p0, nz0, nz1);
+      load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
       fft_forward<N>(z, t, sm, a.tw);
       __syncthreads();
 #pragma unroll
@@ -556,7 +601,7 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_
       for (int i = 0; i < kE; ++i) ye[i] = z[i];
     }
     float2 z[kE];
-    load_pair_n<N>(z, a.x, t, act0, act1, p0, nz0, nz1);
+    load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
     modulate<N>(z, a.mod, t);
     fft_forward<N>(z, t, sm, a.tw);
     __syncthreads();
@@ -1120,7 +1165,8 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
   const size_t n_edge = (size_t)2 * B * 512 * 2;
   const int nh = m / 2;
   int nsh, rh[4];
-  const bool split = (nh == n) && nh >= 256 && plan_of_m(nh, nsh, rh);
+  // the split kernels stage 64 KB of input + the exchange buffer: n <= 4096 keeps two CTAs per SM
+  const bool split = (nh == n) && nh >= 256 && nh <= 4096 && plan_of_m(nh, nsh, rh);
   const size_t n_split = split ? ((size_t)2 * B * nh + (size_t)2 * B * (nh / 2) + (size_t)2 * nh) : 0;
   int rc = ws_get(c, WS_FIR, (n_hq + n_wq + n_ny + n_edge + n_split) * sizeof(float), &dp);
   if (rc != THZ_OK) return rc;
@@ -1216,9 +1262,9 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
 }
 
 template <int M, typename K>
-static int launch_fir(thz_ctx* c, cudaStream_t s, K kernel, const FirArgs& a) {
+static int launch_fir(thz_ctx* c, cudaStream_t s, K kernel, const FirArgs& a, size_t smem_override = 0) {
   using GEO = DGeo<M>;
-  const size_t smem = GEO::smem_bytes;
+  const size_t smem = smem_override ? smem_override : GEO::smem_bytes;
   const void* key = (const void*)kernel;
   auto it = c->occ.find(key);
   if (it == c->occ.end()) {
@@ -1253,10 +1299,10 @@ template <int M> static int do_energy_total(thz_ctx* c, cudaStream_t s, const Fi
 }
 // split kernels use the N-point geometry (identical to DGeo<N>)
 template <int N> static int do_energy_split(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
-  return launch_fir<N>(c, s, k_fir_energy_split<N>, a);
+  return launch_fir<N>(c, s, k_fir_energy_split<N>, a, SGeo<N>::smem_bytes);
 }
 template <int N> static int do_apply_split(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
-  return launch_fir<N>(c, s, k_fir_apply_split<N>, a);
+  return launch_fir<N>(c, s, k_fir_apply_split<N>, a, SGeo<N>::smem_bytes);
 }
 
 #define THZ_DISPATCH_M(m, FN, ...)                 \
@@ -1289,6 +1335,7 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
   if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
   if (P == 0) return THZ_OK;
   if (!d_cube || !d_energy || n < 2) return set_err(c, THZ_EINVAL, "null pointer");
+  if ((reinterpret_cast<uintptr_t>(d_cube) & 15u) != 0) return set_err(c, THZ_EINVAL, "cube must be 16-byte aligned");
   FirTables ft;
   int rc = upload_fir_tables(c, s, n, bands, B, ft);
   if (rc != THZ_OK) return rc;
@@ -1328,6 +1375,7 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
   if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
   if (P == 0) return THZ_OK;
   if (!d_cube || !d_gain || !d_out || n < 2) return set_err(c, THZ_EINVAL, "null pointer");
+  if ((reinterpret_cast<uintptr_t>(d_cube) & 15u) != 0) return set_err(c, THZ_EINVAL, "cube must be 16-byte aligned");
   FirTables ft;
   int rc = upload_fir_tables(c, s, n, bands, B, ft);
   if (rc != THZ_OK) return rc;

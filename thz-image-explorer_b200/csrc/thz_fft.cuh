@@ -224,15 +224,23 @@ __device__ __forceinline__ int pos_to_bin(int p) {
   }
 }
 
+// Barrier between the exchange phases of one transform.  A group of T = N/16 threads only ever
+// touches its own slice of the exchange buffer, so groups that fit in one warp (N <= 512)
+// synchronise with __syncwarp() and never stall the other groups of the CTA.
+template <int N> __device__ __forceinline__ void group_sync() {
+  if constexpr (N / kE <= 32) __syncwarp();
+  else __syncthreads();
+}
+
 // Full forward transform: registers hold stage-0 layout (v[i] <-> element t + i*T) on entry,
 // last-stage layout (digit-reversed positions) on exit.  Uses 2 barriers per exchange.
 template <int N, int S_IDX = 0>
 __device__ __forceinline__ void fft_forward(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw) {
   stage_compute<N, S_IDX, false>(v, t, tw);
   if constexpr (S_IDX + 1 < Plan<N>::ns) {
-    __syncthreads();                       // previous readers of sm are done
+    group_sync<N>();                       // previous readers of sm are done
     stage_store<N, S_IDX>(v, t, sm);
-    __syncthreads();
+    group_sync<N>();
     stage_load<N, S_IDX + 1>(v, t, sm);
     fft_forward<N, S_IDX + 1>(v, t, sm, tw);
   }
@@ -243,9 +251,9 @@ template <int N, int S_IDX = Plan<N>::ns - 1>
 __device__ __forceinline__ void fft_inverse(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw) {
   stage_compute<N, S_IDX, true>(v, t, tw);
   if constexpr (S_IDX > 0) {
-    __syncthreads();
+    group_sync<N>();
     stage_store<N, S_IDX>(v, t, sm);
-    __syncthreads();
+    group_sync<N>();
     stage_load<N, S_IDX - 1>(v, t, sm);
     fft_inverse<N, S_IDX - 1>(v, t, sm, tw);
   }
@@ -296,5 +304,46 @@ __device__ __forceinline__ void nz_resolve(int g, int parity, const unsigned* nz
     z1 = a1 == 0u;
   }
 }
+
+// ------------------------------------------------------------------------------------
+// Bulk-copy staging of a CTA's input slab (TMA, cp.async.bulk global -> shared).
+// The traces of one work item are contiguous in the [P][N] cube, so ONE elected thread moves the
+// whole slab with a single asynchronous copy that completes on an mbarrier; the other threads
+// spend no load instructions on it and the copy of item i+1 overlaps the transforms of item i.
+// Two buffers: buffer (it & 1) holds item `it`; its refill for item it+2 is issued at the top of
+// iteration it+1, after every thread has passed the barriers of iteration `it`.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct BulkStager {
+  uint32_t mbar[2];
+  __device__ __forceinline__ void init(uint64_t* bars) {
+    mbar[0] = smem_addr(bars);
+    mbar[1] = smem_addr(bars + 1);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar[0]), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar[1]), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  // one thread: start the copy of `bytes` (multiple of 16, both addresses 16-byte aligned) into buffer b
+  __device__ __forceinline__ void issue(int b, void* dst, const void* src, uint32_t bytes) const {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar[b]), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(mbar[b])
+                 : "memory");
+  }
+  __device__ __forceinline__ void wait(int b, uint32_t phase) const {
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(ok)
+          : "r"(mbar[b]), "r"(phase)
+          : "memory");
+    }
+  }
+};
 
 }  // namespace thz

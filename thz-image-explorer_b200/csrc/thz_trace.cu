@@ -28,6 +28,10 @@ template <int N> struct Geo {
   static constexpr int kScr = (32 + kNzWords) * G;       // per-CTA scratch words: reductions + zero-trace flags
   static constexpr int kMinBlocks = (NT == 256) ? 2 : 1; // register cap: 128 per thread
   static constexpr size_t smem_bytes = (size_t)G * padded_len(N) * sizeof(float2) + kScr * sizeof(float);
+  // kernels that stage their input with bulk copies: two slabs of 2*G traces + two mbarriers
+  static constexpr int kSlabFloats = 2 * G * N;
+  static constexpr size_t stage_off = (smem_bytes + 127) & ~(size_t)127;
+  static constexpr size_t smem_bytes_staged = stage_off + 2 * (size_t)kSlabFloats * sizeof(float) + 16;
 };
 
 struct TraceArgs {
@@ -106,6 +110,31 @@ __device__ __forceinline__ void load_pair(float2 (&v)[kE], const TraceArgs& a, i
   }
 }
 
+// Same from the staged slab in shared memory (row 2g = trace p0, row 2g+1 = trace p0+1).
+template <int N>
+__device__ __forceinline__ void load_pair_staged(float2 (&v)[kE], const TraceArgs& a, const float* slab, int t, int g,
+                                                 bool act0, bool act1, bool& nz0, bool& nz1) {
+  constexpr int T = Geo<N>::T;
+  const float* r0 = slab + (size_t)(2 * g) * N + t;
+  const float* r1 = r0 + N;
+  nz0 = nz1 = false;
+#pragma unroll
+  for (int i = 0; i < kE; ++i) {
+    v[i].x = act0 ? r0[i * T] : 0.f;
+    v[i].y = act1 ? r1[i * T] : 0.f;
+    nz0 |= (v[i].x != 0.f);
+    nz1 |= (v[i].y != 0.f);
+  }
+  if (a.m_pre != nullptr) {
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      const float m = __ldg(a.m_pre + t + i * T);
+      v[i].x *= m;
+      v[i].y *= m;
+    }
+  }
+}
+
 // multiply by m_post, store both traces, intensity = sum of squares of the stored values
 template <int N>
 __device__ __forceinline__ void store_pair(float2 (&v)[kE], const TraceArgs& a, int t, int g, bool act0,
@@ -165,14 +194,36 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(
   constexpr int UL = kE / RL;
   unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
   int parity = 0;
+  // input slabs arrive through bulk copies (thz_fft.cuh, BulkStager)
+  float* slab[2] = {reinterpret_cast<float*>(smem_raw + GEO::stage_off),
+                    reinterpret_cast<float*>(smem_raw + GEO::stage_off) + GEO::kSlabFloats};
+  BulkStager stager;
+  stager.init(reinterpret_cast<uint64_t*>(smem_raw + GEO::stage_off + 2 * (size_t)GEO::kSlabFloats * sizeof(float)));
+  auto slab_bytes = [&](int64_t it) -> uint32_t {
+    const int64_t first = it * G * 2;
+    int64_t cnt = a.P - first;
+    if (cnt > 2 * G) cnt = 2 * G;
+    return (uint32_t)(cnt * N * sizeof(float));
+  };
+  if (threadIdx.x == 0 && (int64_t)blockIdx.x < nitems)
+    stager.issue(0, slab[0], a.in + (int64_t)blockIdx.x * G * 2 * N, slab_bytes(blockIdx.x));
+  uint32_t it_count = 0;
 
-  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1, ++it_count) {
     const int64_t pair = item * G + g;
     const int64_t p0 = pair * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    const int buf = it_count & 1;
+    const int64_t next = item + gridDim.x;
+    // the refill below overwrites the slab every group read one iteration ago; groups that fit in a
+    // warp only synchronise with __syncwarp() inside the transforms, so order them here
+    if constexpr (T <= 32) __syncthreads();
+    if (threadIdx.x == 0 && next < nitems)
+      stager.issue(buf ^ 1, slab[buf ^ 1], a.in + next * G * 2 * N, slab_bytes(next));
+    stager.wait(buf, (it_count >> 1) & 1);
     float2 v[kE];
     bool nz0, nz1, z0, z1;
-    load_pair<N>(v, a, t, act0, act1, p0, nz0, nz1);
+    load_pair_staged<N>(v, a, slab[buf], t, g, act0, act1, nz0, nz1);
     nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
     fft_forward<N>(v, t, sm, a.tw);
     // band-pass in digit-reversed order: register (u, m) <-> position (t + u*T)*RL + m,
@@ -581,9 +632,9 @@ int build_hq(int n, const float* band, std::vector<float>& hq) {
 }
 
 template <int N, typename K>
-static int launch_geo(thz_ctx* c, cudaStream_t s, K kernel, const TraceArgs& a) {
+static int launch_geo(thz_ctx* c, cudaStream_t s, K kernel, const TraceArgs& a, bool staged = false) {
   using GEO = Geo<N>;
-  const size_t smem = GEO::smem_bytes;
+  const size_t smem = staged ? GEO::smem_bytes_staged : GEO::smem_bytes;
   const void* key = (const void*)kernel;
   auto it = c->occ.find(key);
   if (it == c->occ.end()) {
@@ -621,7 +672,7 @@ static int launch_geo(thz_ctx* c, cudaStream_t s, K kernel, const TraceArgs& a) 
   }
 
 template <int N> static int do_fused(thz_ctx* c, cudaStream_t s, const TraceArgs& a) {
-  return launch_geo<N>(c, s, k_trace_fused<N>, a);
+  return launch_geo<N>(c, s, k_trace_fused<N>, a, true);
 }
 template <int N> static int do_forward(thz_ctx* c, cudaStream_t s, const TraceArgs& a) {
   return launch_geo<N>(c, s, k_trace_forward<N>, a);
@@ -648,6 +699,7 @@ int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_o
   if (rc != THZ_OK) return rc;
   if (P == 0) return THZ_OK;
   if (!d_in || !d_out) return set_err(c, THZ_EINVAL, "null cube pointer");
+  if ((reinterpret_cast<uintptr_t>(d_in) & 15u) != 0) return set_err(c, THZ_EINVAL, "cube must be 16-byte aligned");
   a.in = d_in;
   a.out = d_out;
   a.img = d_img;
