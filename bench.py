@@ -341,7 +341,7 @@ def run_ours(a):
     # end to end through the host-pointer C ABI: pinned host cube -> H2D -> chain -> D2H (filtered cube + img)
     e2e = None
     if not a.no_e2e:
-        e2e = run_e2e(a, m, ctx, d_in, P, N, world, dist, barrier, P_total)
+        e2e = run_e2e(a, m, ctx, d_in, d_out, P, rows, N, world, dist, barrier, P_total, bands, step)
 
     cpu = None
     if rank == 0 and not a.no_cpu:
@@ -371,33 +371,44 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def run_e2e(a, m, ctx, d_in, P, N, world, dist, barrier, P_total):
-    """Same metric through thz_trace_fused_host with HOST buffers (pinned), copies inside the
-    timed region.  The host slab is the rank's whole slab when it fits comfortably in RAM,
-    otherwise a bounded slab (stated in the result)."""
+def run_e2e(a, m, ctx, d_in, d_out, P, rows, N, world, dist, barrier, P_total, bands, step_dev):
+    """The same step through the host-pointer C ABI: pinned host cube in, filtered (and deconvolved)
+    cube + intensity map out, copies inside the timed region.  One GPU: thz_chain_host (copies
+    overlap the cube passes).  Several GPUs: each rank uploads its slab, runs the sharded device
+    step and downloads it (no overlap yet)."""
     import ctypes as C
+    H = a.height
     try:
         avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
     except Exception:
         avail = 64 << 30
-    budget = int(0.55 * avail / max(world, 1))
-    Pe = min(P, max(2, budget // (N * 4 + 4)))
-    Pe -= Pe % 2
-    nbytes = Pe * N * 4
-    hp = C.c_void_p()
-    hi = C.c_void_p()
-    if m.lib.thz_host_alloc(nbytes, C.byref(hp)) != 0 or m.lib.thz_host_alloc(Pe * 4, C.byref(hi)) != 0:
+    nbytes = P * N * 4
+    if nbytes * world > 0.6 * avail:
+        return {"value": None, "unit": UNIT, "note": f"host RAM too small for a {nbytes * world >> 30} GiB pinned cube"}
+    hp, hi = C.c_void_p(), C.c_void_p()
+    if m.lib.thz_host_alloc(nbytes, C.byref(hp)) != 0 or m.lib.thz_host_alloc(P * 4, C.byref(hi)) != 0:
         return None
     try:
         ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_in.ptr, nbytes))
         reps = 2
-        # warm-up (allocates the staging ring)
-        ctx._check(m.lib.thz_trace_fused_host(ctx.handle, hp.value, hp.value, hi.value, min(Pe, 1 << 15)))
+
+        def once():
+            if world == 1:
+                ctx._check(m.lib.thz_chain_host(ctx.handle, hp.value, rows, H, N, bands,
+                                                len(bands) if bands is not None else 0, hp.value, hi.value,
+                                                None, None, None))
+            else:
+                ctx._check(m.lib.thz_copy_h2d(ctx.handle, d_in.ptr, hp.value, nbytes))
+                step_dev()
+                ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_out.ptr, nbytes))
+
+        once()   # warm-up (allocates the device-resident cube / staging ring); restores nothing: re-upload input
         ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_in.ptr, nbytes))
         barrier()
         t0 = time.perf_counter()
         for _ in range(reps):
-            ctx._check(m.lib.thz_trace_fused_host(ctx.handle, hp.value, hp.value, hi.value, Pe))
+            once()
+        ctx.sync()
         barrier()
         dt = (time.perf_counter() - t0) / reps
         if dist is not None:
@@ -405,11 +416,13 @@ def run_e2e(a, m, ctx, d_in, P, N, world, dist, barrier, P_total):
             tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        total_traces = Pe * world if Pe < P else P_total
-        return {"value": total_traces / dt, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
-                "d2h_bytes_per_step": int(nbytes + Pe * 4), "traces_per_rank": int(Pe),
-                "note": "thz_trace_fused_host: pinned host cube in, filtered cube + intensity map out, "
-                        "chunked over 3 streams; wall clock around the call, max over ranks"}
+        return {"value": P_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(nbytes * world),
+                "d2h_bytes_per_step": int((nbytes + P * 4) * world), "seconds_per_step": dt,
+                "note": ("thz_chain_host: pinned host cube -> H2D chunks overlapped with the fused trace pass and the "
+                         "band-energy pass -> Richardson-Lucy -> gain application overlapped with D2H chunks"
+                         if world == 1 else
+                         "per rank: H2D of the slab, sharded device step, D2H of the slab (not overlapped); "
+                         "wall clock, max over ranks")}
     finally:
         m.lib.thz_host_free(hp.value)
         m.lib.thz_host_free(hi.value)

@@ -247,6 +247,14 @@ int thz_deconvolution_host(thz_ctx* ctx, const float* cube, int rows, int cols, 
                            const thz_band_plan* bands, int n_bands, float* out, float* img,
                            const volatile uint8_t* abort_flag, thz_progress_fn progress, void* progress_user);
 
+/* The whole chain in one call, host memory to host memory: the multipliers of thz_plan_trace
+ * (slots 2..7) and, when n_bands > 0, `Deconvolution::filter` on the result; the cube
+ * stays on the device in between (copies overlap the cube passes).  This is what
+ * thzhost::ChainDriver::run_fused and bench.py's end-to-end figure use.  out may alias cube. */
+int thz_chain_host(thz_ctx* ctx, const float* cube, int rows, int cols, int n, const thz_band_plan* bands,
+                   int n_bands, float* out, float* img, const volatile uint8_t* abort_flag,
+                   thz_progress_fn progress, void* progress_user);
+
 /* ------------------------------------------------------- trace pass, host pointers ----- */
 /* Same operators on host arrays (the reference's `ScannedImageFilterData` lives in host
  * memory).  Copies are chunked and overlapped with compute on three streams. */

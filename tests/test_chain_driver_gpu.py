@@ -117,3 +117,22 @@ def test_deconvolution_only_on_apply(ctx, psf_npz_path):
                                      dx=1.0, dy=1.0, width=w, height=h)
     ref = orc.Deconvolution(n_filters=4, n_iterations=10).filter(sin, opsf)
     assert rel_err(s8["data"], ref.data) <= TOL_MAP and rel_err(s8["img"], ref.img) <= TOL_MAP
+
+
+def test_run_fused_with_deconvolution(ctx, psf_npz_path):
+    """ChainDriver::run_fused(run_deconvolution) == the stage-by-stage driver ending in Apply."""
+    m = pkg()
+    n, w, h = 256, 36, 32
+    cube = synthetic_cube(w, h, n, seed=8, noise=0.02)
+    t = time_axis(n)
+    ch = m.Chain(ctx)
+    ch.open(t, cube, 1.0, 1.0)
+    ch.set_active("Deconvolution", True)
+    ch.set_param("Deconvolution", "n_filters", 4)
+    ch.set_param("Deconvolution", "n_iterations", 10)
+    ch.set_psf(m.host.PSF.load(psf_npz_path))
+    ch.run(1)
+    ch.run(ch.slot_of("Deconvolution"), run_deconvolution=True)
+    s8 = ch.slot(8)
+    out, img = ch.run_fused(run_deconvolution=True)
+    assert rel_err(out, s8["data"]) <= 1e-4 and rel_err(img, s8["img"]) <= 1e-4

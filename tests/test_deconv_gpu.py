@@ -140,3 +140,23 @@ def test_abort_flag_stops_the_filter(ctx, psfs):
     flag = ctypes.c_uint8(1)   # layout of Rust AtomicBool
     out, img, rc = ctx.deconvolution(cube, bands, abort_flag=flag)
     assert rc == 1   # THZ_ABORTED: the shim keeps the previous slot, like the cancellable loops
+
+
+def test_chain_host_equals_staged_calls(ctx, psfs):
+    """thz_chain_host (cube resident on the device between the fused trace pass and the deconvolution,
+    chunked copies) == thz_trace_fused_host followed by thz_deconvolution_host."""
+    from helpers import default_multipliers
+    psf, _ = psfs
+    w, h, n = 40, 33, 512
+    cube = synthetic_cube(w, h, n, seed=12, noise=0.02)
+    t, m_pre, band, m_post = default_multipliers(n)
+    ctx.plan_trace(n, m_pre, band, m_post)
+    bands, why = pkg().host.Deconvolution(n_filters=5, n_iterations=20).plan(t, (w, h), 1.0, 1.0, psf)
+    assert why is None
+    fused, fimg = ctx.trace_fused(cube)
+    ref_out, ref_img, _ = ctx.deconvolution(fused, bands)
+    out, img, rc = ctx.chain(cube, bands)
+    assert rc == 0
+    assert rel_err(out, ref_out) <= 1e-6 and rel_err(img, ref_img) <= 1e-6
+    out0, img0, _ = ctx.chain(cube, None)
+    assert np.array_equal(out0, fused) and np.array_equal(img0, fimg)

@@ -145,6 +145,7 @@ def load_library():
         "thz_deconv_apply_dev": (i32, [vp, fp, fp, i64, i32, C.POINTER(BandPlanC), i32, fp, fp]),
         "thz_deconvolution_dev": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_deconv_stage_ms": (i32, [vp, fp]),
+        "thz_chain_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_deconvolution_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_time_multiply_dev": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_time_multiply_host": (i32, [vp, fp, fp, i32, fp, i64]),
@@ -441,6 +442,17 @@ class Context:
             self.handle, cube.ctypes.data, rows, cols, n, bands, len(bands), out.ctypes.data, img.ctypes.data,
             C.addressof(abort_flag) if abort_flag is not None else None,
             C.cast(cb, C.c_void_p) if cb is not None else None, None))
+        return out, img, rc
+
+    def chain(self, cube, bands=None):
+        """thz_chain_host: default chain (+ deconvolution when bands is given) on a host cube."""
+        cube = _f32c(cube)
+        rows, cols, n = cube.shape
+        out = np.empty_like(cube)
+        img = np.empty((rows, cols), np.float32)
+        rc = self._check(lib.thz_chain_host(self.handle, cube.ctypes.data, rows, cols, n, bands,
+                                            len(bands) if bands is not None else 0, out.ctypes.data,
+                                            img.ctypes.data, None, None, None))
         return out, img, rc
 
     def deconv_stage_ms(self):

@@ -467,16 +467,28 @@ int ChainDriver::run_fused(bool run_deconvolution) {
   if (rc != THZ_OK) { last_error = thz_last_error(ctx_); return rc; }
   fused_out.assign(P * n, 0.f);
   fused_img.assign(P, 0.f);
-  rc = thz_trace_fused_host(ctx_, s0.data.data(), fused_out.data(), fused_img.data(), (int64_t)P);
-  if (rc != THZ_OK) { last_error = thz_last_error(ctx_); return rc; }
+  std::vector<thz_band_plan> bands;
+  int n_bands = 0;
   if (run_deconvolution && active("Deconvolution")) {
-    ScannedImageFilterData in = s0;
-    in.data = fused_out;
-    ProgressLock progress = [this](std::optional<float> p) { last_progress = p; };
-    ScannedImageFilterData out = filter_by_name("Deconvolution")->filter(in, gui_settings, progress, abort_flag);
-    fused_out = std::move(out.data);
-    if (!out.img.empty()) fused_img = std::move(out.img);
+    auto* d = dynamic_cast<Deconvolution*>(filter_by_name("Deconvolution"));
+    const thz_psf psf = gui_settings.psf.view();
+    thz_deconv_params prm{d->n_iterations, d->n_filters, d->start_freq, d->end_freq, d->win_width};
+    bands.resize((size_t)std::max(d->n_filters, 1));
+    const bool has = s0.dx && s0.dy;
+    const int prc = thz_deconv_plan_bands(gui_settings.psf.loaded ? &psf : nullptr, &prm, s0.time.data(), (int)n,
+                                          (int)s0.width, (int)s0.height, has ? 1 : 0, has ? *s0.dx : 0.f,
+                                          has ? *s0.dy : 0.f, bands.data());
+    if (prc == THZ_OK) n_bands = d->n_filters;   // otherwise the reference returns the filter's input
   }
+  struct Cb {
+    ChainDriver* self;
+    static void fn(float f, void* u) { static_cast<Cb*>(u)->self->last_progress = f; }
+  } cb{this};
+  rc = thz_chain_host(ctx_, s0.data.data(), (int)s0.width, (int)s0.height, (int)n, n_bands ? bands.data() : nullptr,
+                      n_bands, fused_out.data(), fused_img.data(),
+                      reinterpret_cast<const volatile uint8_t*>(&abort_flag), &Cb::fn, &cb);
+  last_progress = std::nullopt;
+  if (rc != THZ_OK) { last_error = thz_last_error(ctx_); return rc; }
   return THZ_OK;
 }
 

@@ -43,8 +43,9 @@ struct FirArgs {
   int64_t P;
   const float* hq;       // [B][M] zero-phase FIR spectra / M in last-stage register order
   int B;
-  float* energy;         // [B][P]                 (pass A)
-  const float* gain;     // [B][P]                 (pass C)
+  int64_t bstride;       // distance between bands in `energy` / `gain` (>= P; lets a chunk address a larger image)
+  float* energy;         // [B][bstride]           (pass A)
+  const float* gain;     // [B][bstride]           (pass C)
   float* out;            // [P][N]                 (pass C)
   float* img;            // [P] or null            (pass C)
   const float2* tw;
@@ -156,8 +157,8 @@ __global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_energy
       dreduce2<M>(s0, s1, t, g, scr);
       if (t == 0) {
         // an all-zero trace has exactly zero band energy in the reference (-> NaN gain, quirk 10)
-        if (act0) a.energy[(size_t)b * a.P + p0] = z0 ? 0.f : s0;
-        if (act1) a.energy[(size_t)b * a.P + p0 + 1] = z1 ? 0.f : s1;
+        if (act0) a.energy[(size_t)b * a.bstride + p0] = z0 ? 0.f : s0;
+        if (act1) a.energy[(size_t)b * a.bstride + p0 + 1] = z1 ? 0.f : s1;
       }
     }
   }
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_energy
           const int b = b0 + (t >> 1);
           const bool second = (t & 1) != 0;
           if (b < a.B && (second ? act1 : act0))
-            a.energy[(size_t)b * a.P + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : acc;
+            a.energy[(size_t)b * a.bstride + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : acc;
         }
         __syncthreads();
       } else {
@@ -286,8 +287,8 @@ __global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_energy
           for (int bb = 0; bb < 4; ++bb) {
             const int b = b0 + bb;
             if (b < a.B) {
-              if (act0) a.energy[(size_t)b * a.P + p0] = z0 ? 0.f : e1[bb];
-              if (act1) a.energy[(size_t)b * a.P + p0 + 1] = z1 ? 0.f : e2[bb];
+              if (act0) a.energy[(size_t)b * a.bstride + p0] = z0 ? 0.f : e1[bb];
+              if (act1) a.energy[(size_t)b * a.bstride + p0 + 1] = z1 ? 0.f : e2[bb];
             }
           }
         }
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
           const int b = b0 + (t >> 1);
           const bool second = (t & 1) != 0;
           if (b < a.B && (second ? act1 : act0))
-            a.energy[(size_t)b * a.P + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : acc;
+            a.energy[(size_t)b * a.bstride + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : acc;
         }
         __syncthreads();
       } else {
@@ -515,8 +516,8 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
           for (int bb = 0; bb < 4; ++bb) {
             const int b = b0 + bb;
             if (b < a.B) {
-              if (act0) a.energy[(size_t)b * a.P + p0] = z0 ? 0.f : e1[bb];
-              if (act1) a.energy[(size_t)b * a.P + p0 + 1] = z1 ? 0.f : e2[bb];
+              if (act0) a.energy[(size_t)b * a.bstride + p0] = z0 ? 0.f : e1[bb];
+              if (act1) a.energy[(size_t)b * a.bstride + p0 + 1] = z1 ? 0.f : e2[bb];
             }
           }
         }
@@ -541,8 +542,8 @@ __device__ __forceinline__ void mix_subspectrum(float2 (&z)[kE], const float2* s
 #pragma unroll
     for (int j = 0; j < 8; ++j) sacc[j] = dacc[j] = 0.f;
     for (int b = 0; b < a.B; ++b) {
-      float g0 = act0 ? __ldg(a.gain + (size_t)b * a.P + p0) : 0.f;
-      float g1 = act1 ? __ldg(a.gain + (size_t)b * a.P + p0 + 1) : 0.f;
+      float g0 = act0 ? __ldg(a.gain + (size_t)b * a.bstride + p0) : 0.f;
+      float g1 = act1 ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
       if (!(fabsf(g0) <= 3.0e38f)) { bad0 = true; g0 = 0.f; }
       if (!(fabsf(g1) <= 3.0e38f)) { bad1 = true; g1 = 0.f; }
       const float gs = 0.5f * (g0 + g1), gd = 0.5f * (g0 - g1);
@@ -721,12 +722,12 @@ __global__ void __launch_bounds__(256, 2) k_fir_edges(const FirArgs a) {
         }
         if (t == 0) {   // only this warp touches the pair's entries; exact zeros (dead pixels) stay zero
           if (act0) {
-            float* e = a.energy + (size_t)b * a.P + p0;
+            float* e = a.energy + (size_t)b * a.bstride + p0;
             const float v = *e;
             if (v != 0.f) *e = fmaxf(v - s0, 0.f);
           }
           if (act1) {
-            float* e = a.energy + (size_t)b * a.P + p0 + 1;
+            float* e = a.energy + (size_t)b * a.bstride + p0 + 1;
             const float v = *e;
             if (v != 0.f) *e = fmaxf(v - s1, 0.f);
           }
@@ -770,8 +771,8 @@ __global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_apply(
     for (int i = 0; i < kE; ++i) sacc[i] = dacc[i] = 0.f;
     bool bad0 = false, bad1 = false;   // non-finite gain: the reference's output trace is NaN (quirk 10)
     for (int b = 0; b < a.B; ++b) {
-      float g0 = act0 ? __ldg(a.gain + (size_t)b * a.P + p0) : 0.f;
-      float g1 = act1 ? __ldg(a.gain + (size_t)b * a.P + p0 + 1) : 0.f;
+      float g0 = act0 ? __ldg(a.gain + (size_t)b * a.bstride + p0) : 0.f;
+      float g1 = act1 ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
       if (!(fabsf(g0) <= 3.0e38f)) { bad0 = true; g0 = 0.f; }
       if (!(fabsf(g1) <= 3.0e38f)) { bad1 = true; g1 = 0.f; }
       const float gs = 0.5f * (g0 + g1), gd = 0.5f * (g0 - g1);
@@ -1331,7 +1332,8 @@ static int dispatch_apply_split(thz_ctx* c, cudaStream_t s, int n, const FirArgs
 }
 
 int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
-                    int B, float* d_energy) {
+                    int B, float* d_energy, int64_t bstride = 0) {
+  if (bstride == 0) bstride = P;
   if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
   if (P == 0) return THZ_OK;
   if (!d_cube || !d_energy || n < 2) return set_err(c, THZ_EINVAL, "null pointer");
@@ -1344,6 +1346,7 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
   if (rc == THZ_OK) {
     FirArgs a{};
     a.x = d_cube; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.energy = d_energy; a.tw = tb->d_tw;
+    a.bstride = bstride;
     a.wq = ft.d_wq; a.wnyq = ft.d_wnyq; a.edge = ft.d_edge;
     if (n >= 512 && ft.m >= n + THZ_FIR_TAPS - 1) {
       // Parseval total energy of the full linear convolution minus the two excluded edge segments
@@ -1371,7 +1374,8 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
 }
 
 int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d_gain, int64_t P, int n,
-                 const thz_band_plan* bands, int B, float* d_out, float* d_img) {
+                 const thz_band_plan* bands, int B, float* d_out, float* d_img, int64_t bstride = 0) {
+  if (bstride == 0) bstride = P;
   if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
   if (P == 0) return THZ_OK;
   if (!d_cube || !d_gain || !d_out || n < 2) return set_err(c, THZ_EINVAL, "null pointer");
@@ -1384,6 +1388,7 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
   if (rc == THZ_OK) {
     FirArgs a{};
     a.x = d_cube; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.gain = d_gain; a.out = d_out; a.img = d_img;
+    a.bstride = bstride;
     a.tw = tb->d_tw;
     if (ft.split) {
       const FftTables* tbn = nullptr;
@@ -1732,6 +1737,82 @@ int thz_deconvolution_host(thz_ctx* c, const float* cube, int rows, int cols, in
   cudaError_t e = cudaStreamSynchronize(c->stream);
   if (rc == THZ_OK && e != cudaSuccess) return cuda_fail(c, e, "thz_deconvolution_host");
   return rc;
+}
+
+// The whole default chain + deconvolution from host memory to host memory with the cube resident on
+// the device in between: H2D chunks overlap the fused trace pass and the band-energy pass, the gain
+// application overlaps the D2H chunks; Richardson-Lucy runs in the middle on the B small images.
+int thz_chain_host(thz_ctx* c, const float* cube, int rows, int cols, int n, const thz_band_plan* bands, int n_bands,
+                   float* out, float* img, const volatile uint8_t* abort_flag, thz_progress_fn progress,
+                   void* progress_user) {
+  CHECK_CTX(c);
+  if (c->plan.n != n) return set_err(c, THZ_ESTATE, "thz_plan_trace(n, ...) must be called first");
+  const int64_t P = (int64_t)rows * cols;
+  if (P == 0) return THZ_OK;
+  if (!cube || !out) return set_err(c, THZ_EINVAL, "null pointer");
+  if (n_bands < 0 || n_bands > THZ_MAX_BANDS || (n_bands > 0 && !bands)) return set_err(c, THZ_EINVAL, "bad bands");
+  void *pc = nullptr, *pi = nullptr, *pe = nullptr, *pg = nullptr;
+  int rc = ws_get(c, WS_HOST_CUBE, (size_t)P * n * sizeof(float), &pc);
+  if (rc == THZ_OK) rc = ws_get(c, WS_HOST_IMG, (size_t)P * sizeof(float), &pi);
+  if (rc == THZ_OK && n_bands) rc = ws_get(c, WS_ENERGY, (size_t)n_bands * P * sizeof(float), &pe);
+  if (rc == THZ_OK && n_bands) rc = ws_get(c, WS_GAIN, (size_t)n_bands * P * sizeof(float), &pg);
+  if (rc != THZ_OK) return rc;
+  float *d_cube = (float*)pc, *d_img = (float*)pi, *d_energy = (float*)pe, *d_gain = (float*)pg;
+  if (progress) progress(0.0f, progress_user);
+  // FIR tables are built (and cached) before the pipelined loop so that no chunk waits on the host
+  if (n_bands) {
+    FirTables ft;
+    rc = upload_fir_tables(c, c->stream, n, bands, n_bands, ft);
+    if (rc != THZ_OK) return rc;
+  }
+  int64_t ct = ((int64_t)256 << 20) / ((int64_t)n * 4);   // 256 MiB chunks, whole pairs
+  ct &= ~(int64_t)1;
+  if (ct < 2) ct = 2;
+  int i = 0;
+  for (int64_t p = 0; p < P && rc == THZ_OK; p += ct, ++i) {
+    const int64_t np = std::min(ct, P - p);
+    cudaStream_t s = c->hstream[i % kHostStreams];
+    float* d = d_cube + p * n;
+    THZ_CUDA(c, cudaMemcpyAsync(d, cube + p * n, (size_t)np * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = launch_trace_fused(c, s, d, d, d_img + p, np);
+    if (rc == THZ_OK && n_bands) rc = deconv_energies(c, s, d, np, n, bands, n_bands, d_energy + p, P);
+    if (rc == THZ_OK && !n_bands) {
+      THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+  }
+  for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
+  if (rc != THZ_OK) return rc;
+  if (n_bands) {
+    long total_iter = 0, done_iter = 0;
+    for (int b = 0; b < n_bands; ++b) total_iter += std::max(bands[b].n_iter, 1);
+    for (int b = 0; rc == THZ_OK && b < n_bands; ++b) {
+      if (abort_flag && *abort_flag) return THZ_ABORTED;
+      const float base = 0.1f + 0.8f * (float)done_iter / (float)total_iter;
+      const float span = 0.8f * (float)std::max(bands[b].n_iter, 1) / (float)total_iter;
+      rc = richardson_lucy(c, c->stream, d_energy + (size_t)b * P, rows, cols, bands[b].psf_x, bands[b].kx,
+                           bands[b].psf_y, bands[b].ky, nullptr, bands[b].direct, bands[b].n_iter, nullptr,
+                           d_gain + (size_t)b * P, abort_flag, progress, progress_user, base, span);
+      done_iter += std::max(bands[b].n_iter, 1);
+    }
+    if (rc != THZ_OK) return rc;
+    i = 0;
+    for (int64_t p = 0; p < P && rc == THZ_OK; p += ct, ++i) {
+      const int64_t np = std::min(ct, P - p);
+      cudaStream_t s = c->hstream[i % kHostStreams];
+      float* d = d_cube + p * n;
+      rc = deconv_apply(c, s, d, d_gain + p, np, n, bands, n_bands, d, d_img + p, P);
+      if (rc == THZ_OK)
+        THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
+    if (rc != THZ_OK) return rc;
+  }
+  if (img) {
+    THZ_CUDA(c, cudaMemcpyAsync(img, d_img, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  if (progress) progress(1.0f, progress_user);
+  return THZ_OK;
 }
 
 }  // extern "C"
