@@ -391,6 +391,10 @@ def run_e2e(a, m, ctx, d_in, d_out, P, rows, N, world, dist, barrier, P_total, b
     try:
         ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_in.ptr, nbytes))
         reps = 2
+        if world == 1:
+            # thz_chain_host keeps its own device-resident cube: release the bench's output buffer first;
+            # d_in stays as the pristine copy from which the (in-place) host buffer is restored, untimed
+            d_out.free()
 
         def once():
             if world == 1:
@@ -402,15 +406,16 @@ def run_e2e(a, m, ctx, d_in, d_out, P, rows, N, world, dist, barrier, P_total, b
                 step_dev()
                 ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_out.ptr, nbytes))
 
-        once()   # warm-up (allocates the device-resident cube / staging ring); restores nothing: re-upload input
-        ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_in.ptr, nbytes))
-        barrier()
-        t0 = time.perf_counter()
+        once()   # warm-up (allocates the device-resident cube / staging ring)
+        dt = 0.0
         for _ in range(reps):
+            ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_in.ptr, nbytes))   # restore the input, untimed
+            barrier()
+            t0 = time.perf_counter()
             once()
-        ctx.sync()
-        barrier()
-        dt = (time.perf_counter() - t0) / reps
+            ctx.sync()
+            barrier()
+            dt += (time.perf_counter() - t0) / reps
         if dist is not None:
             import torch
             tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
