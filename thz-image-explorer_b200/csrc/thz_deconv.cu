@@ -994,6 +994,148 @@ __global__ void __launch_bounds__(256, 2) k_rl_conv(const __grid_constant__ CUte
   }
 }
 
+
+// ------------------------------------------------------------------------------------
+// Persistent separable RL filtering: one CTA per SM loops over the 64x64 output tiles; the haloed
+// input tile of the NEXT tile is fetched by TMA into the other buffer while the current one is
+// filtered (column pass -> row pass -> fused epilogue).  512 threads: 880 column-pass items
+// (row, 8 columns), 512 row-pass items (column, 8 rows).
+// ------------------------------------------------------------------------------------
+constexpr int kRlThreads = 512;
+
+template <int MODE>
+__global__ void __launch_bounds__(kRlThreads, 1) k_rl_conv_persistent(const __grid_constant__ CUtensorMap tmap,
+                                                                      const ConvArgs a, int tiles_x, int tiles_y) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint64_t* mbar_ptr = reinterpret_cast<uint64_t*>(base);   // two barriers
+  const int tile_floats = (a.box_rows * a.box_cols + 31) & ~31;
+  float* tile0 = reinterpret_cast<float*>(base + 128);
+  float* tile1 = tile0 + tile_floats;
+  float* mid = tile1 + tile_floats;                           // [box_rows][kMidStride]
+  float* wxs = mid + a.box_rows * kMidStride;
+  float* wys = wxs + a.kxp;
+  const uint32_t mbar[2] = {smem_u32(mbar_ptr), smem_u32(mbar_ptr + 1)};
+  const int ntiles = tiles_x * tiles_y;
+  const uint32_t tile_bytes = (uint32_t)(a.box_rows * a.box_cols * sizeof(float));
+
+  if (threadIdx.x == 0) {
+    mbar_init(mbar[0], 1);
+    mbar_init(mbar[1], 1);
+  }
+  for (int i = threadIdx.x; i < a.kxp; i += blockDim.x) wxs[i] = a.wx[i];
+  for (int i = threadIdx.x; i < a.kyp; i += blockDim.x) wys[i] = a.wy[i];
+  __syncthreads();
+  auto origin = [&](int tidx, int& row0, int& col0) {
+    row0 = (tidx / tiles_x) * kTH;
+    col0 = (tidx % tiles_x) * kTW + a.col_shift;
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) {
+    int r0, c0;
+    origin(blockIdx.x, r0, c0);
+    mbar_expect_tx(mbar[0], tile_bytes);
+    tma_load_2d(smem_u32(tile0), &tmap, c0 - a.ky / 2, r0 - a.kx / 2, mbar[0]);
+  }
+  const int bc = a.box_cols;
+  uint32_t it = 0;
+  for (int tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x, ++it) {
+    const int buf = it & 1;
+    float* tile = buf ? tile1 : tile0;
+    int row0, col0;
+    origin(tidx, row0, col0);
+    const int nxt = tidx + gridDim.x;
+    if (threadIdx.x == 0 && nxt < ntiles) {   // the other buffer was last read before the barrier that ended
+      int r0, c0;                              // the previous iteration
+      origin(nxt, r0, c0);
+      mbar_expect_tx(mbar[buf ^ 1], tile_bytes);
+      tma_load_2d(smem_u32(buf ? tile0 : tile1), &tmap, c0 - a.ky / 2, r0 - a.kx / 2, mbar[buf ^ 1]);
+    }
+    // epilogue operands: fetch early so that their latency hides behind the column pass
+    const int c = threadIdx.x % kTW, rg = threadIdx.x / kTW;
+    float ep[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int gr = row0 + rg * 8 + q, gc = col0 + c;
+      ep[q] = 0.f;
+      if (MODE != 0 && gr < a.Hp && gc >= 0 && gc < a.Wp) {
+        const size_t o = (size_t)gr * a.pitch + gc;
+        ep[q] = (MODE == 1) ? __ldg(a.d + o) : a.out[o];
+      }
+    }
+    while (!mbar_try_wait(mbar[buf], (it >> 1) & 1)) {
+    }
+    // column pass (axis 1)
+    const int nitems = a.box_rows * (kTW / 8);
+    for (int itx = threadIdx.x; itx < nitems; itx += blockDim.x) {
+      const int r = itx % a.box_rows, cg = itx / a.box_rows;
+      const float* src = tile + r * bc + cg * 8;
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+      float win[16];
+      {
+        const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+        win[0] = v0.x; win[1] = v0.y; win[2] = v0.z; win[3] = v0.w;
+        win[4] = v1.x; win[5] = v1.y; win[6] = v1.z; win[7] = v1.w;
+      }
+      for (int nb = 0; nb < a.kyp; nb += 8) {
+        const float4 v0 = *reinterpret_cast<const float4*>(src + nb + 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + nb + 12);
+        win[8] = v0.x; win[9] = v0.y; win[10] = v0.z; win[11] = v0.w;
+        win[12] = v1.x; win[13] = v1.y; win[14] = v1.z; win[15] = v1.w;
+        const float4 w0 = *reinterpret_cast<const float4*>(wys + nb), w1 = *reinterpret_cast<const float4*>(wys + nb + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[n], win[q + n], acc[q]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) win[q] = win[q + 8];
+      }
+      float* dst = mid + r * kMidStride + cg * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+    // row pass (axis 0): one item per thread
+    {
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+      const float* src = mid + (rg * 8) * kMidStride + c;
+      float win[16];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) win[q] = src[q * kMidStride];
+      for (int mb = 0; mb < a.kxp; mb += 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int rr = rg * 8 + mb + 8 + q;
+          win[8 + q] = (rr < a.box_rows) ? mid[rr * kMidStride + c] : 0.f;
+        }
+        const float4 w0 = *reinterpret_cast<const float4*>(wxs + mb), w1 = *reinterpret_cast<const float4*>(wxs + mb + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[n], win[q + n], acc[q]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) win[q] = win[q + 8];
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int gr = row0 + rg * 8 + q, gc = col0 + c;
+        if (gr < a.Hp && gc >= 0 && gc < a.Wp) {
+          const size_t o = (size_t)gr * a.pitch + gc;
+          if constexpr (MODE == 0) a.out[o] = acc[q];
+          else if constexpr (MODE == 1) a.out[o] = ep[q] / (acc[q] + a.eps);
+          else a.out[o] = ep[q] * acc[q];
+        }
+      }
+    }
+    __syncthreads();   // tile[buf] and mid are free again
+  }
+}
+
 // numpy-"reflect" padding exactly as richardson_lucy writes it (deconvolution.rs:638-667)
 __global__ void k_reflect_pad(const float* __restrict__ img, int h, int w, int pad_y, int pad_x, float* __restrict__ out,
                               int pitch) {
@@ -1515,6 +1657,27 @@ static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUt
   a.out = out;
   dim3 grid((a.Wp - a.col_shift + kTW - 1) / kTW, (a.Hp + kTH - 1) / kTH);
   cudaError_t e;
+  if (!cp.dense) {
+    // persistent, double-buffered form: two haloed tiles + the intermediate tile
+    const int tile_floats = (a.box_rows * a.box_cols + 31) & ~31;
+    const size_t smem = (size_t)(2 * tile_floats + a.box_rows * kMidStride + a.kxp + a.kyp) * sizeof(float) + 256;
+    if (smem <= 227 * 1024) {
+      const void* pkey = (const void*)k_rl_conv_persistent<MODE>;
+      size_t& phave = c->smem_set[pkey];
+      if (phave < smem) {
+        e = cudaFuncSetAttribute(pkey, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl persistent)");
+        phave = smem;
+      }
+      const int ntiles = (int)(grid.x * grid.y);
+      const int nb = std::min(ntiles, c->sm_count);
+      k_rl_conv_persistent<MODE><<<nb, kRlThreads, smem, s>>>(map, a, (int)grid.x, (int)grid.y);
+      c->launches++;
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_conv_persistent launch");
+      return THZ_OK;
+    }
+  }
   const void* key = cp.dense ? (const void*)k_rl_conv<MODE, true> : (const void*)k_rl_conv<MODE, false>;
   size_t& have = c->smem_set[key];
   if (have < cp.smem) {
