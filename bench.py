@@ -355,14 +355,11 @@ def run_ours(a):
     stages = {"trace_fused": {"ms": trace_ms, "kernel": f"k_trace_fused<{N}>", "algorithmic_bytes": (8 * N + 4) * P}}
     if bands is not None and world == 1:
         st = ctx.deconv_stage_ms()
-        M = 64
-        while M < N + 249:
-            M *= 2
-        stages["deconv_energies"] = {"ms": st["energies_ms"], "kernel": f"k_fir_energy<{M}>",
+        stages["deconv_energies"] = {"ms": st["energies_ms"], "kernel": f"k_fir_energy_split<{N}> + k_fir_edges",
                                      "algorithmic_bytes": (4 * N + 4 * B) * P}
-        stages["deconv_apply"] = {"ms": st["apply_ms"], "kernel": f"k_fir_apply<{M}>",
+        stages["deconv_apply"] = {"ms": st["apply_ms"], "kernel": f"k_fir_apply_split<{N}>",
                                   "algorithmic_bytes": (8 * N + 4 * B) * P}
-        stages["richardson_lucy"] = {"ms": st["rl_ms"], "kernel": "k_rl_conv<1|2,separable>",
+        stages["richardson_lucy"] = {"ms": st["rl_ms"], "kernel": "k_rl_conv_persistent<1|2>",
                                      "iterations": st["rl_iterations"],
                                      "iters_per_s": st["rl_iterations"] / (st["rl_ms"] / 1e3) if st["rl_ms"] > 0 else None}
     for v in stages.values():
@@ -370,8 +367,17 @@ def run_ours(a):
             v["gbs"] = v["algorithmic_bytes"] / (v["ms"] / 1e3) / 1e9
             v["frac_of_hbm_peak"] = v["gbs"] / peak
     dom = max((k for k in stages if "algorithmic_bytes" in stages[k]), key=lambda k: stages[k]["ms"])
+    # DRAM traffic of the same kernel from the committed ncu capture (profiles/r01_traffic.json, C5 on 1 GPU)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
+        if world == 1 and (W, H, N, B if bands is not None else 8) == (2048, 2048, 4096, 8):
+            traffic = sum(v["traffic_bytes_per_launch"] for k, v in tj.items()
+                          if k.split("<")[0] in stages[dom]["kernel"])
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": stages[dom]["kernel"], "stage": dom, "achieved": stages[dom]["gbs"],
-                "peak": peak, "unit": "GB/s", "frac": stages[dom]["gbs"] / peak, "traffic": None,
+                "peak": peak, "unit": "GB/s", "frac": stages[dom]["gbs"] / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"],
                 "kernel_ms": stages[dom]["ms"]}
     # whole-step roofline: 20N + 8B + 4 bytes per trace for the three cube passes
