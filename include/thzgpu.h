@@ -140,6 +140,15 @@ int thz_trace_inverse_dev(thz_ctx* ctx, const float* d_fft, int use_band, int us
  * host vector of n floats; d_out may alias d_in. */
 int thz_time_multiply_dev(thz_ctx* ctx, const float* d_in, const float* mult, int n, float* d_out, int64_t P);
 
+/* `scaling` / `scale_3d` (src/math_tools.rs:242-310): block mean over scale x scale pixels of a
+ * [width][height][zlen] f32 array (complex arrays: zlen = 2F); output [width/scale][height/scale][zlen].
+ * Same accumulation order as the reference: bit-exact. */
+int thz_scale_blocks_dev(thz_ctx* ctx, const float* d_in, int width, int height, int zlen, int scale, float* d_out);
+int thz_scale_blocks_host(thz_ctx* ctx, const float* in, int width, int height, int zlen, int scale, float* out);
+/* Load path of `open_scan_from_thz` (src/io.rs:578-596): per-trace bias subtraction x <- x - x[0]
+ * and the initial intensity image (d_img nullable).  d_out may alias d_in. */
+int thz_bias_subtract_dev(thz_ctx* ctx, const float* d_in, int n, float* d_out, float* d_img, int64_t P);
+
 /* Pixel means that `ifft` computes first (src/math_tools.rs:421-440): mean over all P traces
  * of fft (2F floats), amplitudes (F), phases (F).  Host outputs, any may be NULL. */
 int thz_spectral_means(thz_ctx* ctx, const float* d_fft, const float* d_amp, const float* d_phase,

@@ -136,3 +136,20 @@ def test_run_fused_with_deconvolution(ctx, psf_npz_path):
     s8 = ch.slot(8)
     out, img = ch.run_fused(run_deconvolution=True)
     assert rel_err(out, s8["data"]) <= 1e-4 and rel_err(img, s8["img"]) <= 1e-4
+
+
+def test_chain_with_downscaling(ctx):
+    """scale_factor = 2: the driver's scaling stage halves the image; later stages run on 3x4 pixels."""
+    n, w, h = 512, 6, 8
+    cube = synthetic_cube(w, h, n, seed=6)
+    t = time_axis(n)
+    ch = pkg().Chain(ctx)
+    ch.set_config(scale_factor=2)
+    ch.open(t, cube, 0.5, 0.5)
+    ch.run(1)
+    p = orc.ChainParams()
+    p.config.scale_factor = 2
+    ref = orc.run_default_chain(slot0(cube, t), p)
+    ch.shape = (w // 2, h // 2, n)
+    assert np.array_equal(ch.slot(1)["data"], ref[1].data)
+    assert rel_err(ch.slot(7)["data"], ref[7].data) <= TOL_TRACE

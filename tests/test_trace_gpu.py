@@ -238,3 +238,33 @@ def test_all_zero_traces_stay_exactly_zero(ctx):
         back, _ = ctx.trace_inverse(spec)
         for (i, j) in [(0, 1), (1, 2), (2, 4), (2, 5)]:
             assert not back[i, j].any()
+
+
+@pytest.mark.parametrize("s", [2, 3])
+def test_scaling_block_mean_is_bit_exact(ctx, s):
+    """`scaling` (src/math_tools.rs:242-310): block means of data / amplitudes / phases / fft in the
+    reference's accumulation order; width and height not divisible by s drop the remainder."""
+    w, h, n = 7, 9, 128
+    rng = np.random.default_rng(s)
+    cube = rng.standard_normal((w, h, n)).astype(F32)
+    spec = (rng.standard_normal((w, h, n // 2 + 1)) + 1j * rng.standard_normal((w, h, n // 2 + 1))).astype(np.complex64)
+    t = time_axis(n)
+    inp = slot0(cube, t)
+    inp.fft = spec
+    inp.amplitudes = np.abs(spec).astype(F32)
+    inp.phases = np.angle(spec).astype(F32)
+    ref = orc.scaling(inp, orc.ConfigContainer(scale_factor=s))
+    assert np.array_equal(ctx.scale_blocks(cube, s), ref.data)
+    assert np.array_equal(ctx.scale_blocks(inp.amplitudes, s), ref.amplitudes)
+    assert np.array_equal(ctx.scale_blocks(spec, s), ref.fft)
+    assert ref.data.shape == (w // s, h // s, n)
+
+
+def test_load_path_bias_subtraction(ctx):
+    """src/io.rs:578-596: x <- x - x[0] per trace and the initial intensity image."""
+    raw = synthetic_cube(4, 5, 256, seed=2) + F32(0.37)
+    t = time_axis(256)
+    ref = orc.load_scan(t, raw, 0.5, 0.5)
+    data, img = ctx.bias_subtract(raw)
+    assert np.array_equal(data, ref.data)
+    assert rel_err(img, ref.img) <= 1e-6

@@ -147,6 +147,9 @@ def load_library():
         "thz_deconv_stage_ms": (i32, [vp, fp]),
         "thz_chain_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_deconvolution_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
+        "thz_scale_blocks_dev": (i32, [vp, fp, i32, i32, i32, i32, fp]),
+        "thz_scale_blocks_host": (i32, [vp, fp, i32, i32, i32, i32, fp]),
+        "thz_bias_subtract_dev": (i32, [vp, fp, i32, fp, fp, i64]),
         "thz_time_multiply_dev": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_time_multiply_host": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_band_apply_host": (i32, [vp, fp, fp, i64]),
@@ -454,6 +457,25 @@ class Context:
                                             len(bands) if bands is not None else 0, out.ctypes.data,
                                             img.ctypes.data, None, None, None))
         return out, img, rc
+
+    def scale_blocks(self, a, scale):
+        """`scale_3d` on a host array [width][height][z] (float32 or complex64)."""
+        a = np.ascontiguousarray(a)
+        cplx = np.iscomplexobj(a)
+        f = a.astype(np.complex64).view(np.float32) if cplx else a.astype(np.float32)
+        w, h, z = f.shape
+        out = np.empty((w // scale, h // scale, z), np.float32)
+        self._check(lib.thz_scale_blocks_host(self.handle, f.ctypes.data, w, h, z, int(scale), out.ctypes.data))
+        return out.view(np.complex64) if cplx else out
+
+    def bias_subtract(self, cube):
+        cube = _f32c(cube)
+        n = cube.shape[-1]
+        P = cube.size // n
+        d = self.to_device(cube)
+        d_img = self.alloc(max(P * 4, 16))
+        self._check(lib.thz_bias_subtract_dev(self.handle, d.ptr, n, d.ptr, d_img.ptr, P))
+        return d.download(cube.shape), d_img.download(cube.shape[:-1])
 
     def deconv_stage_ms(self):
         ms = np.zeros(4, np.float32)

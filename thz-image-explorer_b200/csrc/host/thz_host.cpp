@@ -88,11 +88,31 @@ static int multiply_stage(thz_ctx* ctx, const ScannedImageFilterData& in, const 
 // ---------------------------------------------------------------------------------------
 // built-in stages (src/math_tools.rs:242-310, 330-398, 418-571)
 // ---------------------------------------------------------------------------------------
-ScannedImageFilterData scaling(thz_ctx*, const ScannedImageFilterData& input, const ConfigContainer& config) {
-  // scale_factor <= 1 returns a clone (math_tools.rs:244-246).  Block-mean down-scaling (s > 1) is a
-  // "next" row of the scope table and is not built yet: the scan passes through unscaled.
-  (void)config;
-  return input;
+ScannedImageFilterData scaling(thz_ctx* ctx, const ScannedImageFilterData& input, const ConfigContainer& config) {
+  const int s = config.scale_factor;
+  if (s <= 1) return input;                                   // math_tools.rs:244-246
+  const size_t new_w = input.width / (size_t)s, new_h = input.height / (size_t)s;
+  if (new_w == 0 || new_h == 0) return input;                  // "scaling is too large"
+  ScannedImageFilterData out = input;
+  out.width = new_w;
+  out.height = new_h;
+  if (out.dx) out.dx = *out.dx * (float)s;
+  if (out.dy) out.dy = *out.dy * (float)s;
+  const size_t n = input.n(), F = input.f(), P = new_w * new_h;
+  const int W = (int)input.width, H = (int)input.height;
+  out.data.assign(P * n, 0.f);
+  thz_scale_blocks_host(ctx, input.data.data(), W, H, (int)n, s, out.data.data());
+  if (input.amplitudes.size() == input.pixels() * F) {
+    out.amplitudes.assign(P * F, 0.f);
+    out.phases.assign(P * F, 0.f);
+    out.fft.assign(P * F, {0.f, 0.f});
+    thz_scale_blocks_host(ctx, input.amplitudes.data(), W, H, (int)F, s, out.amplitudes.data());
+    thz_scale_blocks_host(ctx, input.phases.data(), W, H, (int)F, s, out.phases.data());
+    thz_scale_blocks_host(ctx, reinterpret_cast<const float*>(input.fft.data()), W, H, (int)(2 * F), s,
+                          reinterpret_cast<float*>(out.fft.data()));
+  }
+  out.img.assign(P, 0.f);   // the driver recomputes the intensity of the last slot
+  return out;
 }
 
 ScannedImageFilterData fft(thz_ctx* ctx, const ScannedImageFilterData& input, const ConfigContainer& config) {

@@ -555,4 +555,33 @@ int thz_spectral_means_host(thz_ctx* c, const float* fft, const float* amp, cons
   return THZ_OK;
 }
 
+int thz_scale_blocks_dev(thz_ctx* c, const float* d_in, int width, int height, int zlen, int scale, float* d_out) {
+  CHECK_CTX(c);
+  if (!d_in || !d_out || scale < 1 || width < 0 || height < 0 || zlen < 0) return set_err(c, THZ_EINVAL, "bad argument");
+  return launch_scale_blocks(c, c->stream, d_in, width, height, zlen, scale, d_out);
+}
+
+int thz_scale_blocks_host(thz_ctx* c, const float* in, int width, int height, int zlen, int scale, float* out) {
+  CHECK_CTX(c);
+  if (!in || !out || scale < 1) return set_err(c, THZ_EINVAL, "bad argument");
+  const size_t nin = (size_t)width * height * zlen, nout = (size_t)(width / scale) * (height / scale) * zlen;
+  if (nout == 0) return THZ_OK;
+  void *pi = nullptr, *po = nullptr;
+  int rc = ws_get(c, WS_SCALE_IN, nin * sizeof(float), &pi);
+  if (rc == THZ_OK) rc = ws_get(c, WS_SCALE_OUT, nout * sizeof(float), &po);
+  if (rc != THZ_OK) return rc;
+  THZ_CUDA(c, cudaMemcpyAsync(pi, in, nin * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  rc = launch_scale_blocks(c, c->stream, (const float*)pi, width, height, zlen, scale, (float*)po);
+  if (rc != THZ_OK) return rc;
+  THZ_CUDA(c, cudaMemcpyAsync(out, po, nout * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  return THZ_OK;
+}
+
+int thz_bias_subtract_dev(thz_ctx* c, const float* d_in, int n, float* d_out, float* d_img, int64_t P) {
+  CHECK_CTX(c);
+  if (!d_in || !d_out || n <= 0) return set_err(c, THZ_EINVAL, "bad argument");
+  return launch_bias_subtract(c, c->stream, d_in, n, d_out, P, d_img);
+}
+
 }  // extern "C"

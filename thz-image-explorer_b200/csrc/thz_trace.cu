@@ -485,6 +485,48 @@ __global__ void k_time_multiply(const float* __restrict__ in, const float* __res
   }
 }
 
+// `scale_3d` (src/math_tools.rs:270-298): out[nx][ny][z] = (sum_{i<s} sum_{j<s} in[nx*s+i][ny*s+j][z]) / (s*s),
+// accumulated sequentially in the reference's order (i outer, j inner) so that the result is bit-exact.
+__global__ void k_scale_blocks(const float* __restrict__ in, int width, int height, int zlen, int s, int new_w,
+                               int new_h, float* __restrict__ out) {
+  const int64_t total = (int64_t)new_w * new_h * zlen;
+  const float factor = (float)(s * s);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(idx % zlen);
+    const int64_t pix = idx / zlen;
+    const int ny = (int)(pix % new_h), nx = (int)(pix / new_h);
+    float sum = 0.f;
+    for (int i = 0; i < s; ++i)
+      for (int j = 0; j < s; ++j) {
+        const int ox = nx * s + i, oy = ny * s + j;
+        if (ox < width && oy < height) sum += __ldg(in + ((int64_t)ox * height + oy) * zlen + z);
+      }
+    out[idx] = sum / factor;
+  }
+}
+
+// load path of `open_scan_from_thz` (src/io.rs:578-596): x <- x - x[0] per trace, img = sum x^2
+__global__ void k_bias_subtract(const float* __restrict__ in, int n, float* __restrict__ out, int64_t P,
+                                float* __restrict__ img) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < P; p += nwarps) {
+    const float b = __ldg(in + p * n);
+    float acc = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float v = __ldcs(in + p * n + i) - b;
+      __stcs(out + p * n + i, v);
+      acc = fmaf(v, v, acc);
+    }
+    if (img) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) img[p] = acc;
+    }
+  }
+}
+
 // partial column sums of x[rows][cols]: block b sums rows [b*rpb, (b+1)*rpb) sequentially
 __global__ void k_column_sums(const float* __restrict__ x, int64_t rows, int cols, float* __restrict__ partials) {
   const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
@@ -766,6 +808,33 @@ int launch_time_multiply(thz_ctx* c, cudaStream_t s, const float* d_in, const fl
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(c, e, "k_time_multiply launch");
+  return THZ_OK;
+}
+
+int launch_scale_blocks(thz_ctx* c, cudaStream_t s, const float* d_in, int width, int height, int zlen, int sf,
+                        float* d_out) {
+  const int new_w = width / sf, new_h = height / sf;
+  const int64_t total = (int64_t)new_w * new_h * zlen;
+  if (total == 0) return THZ_OK;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)c->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  k_scale_blocks<<<(unsigned)blocks, 256, 0, s>>>(d_in, width, height, zlen, sf, new_w, new_h, d_out);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_scale_blocks launch");
+  return THZ_OK;
+}
+
+int launch_bias_subtract(thz_ctx* c, cudaStream_t s, const float* d_in, int n, float* d_out, int64_t P, float* d_img) {
+  if (P == 0) return THZ_OK;
+  int64_t blocks = (P * 32 + 255) / 256;
+  const int64_t cap = (int64_t)c->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  k_bias_subtract<<<(unsigned)blocks, 256, 0, s>>>(d_in, n, d_out, P, d_img);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_bias_subtract launch");
   return THZ_OK;
 }
 
