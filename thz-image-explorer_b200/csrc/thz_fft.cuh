@@ -224,23 +224,38 @@ __device__ __forceinline__ int pos_to_bin(int p) {
   }
 }
 
-// Barrier between the exchange phases of one transform.  A group of T = N/16 threads only ever
-// touches its own slice of the exchange buffer, so groups that fit in one warp (N <= 512)
-// synchronise with __syncwarp() and never stall the other groups of the CTA.
-template <int N> __device__ __forceinline__ void group_sync() {
-  if constexpr (N / kE <= 32) __syncwarp();
+// Synchronisation of the exchanges.
+//  * A group of T = N/16 threads only ever touches its own slice of the exchange buffer, so groups
+//    that fit in one warp (N <= 512) synchronise with __syncwarp() and never stall the rest of the CTA.
+//  * The exchange between stage s and s+1 moves data only inside aligned groups of S_s = L_s / R_s
+//    consecutive threads when both stages run one radix-16 butterfly per thread (block b' = b R + q of
+//    stage s+1 is written by threads [b S, (b+1) S) of stage s and read by threads inside the same
+//    range).  When S_s <= 32 those groups live inside one warp: __syncwarp() is enough (N = 4096:
+//    the exchange between the second and third stage; N = 8192: between the third and fourth).
+//  * A stage stores to exactly the positions the same thread loaded at the end of the previous
+//    exchange, so only the FIRST exchange of a transform needs a barrier in front of its stores
+//    (other threads may still be reading the buffer from whatever used it before).
+template <int N, int S_IDX> struct ExchangeScope {   // exchange between stage S_IDX and S_IDX + 1
+  static constexpr int T = N / kE;
+  static constexpr int R0 = Plan<N>::r[S_IDX], R1 = Plan<N>::r[S_IDX + 1];
+  static constexpr int S = StageLen<N, S_IDX>::value / R0;
+  static constexpr bool warp_local = (T <= 32) || (R0 == kE && R1 == kE && S <= 32);
+};
+template <bool WARP> __device__ __forceinline__ void scoped_sync() {
+  if constexpr (WARP) __syncwarp();
   else __syncthreads();
 }
+template <int N> __device__ __forceinline__ void group_sync() { scoped_sync<(N / kE <= 32)>(); }
 
 // Full forward transform: registers hold stage-0 layout (v[i] <-> element t + i*T) on entry,
-// last-stage layout (digit-reversed positions) on exit.  Uses 2 barriers per exchange.
+// last-stage layout (digit-reversed positions) on exit.
 template <int N, int S_IDX = 0>
 __device__ __forceinline__ void fft_forward(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw) {
   stage_compute<N, S_IDX, false>(v, t, tw);
   if constexpr (S_IDX + 1 < Plan<N>::ns) {
-    group_sync<N>();                       // previous readers of sm are done
+    if constexpr (S_IDX == 0) group_sync<N>();   // previous users of sm are done
     stage_store<N, S_IDX>(v, t, sm);
-    group_sync<N>();
+    scoped_sync<ExchangeScope<N, S_IDX>::warp_local>();
     stage_load<N, S_IDX + 1>(v, t, sm);
     fft_forward<N, S_IDX + 1>(v, t, sm, tw);
   }
@@ -251,9 +266,9 @@ template <int N, int S_IDX = Plan<N>::ns - 1>
 __device__ __forceinline__ void fft_inverse(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw) {
   stage_compute<N, S_IDX, true>(v, t, tw);
   if constexpr (S_IDX > 0) {
-    group_sync<N>();
+    if constexpr (S_IDX == Plan<N>::ns - 1) group_sync<N>();
     stage_store<N, S_IDX>(v, t, sm);
-    group_sync<N>();
+    scoped_sync<ExchangeScope<N, S_IDX - 1>::warp_local>();
     stage_load<N, S_IDX - 1>(v, t, sm);
     fft_inverse<N, S_IDX - 1>(v, t, sm, tw);
   }
