@@ -155,34 +155,57 @@ template <int R, bool INV> __device__ __forceinline__ void dftR(float2 (&a)[R]) 
 // Register v[u + U*m] <-> element index b*L + j + m*S, with beta = t + u*T, b = beta / S,
 // j = beta % S, U = 16/R, S = L/R.
 //   forward (DIF): butterfly then twiddle;  inverse (DIT): conj twiddle then butterfly.
+// The twiddles of a stage depend only on the thread: they are fetched into registers by load_tw()
+// ahead of the barrier of the preceding exchange (the data registers are dead at that point), so
+// their L1/L2 latency overlaps the barrier wait instead of stalling the butterfly.
 // ------------------------------------------------------------------------------------
-template <int N, int S_IDX, bool INV>
-__device__ __forceinline__ void stage_compute(float2 (&v)[kE], int t, const float2* __restrict__ tw_base) {
+template <int N, int S_IDX>
+__device__ __forceinline__ void load_tw(float2 (&w)[kE], int t, const float2* __restrict__ tw_base) {
   constexpr int T = N / kE;
   constexpr int L = StageLen<N, S_IDX>::value;
   constexpr int R = Plan<N>::r[S_IDX];
   constexpr int S = L / R;
   constexpr int U = kE / R;
+  if constexpr (S_IDX < Plan<N>::ns - 1) {
+    const float2* tw = tw_base + TwOffset<N, S_IDX>::value;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = (t + u * T) & (S - 1);
+#pragma unroll
+      for (int q = 1; q < R; ++q) w[u + U * q] = __ldg(&tw[(q - 1) * S + j]);
+    }
+  }
+}
+
+template <int N, int S_IDX, bool INV>
+__device__ __forceinline__ void stage_compute_tw(float2 (&v)[kE], const float2 (&w)[kE]) {
+  constexpr int R = Plan<N>::r[S_IDX];
+  constexpr int U = kE / R;
   constexpr bool kTw = (S_IDX < Plan<N>::ns - 1);
-  const float2* tw = tw_base + TwOffset<N, S_IDX>::value;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const int j = (t + u * T) & (S - 1);
     float2 a[R];
 #pragma unroll
     for (int m = 0; m < R; ++m) a[m] = v[u + U * m];
     if constexpr (INV && kTw) {
 #pragma unroll
-      for (int q = 1; q < R; ++q) a[q] = cmul_conj(a[q], __ldg(&tw[(q - 1) * S + j]));
+      for (int q = 1; q < R; ++q) a[q] = cmul_conj(a[q], w[u + U * q]);
     }
     dftR<R, INV>(a);
     if constexpr (!INV && kTw) {
 #pragma unroll
-      for (int q = 1; q < R; ++q) a[q] = cmul(a[q], __ldg(&tw[(q - 1) * S + j]));
+      for (int q = 1; q < R; ++q) a[q] = cmul(a[q], w[u + U * q]);
     }
 #pragma unroll
     for (int m = 0; m < R; ++m) v[u + U * m] = a[m];
   }
+}
+
+template <int N, int S_IDX, bool INV>
+__device__ __forceinline__ void stage_compute(float2 (&v)[kE], int t, const float2* __restrict__ tw_base) {
+  float2 w[kE];
+  load_tw<N, S_IDX>(w, t, tw_base);
+  stage_compute_tw<N, S_IDX, INV>(v, w);
 }
 
 // element index owned by register i = u + U*m of thread t at stage S_IDX
@@ -247,31 +270,66 @@ template <bool WARP> __device__ __forceinline__ void scoped_sync() {
 }
 template <int N> __device__ __forceinline__ void group_sync() { scoped_sync<(N / kE <= 32)>(); }
 
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+
 // Full forward transform: registers hold stage-0 layout (v[i] <-> element t + i*T) on entry,
-// last-stage layout (digit-reversed positions) on exit.
-template <int N, int S_IDX = 0>
-__device__ __forceinline__ void fft_forward(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw) {
-  stage_compute<N, S_IDX, false>(v, t, tw);
+// last-stage layout (digit-reversed positions) on exit.  `w` holds the twiddles of stage S_IDX
+// (preloaded by the caller or by the previous exchange); `hook` runs between the stores and the
+// barrier of the LAST exchange (callers prefetch the operands of their epilogue there).
+template <int N, int S_IDX, typename Hook>
+__device__ __forceinline__ void fft_forward_rec(float2 (&v)[kE], float2 (&w)[kE], int t, float2* sm,
+                                                const float2* __restrict__ tw, Hook& hook) {
+  stage_compute_tw<N, S_IDX, false>(v, w);
   if constexpr (S_IDX + 1 < Plan<N>::ns) {
     if constexpr (S_IDX == 0) group_sync<N>();   // previous users of sm are done
     stage_store<N, S_IDX>(v, t, sm);
+    load_tw<N, S_IDX + 1>(w, t, tw);             // in flight across the barrier
+    if constexpr (S_IDX + 2 == Plan<N>::ns) hook();
     scoped_sync<ExchangeScope<N, S_IDX>::warp_local>();
     stage_load<N, S_IDX + 1>(v, t, sm);
-    fft_forward<N, S_IDX + 1>(v, t, sm, tw);
+    fft_forward_rec<N, S_IDX + 1>(v, w, t, sm, tw, hook);
   }
+}
+template <int N, typename Hook>
+__device__ __forceinline__ void fft_forward_hook(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw,
+                                                 Hook& hook) {
+  float2 w[kE];
+  load_tw<N, 0>(w, t, tw);
+  fft_forward_rec<N, 0>(v, w, t, sm, tw, hook);
+}
+template <int N>
+__device__ __forceinline__ void fft_forward(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw) {
+  NoHook h;
+  fft_forward_hook<N>(v, t, sm, tw, h);
 }
 
 // Full inverse (unnormalised) transform: last-stage layout in, stage-0 layout out.
-template <int N, int S_IDX = Plan<N>::ns - 1>
-__device__ __forceinline__ void fft_inverse(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw) {
-  stage_compute<N, S_IDX, true>(v, t, tw);
+template <int N, int S_IDX, typename Hook>
+__device__ __forceinline__ void fft_inverse_rec(float2 (&v)[kE], float2 (&w)[kE], int t, float2* sm,
+                                                const float2* __restrict__ tw, Hook& hook) {
+  stage_compute_tw<N, S_IDX, true>(v, w);
   if constexpr (S_IDX > 0) {
     if constexpr (S_IDX == Plan<N>::ns - 1) group_sync<N>();
     stage_store<N, S_IDX>(v, t, sm);
+    load_tw<N, S_IDX - 1>(w, t, tw);
+    if constexpr (S_IDX == 1) hook();
     scoped_sync<ExchangeScope<N, S_IDX - 1>::warp_local>();
     stage_load<N, S_IDX - 1>(v, t, sm);
-    fft_inverse<N, S_IDX - 1>(v, t, sm, tw);
+    fft_inverse_rec<N, S_IDX - 1>(v, w, t, sm, tw, hook);
   }
+}
+template <int N, typename Hook>
+__device__ __forceinline__ void fft_inverse_hook(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw,
+                                                 Hook& hook) {
+  float2 w[kE];   // the last stage has no twiddles
+  fft_inverse_rec<N, Plan<N>::ns - 1>(v, w, t, sm, tw, hook);
+}
+template <int N>
+__device__ __forceinline__ void fft_inverse(float2 (&v)[kE], int t, float2* sm, const float2* __restrict__ tw) {
+  NoHook h;
+  fft_inverse_hook<N>(v, t, sm, tw, h);
 }
 
 // ------------------------------------------------------------------------------------

@@ -225,15 +225,21 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(
     bool nz0, nz1, z0, z1;
     load_pair_staged<N>(v, a, slab[buf], t, g, act0, act1, nz0, nz1);
     nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
-    fft_forward<N>(v, t, sm, a.tw);
-    // band-pass in digit-reversed order: register (u, m) <-> position (t + u*T)*RL + m,
-    // hq is stored [m][beta] so that a warp reads consecutive floats
+    // band-pass in digit-reversed order: register (u, m) <-> position (t + u*T)*RL + m, hq is stored
+    // [m][beta] so that a warp reads consecutive floats; fetched while the last exchange is in flight
+    float hq[kE];
+    auto fetch_hq = [&]() {
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        const int u = i % UL, m = i / UL;
+        hq[i] = __ldg(a.hq + m * (N / RL) + t + u * T);
+      }
+    };
+    fft_forward_hook<N>(v, t, sm, a.tw, fetch_hq);
 #pragma unroll
     for (int i = 0; i < kE; ++i) {
-      const int u = i % UL, m = i / UL;
-      const float h = __ldg(a.hq + m * (N / RL) + t + u * T);
-      v[i].x *= h;
-      v[i].y *= h;
+      v[i].x *= hq[i];
+      v[i].y *= hq[i];
     }
     fft_inverse<N>(v, t, sm, a.tw);
     nz_resolve<T>(g, parity, nzbuf, z0, z1);
