@@ -149,6 +149,17 @@ int thz_scale_blocks_host(thz_ctx* ctx, const float* in, int width, int height, 
  * and the initial intensity image (d_img nullable).  d_out may alias d_in. */
 int thz_bias_subtract_dev(thz_ctx* ctx, const float* d_in, int n, float* d_out, float* d_img, int64_t P);
 
+/* `average_polygon_roi` (src/math_tools.rs:599-661): mean over the pixels inside a polygon of a device array
+ * [dim0][dim1][zlen] (data, amplitudes or phases); polygon vertices (x, y) are divided by `scaling`; the
+ * reference's row flip data[[dim0 - y - 1, x, z]], unsigned ray-casting arithmetic and sequential f32
+ * summation order are kept.  `out` is a host vector of zlen floats. */
+int thz_roi_average_dev(thz_ctx* ctx, const float* d_data, int dim0, int dim1, int zlen, const int64_t* poly_x,
+                        const int64_t* poly_y, int n_points, int scaling, float* out);
+/* `calculate_optical_properties` (src/math_tools.rs:663-701), host arithmetic on F values; outputs nullable. */
+int thz_optical_properties(const float* sample_amp, const float* sample_phase, const float* ref_amp,
+                           const float* ref_phase, const float* freqs, int f, float thickness, float* n_out,
+                           float* alpha_out, float* kappa_out);
+
 /* Pixel means that `ifft` computes first (src/math_tools.rs:421-440): mean over all P traces
  * of fft (2F floats), amplitudes (F), phases (F).  Host outputs, any may be NULL. */
 int thz_spectral_means(thz_ctx* ctx, const float* d_fft, const float* d_amp, const float* d_phase,

@@ -1088,3 +1088,47 @@ def calculate_optical_properties(sample_amp, sample_phase, ref_amp, ref_phase, f
         alpha = F32(-2.0) / d * np.log(arg.astype(np.float64)).astype(F32)
         kappa = alpha * C_LIGHT / (F32(4.0) * PI32 * f_hz)
     return n.astype(F32), alpha.astype(F32), kappa.astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# ROI averages (src/math_tools.rs:572-661) -- "next" row, restated for completeness
+# --------------------------------------------------------------------------------------
+_U64 = (1 << 64) - 1
+
+
+def point_in_polygon(x, y, polygon):
+    """Ray casting with the reference's `usize` arithmetic (release build: wrapping)."""
+    inside = False
+    j = len(polygon) - 1
+    for i in range(len(polygon)):
+        xi, yi = polygon[i]
+        xj, yj = polygon[j]
+        if (yi > y) != (yj > y):
+            num = (((xj - xi) & _U64) * ((y - yi) & _U64)) & _U64
+            den = (yj - yi) & _U64
+            if x < (((num // den) + xi) & _U64):
+                inside = not inside
+        j = i
+    return inside
+
+
+def average_polygon_roi(data, polygon, scaling=1):
+    """`average_polygon_roi` (src/math_tools.rs:599-661): sequential f32 sums over the pixels inside the
+    polygon (bounding box scan y outer, x inner; row index flipped: data[y_size - y - 1, x, :])."""
+    data = np.asarray(data, dtype=F32)
+    poly = [(int(x) // scaling, int(y) // scaling) for x, y in polygon]
+    y_size, x_size, z_size = data.shape
+    x_min = min(min(p[0] for p in poly), x_size - 1)
+    y_min = min(min(p[1] for p in poly), y_size - 1)
+    x_max = min(max(p[0] for p in poly), x_size - 1)
+    y_max = min(max(p[1] for p in poly), y_size - 1)
+    result = np.zeros(z_size, dtype=F32)
+    count = 0
+    for y in range(y_min, y_max + 1):
+        for x in range(x_min, x_max + 1):
+            if point_in_polygon(x, y, poly):
+                result = result + data[y_size - y - 1, x, :]
+                count += 1
+    if count > 0:
+        result = result / F32(count)
+    return result.astype(F32)

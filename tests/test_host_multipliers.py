@@ -57,3 +57,17 @@ def test_gate_and_band_indices():
     b, bl, bu = h.band_pass(f, 0.1, 1.0, 0.1)
     assert (bl, bu) == orc.fd_band_indices(f, 0.1, 1.0)
     _close(b, orc.fd_band_multiplier(f, 0.1, 1.0, 0.1))
+
+
+def test_optical_properties_match_oracle():
+    """calculate_optical_properties (src/math_tools.rs:663-701), host routine of the library."""
+    h = pkg().host
+    rng = np.random.default_rng(0)
+    f = (np.arange(1, 200, dtype=F32) * F32(0.01)).astype(F32)
+    sa, ra = rng.uniform(0.1, 2.0, f.size).astype(F32), rng.uniform(0.5, 3.0, f.size).astype(F32)
+    sp, rp = np.cumsum(rng.uniform(-0.5, 0.1, f.size)).astype(F32), np.cumsum(rng.uniform(-0.4, 0.1, f.size)).astype(F32)
+    n, al, ka = h.optical_properties(sa, sp, ra, rp, f, 1e-3)
+    on, oal, oka = orc.calculate_optical_properties(sa, sp, ra, rp, f, 1e-3)
+    np.testing.assert_allclose(n, on, rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(al, oal, rtol=2e-5, atol=1e-3)
+    np.testing.assert_allclose(ka, oka, rtol=2e-5, atol=1e-9)

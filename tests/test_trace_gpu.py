@@ -268,3 +268,16 @@ def test_load_path_bias_subtraction(ctx):
     data, img = ctx.bias_subtract(raw)
     assert np.array_equal(data, ref.data)
     assert rel_err(img, ref.img) <= 1e-6
+
+
+def test_roi_polygon_average(ctx):
+    """average_polygon_roi (src/math_tools.rs:599-661): same pixels (unsigned ray casting, row flip) and the
+    same sequential f32 summation order -> bit-exact."""
+    rng = np.random.default_rng(4)
+    data = rng.standard_normal((24, 30, 65)).astype(F32)
+    for poly, s in [([(3, 2), (20, 4), (25, 18), (8, 21)], 1), ([(10, 4), (50, 10), (40, 40), (6, 30)], 2),
+                    ([(0, 0), (29, 0), (29, 23), (0, 23)], 1)]:
+        ref = orc.average_polygon_roi(data, poly, s)
+        got = ctx.roi_average(data, poly, s)
+        assert np.array_equal(got, ref), (poly, s)
+    assert np.abs(orc.average_polygon_roi(data, [(3, 2), (20, 4), (25, 18), (8, 21)], 1)).max() > 0

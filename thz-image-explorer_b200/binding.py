@@ -150,6 +150,8 @@ def load_library():
         "thz_scale_blocks_dev": (i32, [vp, fp, i32, i32, i32, i32, fp]),
         "thz_scale_blocks_host": (i32, [vp, fp, i32, i32, i32, i32, fp]),
         "thz_bias_subtract_dev": (i32, [vp, fp, i32, fp, fp, i64]),
+        "thz_roi_average_dev": (i32, [vp, fp, i32, i32, i32, fp, fp, i32, i32, fp]),
+        "thz_optical_properties": (i32, [fp, fp, fp, fp, fp, i32, f32, fp, fp, fp]),
         "thz_time_multiply_dev": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_time_multiply_host": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_band_apply_host": (i32, [vp, fp, fp, i64]),
@@ -476,6 +478,18 @@ class Context:
         d_img = self.alloc(max(P * 4, 16))
         self._check(lib.thz_bias_subtract_dev(self.handle, d.ptr, n, d.ptr, d_img.ptr, P))
         return d.download(cube.shape), d_img.download(cube.shape[:-1])
+
+    def roi_average(self, data, polygon, scaling=1):
+        """`average_polygon_roi` of a host array [dim0][dim1][z] (uploaded for the call)."""
+        data = _f32c(data)
+        d0, d1, z = data.shape
+        d = self.to_device(data)
+        px = np.ascontiguousarray([p[0] for p in polygon], np.int64)
+        py = np.ascontiguousarray([p[1] for p in polygon], np.int64)
+        out = np.empty(z, np.float32)
+        self._check(lib.thz_roi_average_dev(self.handle, d.ptr, d0, d1, z, px.ctypes.data, py.ctypes.data, px.size,
+                                            int(scaling), out.ctypes.data))
+        return out
 
     def deconv_stage_ms(self):
         ms = np.zeros(4, np.float32)

@@ -584,4 +584,51 @@ int thz_bias_subtract_dev(thz_ctx* c, const float* d_in, int n, float* d_out, fl
   return launch_bias_subtract(c, c->stream, d_in, n, d_out, P, d_img);
 }
 
+// point_in_polygon with the reference's `usize` arithmetic (release build: wrapping), src/math_tools.rs:573-591
+static bool point_in_polygon(uint64_t x, uint64_t y, const std::vector<std::pair<uint64_t, uint64_t>>& poly) {
+  bool inside = false;
+  size_t j = poly.size() - 1;
+  for (size_t i = 0; i < poly.size(); ++i) {
+    const uint64_t xi = poly[i].first, yi = poly[i].second, xj = poly[j].first, yj = poly[j].second;
+    if ((yi > y) != (yj > y)) {
+      const uint64_t lim = (xj - xi) * (y - yi) / (yj - yi) + xi;   // unsigned wrap-around, as in Rust release
+      if (x < lim) inside = !inside;
+    }
+    j = i;
+  }
+  return inside;
+}
+
+int thz_roi_average_dev(thz_ctx* c, const float* d_data, int dim0, int dim1, int zlen, const int64_t* poly_x,
+                        const int64_t* poly_y, int n_points, int scaling, float* out) {
+  CHECK_CTX(c);
+  if (!d_data || !poly_x || !poly_y || !out || n_points < 1 || dim0 < 1 || dim1 < 1 || zlen < 1 || scaling < 1)
+    return set_err(c, THZ_EINVAL, "bad argument");
+  std::vector<std::pair<uint64_t, uint64_t>> poly(n_points);
+  for (int i = 0; i < n_points; ++i) poly[i] = {(uint64_t)poly_x[i] / (uint64_t)scaling, (uint64_t)poly_y[i] / (uint64_t)scaling};
+  const uint64_t x_size = (uint64_t)dim1, y_size = (uint64_t)dim0;
+  uint64_t x_min = UINT64_MAX, y_min = UINT64_MAX, x_max = 0, y_max = 0;
+  for (auto& p : poly) {
+    x_min = std::min(x_min, p.first); y_min = std::min(y_min, p.second);
+    x_max = std::max(x_max, p.first); y_max = std::max(y_max, p.second);
+  }
+  x_min = std::min(x_min, x_size - 1); y_min = std::min(y_min, y_size - 1);
+  x_max = std::min(x_max, x_size - 1); y_max = std::min(y_max, y_size - 1);
+  std::vector<int64_t> pix;
+  for (uint64_t y = y_min; y <= y_max; ++y)
+    for (uint64_t x = x_min; x <= x_max; ++x)
+      if (point_in_polygon(x, y, poly)) pix.push_back((int64_t)((y_size - y - 1) * x_size + x));   // data[[y_size-y-1, x, z]]
+  void *dp = nullptr, *dout = nullptr;
+  int rc = ws_get(c, WS_ROI_PIX, std::max<size_t>(pix.size(), 1) * sizeof(int64_t), &dp);
+  if (rc == THZ_OK) rc = ws_get(c, WS_ROI_OUT, (size_t)zlen * sizeof(float), &dout);
+  if (rc != THZ_OK) return rc;
+  if (!pix.empty())
+    THZ_CUDA(c, cudaMemcpyAsync(dp, pix.data(), pix.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  rc = launch_roi_average(c, c->stream, d_data, (const int64_t*)dp, (int)pix.size(), zlen, (float*)dout);
+  if (rc != THZ_OK) return rc;
+  THZ_CUDA(c, cudaMemcpyAsync(out, dout, (size_t)zlen * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  return THZ_OK;
+}
+
 }  // extern "C"

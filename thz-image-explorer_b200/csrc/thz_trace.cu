@@ -533,6 +533,17 @@ __global__ void k_bias_subtract(const float* __restrict__ in, int n, float* __re
   }
 }
 
+// `average_polygon_roi` inner loops (src/math_tools.rs:636-659): out[z] = (sum over the listed pixels, in list
+// order, of data[pix][z]) / count -- one thread per z keeps the reference's sequential f32 summation order.
+__global__ void k_roi_average(const float* __restrict__ data, const int64_t* __restrict__ pix, int npix, int zlen,
+                              float* __restrict__ out) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= zlen) return;
+  float acc = 0.f;
+  for (int i = 0; i < npix; ++i) acc += __ldg(data + pix[i] * zlen + z);
+  out[z] = npix > 0 ? acc / (float)npix : acc;
+}
+
 // partial column sums of x[rows][cols]: block b sums rows [b*rpb, (b+1)*rpb) sequentially
 __global__ void k_column_sums(const float* __restrict__ x, int64_t rows, int cols, float* __restrict__ partials) {
   const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
@@ -841,6 +852,16 @@ int launch_bias_subtract(thz_ctx* c, cudaStream_t s, const float* d_in, int n, f
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(c, e, "k_bias_subtract launch");
+  return THZ_OK;
+}
+
+int launch_roi_average(thz_ctx* c, cudaStream_t s, const float* d_data, const int64_t* d_pix, int npix, int zlen,
+                       float* d_out) {
+  if (zlen <= 0) return THZ_OK;
+  k_roi_average<<<(zlen + 127) / 128, 128, 0, s>>>(d_data, d_pix, npix, zlen, d_out);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_roi_average launch");
   return THZ_OK;
 }
 

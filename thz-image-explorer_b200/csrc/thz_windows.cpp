@@ -148,4 +148,28 @@ int thz_band_pass_multiplier(const float* freq, int f, double low, double high, 
   return THZ_OK;
 }
 
+/* `calculate_optical_properties` (src/math_tools.rs:663-701): refractive index, absorption and extinction
+ * coefficient per bin from a sample and a reference spectrum (selected pixel or ROI mean; F values). */
+int thz_optical_properties(const float* sample_amp, const float* sample_phase, const float* ref_amp,
+                           const float* ref_phase, const float* freqs, int f, float thickness, float* n_out,
+                           float* alpha_out, float* kappa_out) {
+  if (!sample_amp || !sample_phase || !ref_amp || !ref_phase || !freqs || f < 0) return THZ_EINVAL;
+  const float kC = 2.99792458e8f;
+  for (int i = 0; i < f; ++i) {
+    const float frequency_hz = freqs[i] * 1.0e12f;
+    const float delta_phi = sample_phase[i] - ref_phase[i];
+    const float omega = 2.0f * kPi * frequency_hz;
+    const float n = 1.0f + kC * delta_phi / (omega * thickness);
+    const float amp = std::max(sample_amp[i], 1e-12f), amp_ref = std::max(ref_amp[i], 1e-12f);
+    const float n_safe = std::max(n, 1e-6f);
+    const float np1 = n_safe + 1.0f;
+    const float alpha = -2.0f / thickness * logf((np1 * np1) / (4.0f * n_safe) * amp / amp_ref);
+    const float kappa = alpha * kC / (4.0f * kPi * frequency_hz);
+    if (n_out) n_out[i] = n;
+    if (alpha_out) alpha_out[i] = alpha;
+    if (kappa_out) kappa_out[i] = kappa;
+  }
+  return THZ_OK;
+}
+
 }  // extern "C"

@@ -195,3 +195,13 @@ class Deconvolution:
             return None, SKIP_REASONS[rc]
         _chk(rc, "thz_deconv_plan_bands")
         return bands, None
+
+
+def optical_properties(sample_amp, sample_phase, ref_amp, ref_phase, freqs, thickness):
+    """`calculate_optical_properties` -> (n, alpha, kappa), computed by the library's host routine."""
+    arrs = [np.ascontiguousarray(a, np.float32) for a in (sample_amp, sample_phase, ref_amp, ref_phase, freqs)]
+    f = arrs[4].size
+    n, al, ka = (np.empty(f, np.float32) for _ in range(3))
+    _chk(lib.thz_optical_properties(*[a.ctypes.data for a in arrs], f, float(thickness), n.ctypes.data,
+                                    al.ctypes.data, ka.ctypes.data), "thz_optical_properties")
+    return n, al, ka
