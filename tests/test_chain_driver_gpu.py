@@ -153,3 +153,28 @@ def test_chain_with_downscaling(ctx):
     ch.shape = (w // 2, h // 2, n)
     assert np.array_equal(ch.slot(1)["data"], ref[1].data)
     assert rel_err(ch.slot(7)["data"], ref[7].data) <= TOL_TRACE
+
+
+def test_chain_driver_non_power_of_two(ctx, psf_npz_path):
+    """The whole driver (stage by stage and fused, with deconvolution) on N = 1000 samples."""
+    m = pkg()
+    n, w, h = 1000, 34, 32
+    cube = synthetic_cube(w, h, n, seed=13, noise=0.02)
+    t = time_axis(n)
+    slots = orc.run_default_chain(slot0(cube, t, 1.0, 1.0))
+    ch = m.Chain(ctx)
+    ch.open(t, cube, 1.0, 1.0)
+    ch.run(1)
+    assert rel_err(ch.slot(4)["fft"], slots[4].fft) <= TOL_TRACE
+    assert rel_err(ch.slot(7)["data"], slots[7].data) <= TOL_TRACE
+    assert rel_err(ch.slot(8)["img"], slots[7].img) <= TOL_TRACE
+    ch.set_active("Deconvolution", True)
+    ch.set_param("Deconvolution", "n_filters", 4)
+    ch.set_param("Deconvolution", "n_iterations", 8)
+    ch.set_psf(m.host.PSF.load(psf_npz_path))
+    out, img = ch.run_fused(run_deconvolution=True)
+    opsf = orc.load_psf(psf_npz_path)
+    sin = orc.ScannedImageFilterData(time=t, data=slots[7].data, frequency=orc.frequency_axis(t),
+                                     img=slots[7].img, dx=1.0, dy=1.0, width=w, height=h)
+    ref = orc.Deconvolution(n_filters=4, n_iterations=8).filter(sin, opsf)
+    assert rel_err(out, ref.data) <= TOL_MAP and rel_err(img, ref.img) <= TOL_MAP

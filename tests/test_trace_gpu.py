@@ -281,3 +281,35 @@ def test_roi_polygon_average(ctx):
         got = ctx.roi_average(data, poly, s)
         assert np.array_equal(got, ref), (poly, s)
     assert np.abs(orc.average_polygon_roi(data, [(3, 2), (20, 4), (25, 18), (8, 21)], 1)).max() > 0
+
+
+@pytest.mark.parametrize("n", [100, 750, 1000, 2001, 3000, 4095])
+def test_arbitrary_length_traces(ctx, n):
+    """Trace lengths that are not a power of two (real scans; realfft accepts any N): chirp-z kernels.
+    Forward, fused chain and inverse against the oracle (scipy's pocketfft handles any N)."""
+    w, h = 3, 5
+    cube = synthetic_cube(w, h, n, seed=n)
+    t, m_pre, band, m_post = default_multipliers(n)
+    slots = _chain_oracle(cube, t)
+    cfg = orc.ConfigContainer()
+    win = orc.fft_window_multiplier(t, cfg.fft_window_type, cfg.fft_window)
+    ref4 = orc.fft(slot0(cube, t), cfg)
+    ctx.plan_trace(n, m_pre=win)
+    got = ctx.trace_forward(cube)
+    assert np.array_equal(got["windowed"], ref4.data)
+    assert rel_err(got["fft"], ref4.fft) <= TOL_TRACE
+    assert rel_err(got["amp"], ref4.amplitudes) <= TOL_TRACE
+    tol_rad = max(TOL_TRACE * float(np.abs(ref4.phases).max()), 2e-3)
+    check_unwrapped_phase(got["phase"], ref4.phases, ref4.fft, tol_rad)
+    ctx.plan_trace(n, m_pre, band, m_post)
+    out, img = ctx.trace_fused(cube)
+    assert rel_err(out, slots[7].data) <= TOL_TRACE
+    assert rel_err(img, slots[7].img) <= TOL_TRACE
+    back, _ = ctx.trace_inverse(slots[5].fft)
+    assert rel_err(back, slots[6].data) <= TOL_TRACE
+    back2, img2 = ctx.trace_inverse(slots[4].fft, use_band=True, use_post=True, want_img=True)
+    assert rel_err(back2, slots[7].data) <= TOL_TRACE and rel_err(img2, slots[7].img) <= TOL_TRACE
+    # dead pixel stays exactly zero here too
+    cube[1, 2] = 0.0
+    out, img = ctx.trace_fused(cube)
+    assert not out[1, 2].any() and img[1, 2] == 0.0

@@ -77,7 +77,8 @@ static std::vector<float> frequency_of(const std::vector<float>& time) {
   return f;
 }
 
-static bool gpu_size_ok(size_t n) { return n >= 64 && n <= 8192 && (n & (n - 1)) == 0; }
+// power of two in [64, 8192] (fast kernels) or any length up to 4096 (chirp-z kernels)
+static bool gpu_size_ok(size_t n) { return (n >= 64 && n <= 8192 && (n & (n - 1)) == 0) || (n >= 2 && n <= 4096); }
 
 // a time-domain stage that multiplies every trace by one vector
 static int multiply_stage(thz_ctx* ctx, const ScannedImageFilterData& in, const std::vector<float>& mult,
@@ -399,7 +400,7 @@ void ChainDriver::open(const std::vector<float>& time, const float* data, size_t
   s.amplitudes.assign(P * F, 0.f);
   s.phases.assign(P * F, 0.f);
   s.img.assign(P, 0.f);
-  if (P && n % 4 == 0) thz_intensity_host(ctx_, s.data.data(), (int)n, s.img.data(), (int64_t)P);
+  if (P) thz_intensity_host(ctx_, s.data.data(), (int)n, s.img.data(), (int64_t)P);
   filter_data_pipeline[0] = std::move(s);
   const size_t shape[3] = {width, height, n};
   for (auto& kv : filters_) kv.second->reset(time, shape);   // data_thread.rs:1027-1060
@@ -443,7 +444,7 @@ int ChainDriver::run(size_t start_idx, bool run_deconvolution) {
   }
   // intensity image of the last slot (data_thread.rs:1243-1308)
   auto& last = fd[filter_uuid_to_index[filter_chain.back()]];
-  if (last.pixels() && last.n() % 4 == 0) {
+  if (last.pixels()) {
     last.img.assign(last.pixels(), 0.f);
     thz_intensity_host(ctx_, last.data.data(), (int)last.n(), last.img.data(), (int64_t)last.pixels());
   }
@@ -453,7 +454,7 @@ int ChainDriver::run(size_t start_idx, bool run_deconvolution) {
 int ChainDriver::run_fused(bool run_deconvolution) {
   const ScannedImageFilterData& s0 = filter_data_pipeline[0];
   const size_t n = s0.n(), P = s0.pixels();
-  if (!gpu_size_ok(n)) { last_error = "n must be a power of two in [64, 8192]"; return THZ_EINVAL; }
+  if (!gpu_size_ok(n)) { last_error = "unsupported trace length"; return THZ_EINVAL; }
   auto active = [&](const std::string& name) {
     const std::string u = uuid_of(name);
     return !u.empty() && filters_active[u];

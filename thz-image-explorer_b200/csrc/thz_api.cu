@@ -164,6 +164,9 @@ void thz_ctx_destroy(thz_ctx* c) {
   if (c->plan.d_m_post) cudaFree(c->plan.d_m_post);
   if (c->plan.d_band) cudaFree(c->plan.d_band);
   if (c->plan.d_hq) cudaFree(c->plan.d_hq);
+  if (c->plan.d_chirp) cudaFree(c->plan.d_chirp);
+  if (c->plan.d_bhat) cudaFree(c->plan.d_bhat);
+  if (c->plan.d_hn) cudaFree(c->plan.d_hn);
   if (c->d_scratch) cudaFree(c->d_scratch);
   for (auto& kv : c->ws)
     if (kv.second.first) cudaFree(kv.second.first);
@@ -254,10 +257,10 @@ int thz_generate_cube(thz_ctx* c, float* d_cube, int width, int height, int n, i
 
 int thz_plan_trace(thz_ctx* c, int n, const float* m_pre, const float* band, const float* m_post) {
   CHECK_CTX(c);
-  if (!supported_n(n)) return set_err(c, THZ_EINVAL, "n must be a power of two in [64, 8192]");
-  const FftTables* tb = nullptr;
-  int rc = get_tables(c, n, &tb);
-  if (rc != THZ_OK) return rc;
+  const bool pow2 = supported_n(n);
+  if (!pow2 && !blue_supported(n))
+    return set_err(c, THZ_EINVAL, "n must be a power of two in [64, 8192] or any length in [2, 4096]");
+  int rc;
   // make sure no kernel still reads the old vectors
   THZ_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < kHostStreams; ++i) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[i]));
@@ -269,10 +272,28 @@ int thz_plan_trace(thz_ctx* c, int n, const float* m_pre, const float* band, con
   if (m_pre && (rc = upload_vec(c, &p.d_m_pre, m_pre, n)) != THZ_OK) return rc;
   if (m_post && (rc = upload_vec(c, &p.d_m_post, m_post, n)) != THZ_OK) return rc;
   if (band && (rc = upload_vec(c, &p.d_band, band, n / 2 + 1)) != THZ_OK) return rc;
-  std::vector<float> hq;
-  if (build_hq(n, band, hq) != THZ_OK) return set_err(c, THZ_EINVAL, "unsupported n");
-  if ((rc = upload_vec(c, &p.d_hq, hq.data(), n)) != THZ_OK) return rc;
-  THZ_CUDA(c, cudaStreamSynchronize(c->stream));   // hq is a local
+  if (pow2) {
+    const FftTables* tb = nullptr;
+    if ((rc = get_tables(c, n, &tb)) != THZ_OK) return rc;
+    p.blue_m = 0;
+    std::vector<float> hq;
+    if (build_hq(n, band, hq) != THZ_OK) return set_err(c, THZ_EINVAL, "unsupported n");
+    if ((rc = upload_vec(c, &p.d_hq, hq.data(), n)) != THZ_OK) return rc;
+    THZ_CUDA(c, cudaStreamSynchronize(c->stream));   // hq is a local
+    return THZ_OK;
+  }
+  // arbitrary length: chirp-z tables
+  std::vector<float2> chirp, bhat;
+  std::vector<float> hn;
+  int m = 0;
+  if (build_bluestein_tables(n, band, chirp, bhat, hn, m) != THZ_OK) return set_err(c, THZ_EINVAL, "unsupported n");
+  const FftTables* tb = nullptr;
+  if ((rc = get_tables(c, m, &tb)) != THZ_OK) return rc;
+  if ((rc = upload_vec(c, (float**)&p.d_chirp, (const float*)chirp.data(), 2 * (size_t)n)) != THZ_OK) return rc;
+  if ((rc = upload_vec(c, (float**)&p.d_bhat, (const float*)bhat.data(), 2 * (size_t)m)) != THZ_OK) return rc;
+  if ((rc = upload_vec(c, &p.d_hn, hn.data(), n)) != THZ_OK) return rc;
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  p.blue_m = m;
   return THZ_OK;
 }
 
@@ -479,7 +500,7 @@ static int elementwise_host(thz_ctx* c, const float* in, float* out, float* img,
 int thz_time_multiply_host(thz_ctx* c, const float* in, const float* mult, int n, float* out, int64_t P) {
   CHECK_CTX(c);
   if (P == 0) return THZ_OK;
-  if (!in || !out || n <= 0 || n % 4) return set_err(c, THZ_EINVAL, "bad argument");
+  if (!in || !out || n <= 0) return set_err(c, THZ_EINVAL, "bad argument");
   float* d_m = nullptr;
   int rc = upload_mult(c, c->stream, mult, n, &d_m);
   if (rc != THZ_OK) return rc;
@@ -489,7 +510,7 @@ int thz_time_multiply_host(thz_ctx* c, const float* in, const float* mult, int n
 int thz_intensity_host(thz_ctx* c, const float* data, int n, float* img, int64_t P) {
   CHECK_CTX(c);
   if (P == 0) return THZ_OK;
-  if (!data || !img || n <= 0 || n % 4) return set_err(c, THZ_EINVAL, "bad argument");
+  if (!data || !img || n <= 0) return set_err(c, THZ_EINVAL, "bad argument");
   return elementwise_host(c, data, nullptr, img, P, n, nullptr);
 }
 

@@ -23,6 +23,11 @@ struct TracePlan {
   float* d_band = nullptr;      // [n/2+1] or null
   float* d_hq = nullptr;        // [n] band (or ones) / n in last-stage register order (fused kernel)
   bool has_pre = false, has_post = false, has_band = false;
+  // traces whose length is not a power of two go through the chirp-z kernels (thz_bluestein.cu)
+  int blue_m = 0;               // power-of-two transform size (>= 2n - 1), 0 = power-of-two plan
+  float2* d_chirp = nullptr;    // [n]
+  float2* d_bhat = nullptr;     // [blue_m]
+  float* d_hn = nullptr;        // [n]
 };
 
 constexpr int kHostStreams = 3;
@@ -87,5 +92,14 @@ int launch_generate(thz_ctx* c, cudaStream_t s, float* d_cube, int width, int he
 int build_hq(int n, const float* band /*nullable, host*/, std::vector<float>& hq);
 int build_twiddles(int n, std::vector<float2>& tw);
 bool supported_n(int n);
+// thz_bluestein.cu
+bool blue_supported(int n);
+int build_bluestein_tables(int n, const float* band, std::vector<float2>& chirp, std::vector<float2>& bhat,
+                           std::vector<float>& hn, int& m_out);
+int launch_blue_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P);
+int launch_blue_forward(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_win, float2* d_fft, float* d_amp,
+                        float* d_phase, int64_t P);
+int launch_blue_inverse(thz_ctx* c, cudaStream_t s, const float2* d_fft, bool use_band, bool use_post, float* d_out,
+                        float* d_img, int64_t P);
 
 }  // namespace thz

@@ -471,17 +471,26 @@ __global__ void k_time_multiply(const float* __restrict__ in, const float* __res
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t p = warp; p < P; p += nwarps) {
-    const float4* src = reinterpret_cast<const float4*>(in + p * n);
-    float4* dst = out ? reinterpret_cast<float4*>(out + p * n) : nullptr;
     float acc = 0.f;
-    for (int q = lane; q < n / 4; q += 32) {
-      float4 v = __ldcs(src + q);
-      if (mult) {
-        const float4 m = __ldg(reinterpret_cast<const float4*>(mult) + q);
-        v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+    if ((n & 3) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(in + p * n);
+      float4* dst = out ? reinterpret_cast<float4*>(out + p * n) : nullptr;
+      for (int q = lane; q < n / 4; q += 32) {
+        float4 v = __ldcs(src + q);
+        if (mult) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(mult) + q);
+          v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+        }
+        if (dst) __stcs(dst + q, v);
+        acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
       }
-      if (dst) __stcs(dst + q, v);
-      acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+    } else {   // trace length not a multiple of 4: rows are not 16-byte aligned
+      for (int i = lane; i < n; i += 32) {
+        float v = __ldcs(in + p * n + i);
+        if (mult) v *= __ldg(mult + i);
+        if (out) __stcs(out + p * n + i, v);
+        acc = fmaf(v, v, acc);
+      }
     }
     if (img) {
 #pragma unroll
@@ -753,6 +762,11 @@ static int base_args(thz_ctx* c, TraceArgs& a, int64_t P) {
 }
 
 int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P) {
+  if (c->plan.n != 0 && c->plan.blue_m != 0) {
+    if (P == 0) return THZ_OK;
+    if (!d_in || !d_out) return set_err(c, THZ_EINVAL, "null cube pointer");
+    return launch_blue_fused(c, s, d_in, d_out, d_img, P);
+  }
   TraceArgs a;
   int rc = base_args(c, a, P);
   if (rc != THZ_OK) return rc;
@@ -770,6 +784,11 @@ int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_o
 
 int launch_trace_forward(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_win, float2* d_fft, float* d_amp,
                          float* d_phase, int64_t P) {
+  if (c->plan.n != 0 && c->plan.blue_m != 0) {
+    if (P == 0) return THZ_OK;
+    if (!d_in) return set_err(c, THZ_EINVAL, "null cube pointer");
+    return launch_blue_forward(c, s, d_in, d_win, d_fft, d_amp, d_phase, P);
+  }
   TraceArgs a;
   int rc = base_args(c, a, P);
   if (rc != THZ_OK) return rc;
@@ -786,6 +805,11 @@ int launch_trace_forward(thz_ctx* c, cudaStream_t s, const float* d_in, float* d
 
 int launch_trace_inverse(thz_ctx* c, cudaStream_t s, const float2* d_fft, bool use_band, bool use_post, float* d_out,
                          float* d_img, int64_t P) {
+  if (c->plan.n != 0 && c->plan.blue_m != 0) {
+    if (P == 0) return THZ_OK;
+    if (!d_fft || !d_out) return set_err(c, THZ_EINVAL, "null pointer");
+    return launch_blue_inverse(c, s, d_fft, use_band, use_post, d_out, d_img, P);
+  }
   TraceArgs a;
   int rc = base_args(c, a, P);
   if (rc != THZ_OK) return rc;
@@ -816,7 +840,6 @@ int launch_band_apply(thz_ctx* c, cudaStream_t s, float2* d_fft, float* d_amp, i
 
 int launch_time_multiply(thz_ctx* c, cudaStream_t s, const float* d_in, const float* d_mult, int n, float* d_out,
                          int64_t P, float* d_img) {
-  if (n % 4 != 0) return set_err(c, THZ_EINVAL, "n must be a multiple of 4");
   if (P == 0) return THZ_OK;
   int64_t blocks = (P * 32 + 255) / 256;
   const int64_t cap = (int64_t)c->sm_count * 16;
