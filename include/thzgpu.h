@@ -109,7 +109,8 @@ int thz_band_pass_multiplier(const float* freq, int f, double low, double high, 
  *                src/math_tools.rs:102-198, 356-371)
  *   band[n/2+1]: frequency band-pass taper (src/filters/band_pass_fd.rs:155-212)
  *   m_post[n] : time gate after the inverse FFT (src/filters/band_pass_td_after_fft.rs)
- * n must be a power of two in [64, 8192]. */
+ * n: a power of two in [64, 8192] (radix-16 shared-memory kernels) or any length in [2, 4096] (chirp-z
+ * kernels on the same core, thz_bluestein.cu) -- real scans and tilt-extended axes are not powers of two. */
 int thz_plan_trace(thz_ctx* ctx, int n, const float* m_pre, const float* band, const float* m_post);
 
 /* ------------------------------------------------------- trace pass, device pointers --- */
@@ -159,6 +160,15 @@ int thz_roi_average_dev(thz_ctx* ctx, const float* d_data, int dim0, int dim1, i
 int thz_optical_properties(const float* sample_amp, const float* sample_phase, const float* ref_amp,
                            const float* ref_phase, const float* freqs, int f, float thickness, float* n_out,
                            float* alpha_out, float* kappa_out);
+
+/* `TiltCompensation` with a non-zero tilt (src/filters/tilt_compensation.rs:97-226).  thz_tilt_plan is the
+ * host part (extension steps, extended time axis, per-pixel insert index); thz_tilt_shift_host applies it:
+ * out[p][k] = in[p][0] for k < insert[p], in[p][k - insert] * taper[k - insert] up to the end of the trace,
+ * 0 after; out is [P][n_ext], n_ext = n + 2 * num_steps. */
+int thz_tilt_plan(const float* time, int n, int width, int height, float dx, float dy, double tilt_x, double tilt_y,
+                  int* num_steps, float* time_ext, int* insert);
+int thz_tilt_shift_host(thz_ctx* ctx, const float* in, const float* taper, const int* insert, int n, int n_ext,
+                        float* out, int64_t P);
 
 /* Pixel means that `ifft` computes first (src/math_tools.rs:421-440): mean over all P traces
  * of fft (2F floats), amplitudes (F), phases (F).  Host outputs, any may be NULL. */

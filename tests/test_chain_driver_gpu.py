@@ -178,3 +178,31 @@ def test_chain_driver_non_power_of_two(ctx, psf_npz_path):
                                      img=slots[7].img, dx=1.0, dy=1.0, width=w, height=h)
     ref = orc.Deconvolution(n_filters=4, n_iterations=8).filter(sin, opsf)
     assert rel_err(out, ref.data) <= TOL_MAP and rel_err(img, ref.img) <= TOL_MAP
+
+
+def test_non_zero_tilt_extends_the_axis(ctx):
+    """TiltCompensation at 10 / 4 degrees: per-pixel shift, axis extended by 2 * num_steps (the reference's
+    own tilt tests, tilt_compensation.rs:302-389, check extension length and impulse position); the rest of
+    the chain then runs on a non power-of-two length."""
+    n, w, h = 256, 6, 5
+    cube = synthetic_cube(w, h, n, seed=17)
+    cube[2, 3, :] = 0.0
+    cube[2, 3, 100] = 1.0                       # impulse
+    t = time_axis(n)
+    ch = pkg().Chain(ctx)
+    ch.set_param("Tilt Compensation", "tilt_x", 10.0)
+    ch.set_param("Tilt Compensation", "tilt_y", 4.0)
+    ch.open(t, cube, 0.5, 0.5)
+    ch.run(1)
+    p = orc.ChainParams()
+    p.tilt.tilt_x, p.tilt.tilt_y = 10.0, 4.0
+    ref = orc.run_default_chain(slot0(cube, t), p)
+    n_ext = ref[2].data.shape[2]
+    assert n_ext > n
+    ch.shape = (w, h, n_ext)
+    s2 = ch.slot(2)
+    assert s2["data"].shape == ref[2].data.shape
+    assert rel_err(s2["data"], ref[2].data) <= 1e-6
+    assert int(np.argmax(s2["data"][2, 3])) == int(np.argmax(ref[2].data[2, 3]))
+    assert rel_err(ch.slot(7)["data"], ref[7].data) <= TOL_TRACE
+    assert rel_err(ch.slot(8)["img"], ref[7].img) <= TOL_TRACE

@@ -152,6 +152,8 @@ def load_library():
         "thz_bias_subtract_dev": (i32, [vp, fp, i32, fp, fp, i64]),
         "thz_roi_average_dev": (i32, [vp, fp, i32, i32, i32, fp, fp, i32, i32, fp]),
         "thz_optical_properties": (i32, [fp, fp, fp, fp, fp, i32, f32, fp, fp, fp]),
+        "thz_tilt_plan": (i32, [fp, i32, i32, i32, f32, f32, C.c_double, C.c_double, C.POINTER(i32), fp, fp]),
+        "thz_tilt_shift_host": (i32, [vp, fp, fp, fp, i32, i32, fp, i64]),
         "thz_time_multiply_dev": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_time_multiply_host": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_band_apply_host": (i32, [vp, fp, fp, i64]),

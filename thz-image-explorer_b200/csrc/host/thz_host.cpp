@@ -173,8 +173,23 @@ class TiltCompensation : public Filter {
     ScannedImageFilterData out = input;
     if (!(input.dx && input.dy) || input.time.empty()) return out;   // :111
     if (tilt_x != 0.0 || tilt_y != 0.0) {
-      // non-zero tilt extends the time axis to a non power-of-two length ("next" row)
-      return out;
+      // per-pixel integer shift inside an axis extended by 2 * num_steps samples (:117-199)
+      const int n = (int)input.n(), W = (int)input.width, H = (int)input.height;
+      int num_steps = 0;
+      thz_tilt_plan(input.time.data(), n, W, H, *input.dx, *input.dy, tilt_x, tilt_y, &num_steps, nullptr, nullptr);
+      const int n_ext = n + 2 * num_steps;
+      std::vector<float> time_ext((size_t)n_ext), taper((size_t)n);
+      std::vector<int> insert(input.pixels());
+      thz_tilt_plan(input.time.data(), n, W, H, *input.dx, *input.dy, tilt_x, tilt_y, &num_steps, time_ext.data(),
+                    insert.data());
+      thz_adapted_blackman(input.time.data(), n, 0.0f, 7.0f, taper.data());
+      out.data.assign(input.pixels() * (size_t)n_ext, 0.f);
+      thz_tilt_shift_host(env.ctx, input.data.data(), taper.data(), insert.data(), n, n_ext, out.data.data(),
+                          (int64_t)input.pixels());
+      out.time = time_ext;
+      out.frequency = frequency_of(out.time);
+      out.has_plan = true;
+      return out;   // the driver zero-sizes the spectral cubes when the axis length changed (:1193-1227)
     }
     // 0 deg: no shift, no extension; every trace is tapered by the adapted Blackman (0, 7 ps) (:188)
     std::vector<float> taper(input.n());

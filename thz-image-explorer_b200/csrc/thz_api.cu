@@ -652,4 +652,25 @@ int thz_roi_average_dev(thz_ctx* c, const float* d_data, int dim0, int dim1, int
   return THZ_OK;
 }
 
+int thz_tilt_shift_host(thz_ctx* c, const float* in, const float* taper, const int* insert, int n, int n_ext,
+                        float* out, int64_t P) {
+  CHECK_CTX(c);
+  if (P == 0) return THZ_OK;
+  if (!in || !taper || !insert || !out || n < 1 || n_ext < n) return set_err(c, THZ_EINVAL, "bad argument");
+  void *pi = nullptr, *po = nullptr, *px = nullptr, *pt = nullptr;
+  int rc = ws_get(c, WS_TILT_IN, (size_t)P * n * sizeof(float), &pi);
+  if (rc == THZ_OK) rc = ws_get(c, WS_TILT_OUT, (size_t)P * n_ext * sizeof(float), &po);
+  if (rc == THZ_OK) rc = ws_get(c, WS_TILT_IDX, (size_t)P * sizeof(int), &px);
+  if (rc == THZ_OK) rc = ws_get(c, WS_TILT_TAPER, (size_t)n * sizeof(float), &pt);
+  if (rc != THZ_OK) return rc;
+  THZ_CUDA(c, cudaMemcpyAsync(pi, in, (size_t)P * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  THZ_CUDA(c, cudaMemcpyAsync(px, insert, (size_t)P * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  THZ_CUDA(c, cudaMemcpyAsync(pt, taper, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  rc = launch_tilt_shift(c, c->stream, (const float*)pi, (const float*)pt, (const int*)px, n, n_ext, P, (float*)po);
+  if (rc != THZ_OK) return rc;
+  THZ_CUDA(c, cudaMemcpyAsync(out, po, (size_t)P * n_ext * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  return THZ_OK;
+}
+
 }  // extern "C"

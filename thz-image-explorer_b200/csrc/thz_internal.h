@@ -69,7 +69,7 @@ int get_tables(thz_ctx* c, int n, const FftTables** out);
 int ensure_scratch(thz_ctx* c, size_t bytes);
 // grow-only workspace: returns a device buffer of at least `bytes` for `slot`
 int ws_get(thz_ctx* c, int slot, size_t bytes, void** out);
-enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT };
+enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER };
 
 // thz_trace.cu
 int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P);
@@ -84,6 +84,8 @@ int launch_scale_blocks(thz_ctx* c, cudaStream_t s, const float* d_in, int width
 int launch_bias_subtract(thz_ctx* c, cudaStream_t s, const float* d_in, int n, float* d_out, int64_t P, float* d_img);
 int launch_roi_average(thz_ctx* c, cudaStream_t s, const float* d_data, const int64_t* d_pix, int npix, int zlen,
                        float* d_out);
+int launch_tilt_shift(thz_ctx* c, cudaStream_t s, const float* d_in, const float* d_taper, const int* d_insert, int n,
+                      int n_ext, int64_t P, float* d_out);
 int launch_band_apply(thz_ctx* c, cudaStream_t s, float2* d_fft, float* d_amp, int64_t P);
 int launch_column_sums(thz_ctx* c, cudaStream_t s, const float* d_x, int64_t rows, int cols, float* d_partials,
                        int nblocks);

@@ -553,6 +553,29 @@ __global__ void k_roi_average(const float* __restrict__ data, const int64_t* __r
   out[z] = npix > 0 ? acc / (float)npix : acc;
 }
 
+// TiltCompensation with a non-zero tilt (src/filters/tilt_compensation.rs:158-199): every trace is tapered,
+// shifted by its pixel's integer offset inside a time axis extended by 2 * num_steps samples; the head is
+// filled with the trace's first RAW value, the tail with zeros.  insert[p] is computed on the host with the
+// reference's mixed f32 / f64 arithmetic.
+__global__ void k_tilt_shift(const float* __restrict__ in, const float* __restrict__ taper, const int* __restrict__ insert,
+                             int n, int n_ext, int64_t P, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < P; p += nwarps) {
+    const int ins = insert[p];
+    const float first = __ldg(in + p * n);
+    const int end = min(ins + n, n_ext);
+    for (int k = lane; k < n_ext; k += 32) {
+      float v;
+      if (k < ins) v = first;
+      else if (k < end) v = __ldcs(in + p * n + (k - ins)) * __ldg(taper + (k - ins));
+      else v = 0.f;
+      __stcs(out + p * n_ext + k, v);
+    }
+  }
+}
+
 // partial column sums of x[rows][cols]: block b sums rows [b*rpb, (b+1)*rpb) sequentially
 __global__ void k_column_sums(const float* __restrict__ x, int64_t rows, int cols, float* __restrict__ partials) {
   const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
@@ -885,6 +908,19 @@ int launch_roi_average(thz_ctx* c, cudaStream_t s, const float* d_data, const in
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(c, e, "k_roi_average launch");
+  return THZ_OK;
+}
+
+int launch_tilt_shift(thz_ctx* c, cudaStream_t s, const float* d_in, const float* d_taper, const int* d_insert, int n,
+                      int n_ext, int64_t P, float* d_out) {
+  if (P == 0) return THZ_OK;
+  int64_t blocks = (P * 32 + 255) / 256;
+  const int64_t cap = (int64_t)c->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  k_tilt_shift<<<(unsigned)blocks, 256, 0, s>>>(d_in, d_taper, d_insert, n, n_ext, P, d_out);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_tilt_shift launch");
   return THZ_OK;
 }
 

@@ -172,4 +172,48 @@ int thz_optical_properties(const float* sample_amp, const float* sample_phase, c
   return THZ_OK;
 }
 
+/* Host part of `TiltCompensation::filter` (src/filters/tilt_compensation.rs:104-168): number of extension
+ * steps, extended time axis (front linspace | original | back linspace) and the per-pixel insert index
+ * max(num_steps + floor(delta / dt), 0), in the reference's mixed f32 / f64 arithmetic.  time_ext must hold
+ * n + 2 * (*num_steps) floats -- call once with time_ext = insert = NULL to get num_steps. */
+int thz_tilt_plan(const float* time, int n, int width, int height, float dx, float dy, double tilt_x, double tilt_y,
+                  int* num_steps_out, float* time_ext, int* insert) {
+  if (!time || n < 1 || width < 1 || height < 1 || !num_steps_out) return THZ_EINVAL;
+  const float time_shift_x = (float)tilt_x / 180.0f * kPi;
+  const float time_shift_y = (float)tilt_y / 180.0f * kPi;
+  const float center_x = (float)width / 2.0f * dx, center_y = (float)height / 2.0f * dy;
+  const double c = 0.299792458;
+  const float dt = 0.05f;
+  const float max_offset_x = (float)((double)center_x * (double)fabsf(time_shift_x) / c);
+  const float max_offset_y = (float)((double)center_y * (double)fabsf(time_shift_y) / c);
+  float extension = (max_offset_x + max_offset_y) / dt;
+  extension = floorf(extension) * dt;
+  const int num_steps = (int)roundf(extension / dt);
+  *num_steps_out = num_steps;
+  if (time_ext) {
+    const float first = time[0], last = time[n - 1];
+    // ndarray `Array1::linspace(a, b, k)`: a + i * (b - a) / (k - 1)
+    auto linspace = [](float a, float b, int k, float* out) {
+      if (k == 1) out[0] = a;
+      const float step = (k > 1) ? (b - a) / (float)(k - 1) : 0.f;
+      for (int i = 0; i < k; ++i) out[i] = a + step * (float)i;
+    };
+    linspace(first - extension, first - dt, num_steps, time_ext);
+    for (int i = 0; i < n; ++i) time_ext[num_steps + i] = time[i];
+    linspace(last + dt, last + extension, num_steps, time_ext + num_steps + n);
+  }
+  if (insert) {
+    for (int i = 0; i < width; ++i) {
+      const float x_off = (float)((double)(((float)i - (float)width / 2.0f) * dx) * (double)time_shift_x / c);
+      for (int j = 0; j < height; ++j) {
+        const float y_off = (float)((double)(((float)j - (float)height / 2.0f) * dy) * (double)time_shift_y / c);
+        const float delta = x_off + y_off;
+        const long steps = (long)floorf(delta / dt);
+        insert[(size_t)i * height + j] = (int)std::max((long)num_steps + steps, 0L);
+      }
+    }
+  }
+  return THZ_OK;
+}
+
 }  // extern "C"
