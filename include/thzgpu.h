@@ -170,6 +170,14 @@ int thz_tilt_plan(const float* time, int n, int width, int height, float dx, flo
 int thz_tilt_shift_host(thz_ctx* ctx, const float* in, const float* taper, const int* insert, int n, int n_ext,
                         float* out, int64_t P);
 
+/* Reference pulse, `ConfigCommand::OpenRef` (src/data_thread.rs:372-588): integer-shift alignment / zero fill of
+ * a (ref_time, ref_signal) pulse of m samples to the scan's axis of n samples, FFT window on the reference
+ * file's own axis, then r2c, |s| and unwrap(arg s) (the forward kernel on one trace).  signal_out[n],
+ * amp_out / phase_out [n/2+1] (nullable).  Replaces the context's trace plan. */
+int thz_reference_pulse(thz_ctx* ctx, const float* scan_time, int n, const float* ref_time, const float* ref_signal,
+                        int m, int window_type, float window_lo, float window_hi, float* signal_out, float* amp_out,
+                        float* phase_out);
+
 /* Pixel means that `ifft` computes first (src/math_tools.rs:421-440): mean over all P traces
  * of fft (2F floats), amplitudes (F), phases (F).  Host outputs, any may be NULL. */
 int thz_spectral_means(thz_ctx* ctx, const float* d_fft, const float* d_amp, const float* d_phase,

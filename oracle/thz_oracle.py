@@ -1132,3 +1132,44 @@ def average_polygon_roi(data, polygon, scaling=1):
     if count > 0:
         result = result / F32(count)
     return result.astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# reference pulse, ConfigCommand::OpenRef (src/data_thread.rs:372-588) -- "next" row
+# --------------------------------------------------------------------------------------
+def reference_pulse(scan_time, ref_time, ref_signal, config: ConfigContainer = None):
+    """Aligns / resizes a reference pulse to the scan's time axis (integer shift, zero fill,
+    data_thread.rs:405-481), windows it on the REFERENCE file's time axis (:489-511, the zip stops at the
+    shorter of the two), then r2c + |s| + unwrap(arg s) with the scan's plan (:513-533).
+    Returns (signal[n], amplitudes[F], phases[F])."""
+    config = config or ConfigContainer()
+    st = np.asarray(scan_time, F32)
+    rt = np.asarray(ref_time, F32)
+    ref = np.asarray(ref_signal, F32).copy()
+    n = st.shape[0]
+    if n != ref.shape[0] or (rt.shape[0] and abs(float(st[0] - rt[0])) > 1e-9):
+        if n > 1 and rt.shape[0] > 1:
+            new = np.zeros(n, F32)
+            ref_dt = rt[1] - rt[0]
+            time_offset = st[0] - rt[0]
+            index_offset = int(np.round(time_offset / ref_dt))   # f32 division, round half away from zero
+            if abs(float(time_offset / ref_dt)) % 1 == 0.5:
+                index_offset = int(np.sign(float(time_offset / ref_dt)) * np.ceil(abs(float(time_offset / ref_dt))))
+            src_start = index_offset if index_offset > 0 else 0
+            dst_start = -index_offset if index_offset < 0 else 0
+            copy_len = min(max(ref.shape[0] - src_start, 0), max(n - dst_start, 0))
+            if copy_len > 0:
+                new[dst_start:dst_start + copy_len] = ref[src_start:src_start + copy_len]
+            ref = new
+        else:
+            new = np.zeros(n, F32)
+            k = min(n, ref.shape[0])
+            new[:k] = ref[:k]
+            ref = new
+    mult = fft_window_multiplier(rt, config.fft_window_type, config.fft_window)
+    k = min(n, rt.shape[0])
+    ref[:k] = ref[:k] * mult[:k]
+    spec = rfft_unnormalised(ref).astype(np.complex64)
+    amp = np.abs(spec).astype(F32)
+    ph = numpy_unwrap(np.arctan2(spec.imag, spec.real).astype(F32), F32(2.0) * PI32).astype(F32)
+    return ref, amp, ph

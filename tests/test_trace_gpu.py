@@ -313,3 +313,20 @@ def test_arbitrary_length_traces(ctx, n):
     cube[1, 2] = 0.0
     out, img = ctx.trace_fused(cube)
     assert not out[1, 2].any() and img[1, 2] == 0.0
+
+
+@pytest.mark.parametrize("n,m,shift", [(1024, 1024, 0), (1024, 900, 37), (1024, 1200, -50), (1000, 1024, 12)])
+def test_reference_pulse_path(ctx, n, m, shift):
+    """ConfigCommand::OpenRef (src/data_thread.rs:372-588): alignment / resize + window + forward transform of
+    one reference pulse (BASELINE config 2 normalises sample spectra by it)."""
+    dt = F32(0.05)
+    st = time_axis(n)
+    rt = (F32(1000.0) + dt * F32(shift) + dt * np.arange(m, dtype=F32)).astype(F32)
+    tt = np.arange(m) * 0.05 - 12.0
+    ref = (np.exp(-(tt / 0.3) ** 2) * np.cos(2 * np.pi * tt) + 0.001 * np.random.default_rng(1).standard_normal(m)).astype(F32)
+    sig, amp, ph = ctx.reference_pulse(st, rt, ref)
+    osig, oamp, oph = orc.reference_pulse(st, rt, ref)
+    assert rel_err(sig, osig) <= 1e-6
+    assert rel_err(amp, oamp) <= TOL_TRACE
+    spec = np.fft.rfft(osig.astype(np.float64)).astype(np.complex64)
+    check_unwrapped_phase(ph[None, :], oph[None, :], spec[None, :], max(TOL_TRACE * float(np.abs(oph).max()), 2e-3))

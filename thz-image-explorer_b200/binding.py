@@ -154,6 +154,7 @@ def load_library():
         "thz_optical_properties": (i32, [fp, fp, fp, fp, fp, i32, f32, fp, fp, fp]),
         "thz_tilt_plan": (i32, [fp, i32, i32, i32, f32, f32, C.c_double, C.c_double, C.POINTER(i32), fp, fp]),
         "thz_tilt_shift_host": (i32, [vp, fp, fp, fp, i32, i32, fp, i64]),
+        "thz_reference_pulse": (i32, [vp, fp, i32, fp, fp, i32, i32, f32, f32, fp, fp, fp]),
         "thz_time_multiply_dev": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_time_multiply_host": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_band_apply_host": (i32, [vp, fp, fp, i64]),
@@ -492,6 +493,20 @@ class Context:
         self._check(lib.thz_roi_average_dev(self.handle, d.ptr, d0, d1, z, px.ctypes.data, py.ctypes.data, px.size,
                                             int(scaling), out.ctypes.data))
         return out
+
+    def reference_pulse(self, scan_time, ref_time, ref_signal, window_type=0, fft_window=(1.0, 7.0)):
+        st = np.ascontiguousarray(scan_time, np.float32)
+        rt = np.ascontiguousarray(ref_time, np.float32)
+        rs = np.ascontiguousarray(ref_signal, np.float32)
+        n = st.size
+        sig = np.empty(n, np.float32)
+        amp = np.empty(n // 2 + 1, np.float32)
+        ph = np.empty(n // 2 + 1, np.float32)
+        self._check(lib.thz_reference_pulse(self.handle, st.ctypes.data, n, rt.ctypes.data, rs.ctypes.data, rt.size,
+                                            int(window_type), float(fft_window[0]), float(fft_window[1]),
+                                            sig.ctypes.data, amp.ctypes.data, ph.ctypes.data))
+        self.n = n
+        return sig, amp, ph
 
     def deconv_stage_ms(self):
         ms = np.zeros(4, np.float32)

@@ -1,6 +1,7 @@
 // thz_api.cu -- the C ABI (include/thzgpu.h): context, plans, memory, host-pointer pipelines.
 #include "thz_internal.h"
 
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
@@ -671,6 +672,42 @@ int thz_tilt_shift_host(thz_ctx* c, const float* in, const float* taper, const i
   THZ_CUDA(c, cudaMemcpyAsync(out, po, (size_t)P * n_ext * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   THZ_CUDA(c, cudaStreamSynchronize(c->stream));
   return THZ_OK;
+}
+
+int thz_reference_pulse(thz_ctx* c, const float* scan_time, int n, const float* ref_time, const float* ref_signal,
+                        int m, int window_type, float window_lo, float window_hi, float* signal_out, float* amp_out,
+                        float* phase_out) {
+  CHECK_CTX(c);
+  if (!scan_time || !ref_time || !ref_signal || !signal_out || n < 2 || m < 1)
+    return set_err(c, THZ_EINVAL, "bad argument");
+  std::vector<float> ref(ref_signal, ref_signal + m);
+  // resize / align (src/data_thread.rs:405-481)
+  if (n != m || fabsf(scan_time[0] - ref_time[0]) > 1e-9f) {
+    std::vector<float> nr((size_t)n, 0.f);
+    if (n > 1 && m > 1) {
+      const float ref_dt = ref_time[1] - ref_time[0];
+      const float time_offset = scan_time[0] - ref_time[0];
+      const long index_offset = (long)roundf(time_offset / ref_dt);
+      const long src_start = index_offset > 0 ? index_offset : 0;
+      const long dst_start = index_offset < 0 ? -index_offset : 0;
+      const long copy_len = std::min(std::max((long)m - src_start, 0L), std::max((long)n - dst_start, 0L));
+      for (long i = 0; i < copy_len; ++i) nr[(size_t)(dst_start + i)] = ref[(size_t)(src_start + i)];
+    } else {
+      for (int i = 0; i < std::min(n, m); ++i) nr[i] = ref[i];
+    }
+    ref.swap(nr);
+  }
+  // window on the reference file's own time axis; the zip stops at the shorter sequence (:489-511)
+  std::vector<float> mult((size_t)m);
+  int rc = thz_window_multiplier(window_type, ref_time, m, window_lo, window_hi, mult.data());
+  if (rc != THZ_OK) return set_err(c, rc, "bad window type");
+  for (int i = 0; i < std::min(n, m); ++i) ref[i] *= mult[i];
+  memcpy(signal_out, ref.data(), (size_t)n * sizeof(float));
+  if (!amp_out && !phase_out) return THZ_OK;
+  // r2c + |s| + unwrap(arg s) with the scan's plan: the forward kernel on a 1 x 1 cube, no further window
+  rc = thz_plan_trace(c, n, nullptr, nullptr, nullptr);
+  if (rc != THZ_OK) return rc;
+  return thz_trace_forward_host(c, ref.data(), nullptr, nullptr, amp_out, phase_out, 1);
 }
 
 }  // extern "C"
