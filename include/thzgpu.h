@@ -178,6 +178,16 @@ int thz_reference_pulse(thz_ctx* ctx, const float* scan_time, int n, const float
                         int m, int window_type, float window_lo, float window_hi, float* signal_out, float* amp_out,
                         float* phase_out);
 
+/* Voxel opacities of the 3-D view, `instance_from_data` up to the effective threshold
+ * (src/gui/threed_plot.rs:165-219; runs on the data thread on a clone of the cube after every chain update):
+ * per trace (v^2)^contrast, Gaussian(sigma, radius) weighted sum with zero boundary, traces below
+ * opacity_threshold zeroed, the others min/max normalised; *effective_threshold (nullable) = the
+ * max_instances-th largest opacity when the cube has more voxels than that, else 0.  The instance list
+ * itself (positions, colours) is GUI data and stays on the reference side. */
+int thz_voxel_opacity_dev(thz_ctx* ctx, const float* d_cube, int n, int64_t P, float opacity_threshold,
+                          float contrast, float sigma, int radius, int64_t max_instances, float* d_opacity,
+                          float* effective_threshold);
+
 /* Pixel means that `ifft` computes first (src/math_tools.rs:421-440): mean over all P traces
  * of fft (2F floats), amplitudes (F), phases (F).  Host outputs, any may be NULL. */
 int thz_spectral_means(thz_ctx* ctx, const float* d_fft, const float* d_amp, const float* d_phase,

@@ -1173,3 +1173,45 @@ def reference_pulse(scan_time, ref_time, ref_signal, config: ConfigContainer = N
     amp = np.abs(spec).astype(F32)
     ph = numpy_unwrap(np.arctan2(spec.imag, spec.real).astype(F32), F32(2.0) * PI32).astype(F32)
     return ref, amp, ph
+
+
+# --------------------------------------------------------------------------------------
+# voxel envelope of the 3-D view (src/gui/threed_plot.rs:81-236) -- "next" row
+# --------------------------------------------------------------------------------------
+def gaussian_kernel1d(sigma, radius):
+    sigma = F32(sigma)
+    x = np.arange(2 * radius + 1, dtype=F32) - F32(radius)
+    v = _exp32(-x * x / (F32(2.0) * sigma * sigma))
+    s = F32(0.0)
+    for t in v:
+        s = F32(s + t)
+    return (v / s).astype(F32)
+
+
+def voxel_opacity(dataset, opacity_threshold=0.1, contrast=2.0, sigma=3.0, radius=9, max_instances=2_000_000):
+    """`instance_from_data` up to the effective threshold (threed_plot.rs:165-219): per trace v^2,
+    Gaussian-weighted sum of (v^2)^contrast with zero boundary (taps accumulated in order), traces whose
+    maximum is below opacity_threshold are zeroed, the others min/max normalised; the effective threshold is
+    the max_instances-th largest opacity (0 when the cube has fewer voxels).  Returns (opacity, threshold)."""
+    d = np.asarray(dataset, F32)
+    kernel = gaussian_kernel1d(sigma, radius)
+    sq = (d * d).astype(F32)
+    pw = np.power(sq.astype(np.float64), float(F32(contrast))).astype(F32)
+    n = d.shape[-1]
+    env = np.zeros_like(d)
+    for k, coeff in enumerate(kernel):
+        sh = k - radius
+        lo, hi = max(0, -sh), min(n, n - sh)
+        if hi > lo:
+            env[..., lo:hi] = env[..., lo:hi] + pw[..., lo + sh:hi + sh] * coeff
+    mx = env.max(axis=-1, keepdims=True)
+    mn = env.min(axis=-1, keepdims=True)
+    rng = mx - mn
+    ok = (mx >= F32(opacity_threshold)) & (np.abs(rng) > F32(1e-6))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = np.where(ok, (env - mn) / rng, F32(0.0)).astype(F32)
+    flat = out.reshape(-1)
+    thr = F32(0.0)
+    if flat.size > max_instances:
+        thr = np.partition(flat, flat.size - max_instances)[flat.size - max_instances]
+    return out, F32(thr)

@@ -330,3 +330,19 @@ def test_reference_pulse_path(ctx, n, m, shift):
     assert rel_err(amp, oamp) <= TOL_TRACE
     spec = np.fft.rfft(osig.astype(np.float64)).astype(np.complex64)
     check_unwrapped_phase(ph[None, :], oph[None, :], spec[None, :], max(TOL_TRACE * float(np.abs(oph).max()), 2e-3))
+
+
+def test_voxel_opacity_and_threshold(ctx):
+    """instance_from_data up to the effective threshold (src/gui/threed_plot.rs:165-219)."""
+    cube = synthetic_cube(12, 10, 512, seed=23, noise=0.02)
+    cube[3, 4] *= F32(0.01)                       # a faint trace: below the opacity threshold -> zeroed
+    ref, rthr = orc.voxel_opacity(cube, 0.1, 2.0, 3.0, 9, max_instances=5000)
+    got, thr = ctx.voxel_opacity(cube, 0.1, 2.0, 3.0, 9, max_instances=5000)
+    assert rel_err(got, ref) <= 2e-5
+    assert not got[3, 4].any()
+    # the threshold is an exact order statistic of the GPU's own opacities
+    flat = np.sort(got.reshape(-1))[::-1]
+    assert thr == flat[4999]
+    assert abs(thr - float(rthr)) <= 2e-5
+    _, thr0 = ctx.voxel_opacity(cube, 0.1, 2.0, 3.0, 9, max_instances=10 ** 9)
+    assert thr0 == 0.0

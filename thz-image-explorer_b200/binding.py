@@ -155,6 +155,7 @@ def load_library():
         "thz_tilt_plan": (i32, [fp, i32, i32, i32, f32, f32, C.c_double, C.c_double, C.POINTER(i32), fp, fp]),
         "thz_tilt_shift_host": (i32, [vp, fp, fp, fp, i32, i32, fp, i64]),
         "thz_reference_pulse": (i32, [vp, fp, i32, fp, fp, i32, i32, f32, f32, fp, fp, fp]),
+        "thz_voxel_opacity_dev": (i32, [vp, fp, i32, i64, f32, f32, f32, i32, i64, fp, fp]),
         "thz_time_multiply_dev": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_time_multiply_host": (i32, [vp, fp, fp, i32, fp, i64]),
         "thz_band_apply_host": (i32, [vp, fp, fp, i64]),
@@ -507,6 +508,18 @@ class Context:
                                             sig.ctypes.data, amp.ctypes.data, ph.ctypes.data))
         self.n = n
         return sig, amp, ph
+
+    def voxel_opacity(self, cube, opacity_threshold=0.1, contrast=2.0, sigma=3.0, radius=9, max_instances=2_000_000):
+        cube = _f32c(cube)
+        n = cube.shape[-1]
+        P = cube.size // n
+        d = self.to_device(cube)
+        d_o = self.alloc(cube.nbytes)
+        thr = C.c_float(0.0)
+        self._check(lib.thz_voxel_opacity_dev(self.handle, d.ptr, n, P, float(opacity_threshold), float(contrast),
+                                              float(sigma), int(radius), int(max_instances), d_o.ptr,
+                                              C.cast(C.byref(thr), C.c_void_p)))
+        return d_o.download(cube.shape), float(thr.value)
 
     def deconv_stage_ms(self):
         ms = np.zeros(4, np.float32)

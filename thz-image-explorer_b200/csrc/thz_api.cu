@@ -710,4 +710,58 @@ int thz_reference_pulse(thz_ctx* c, const float* scan_time, int n, const float* 
   return thz_trace_forward_host(c, ref.data(), nullptr, nullptr, amp_out, phase_out, 1);
 }
 
+int thz_voxel_opacity_dev(thz_ctx* c, const float* d_cube, int n, int64_t P, float opacity_threshold, float contrast,
+                          float sigma, int radius, int64_t max_instances, float* d_opacity, float* effective_threshold) {
+  CHECK_CTX(c);
+  if (!d_cube || !d_opacity || n < 1 || radius < 0 || radius > 1024) return set_err(c, THZ_EINVAL, "bad argument");
+  // gaussian_kernel1d (src/gui/threed_plot.rs:82-101), f32
+  const int size = 2 * radius + 1;
+  std::vector<float> kernel((size_t)size);
+  const float sigma2 = 2.0f * sigma * sigma;
+  float sum = 0.0f;
+  for (int i = 0; i < size; ++i) {
+    const float x = (float)i - (float)radius;
+    kernel[i] = expf(-x * x / sigma2);
+    sum += kernel[i];
+  }
+  for (float& v : kernel) v /= sum;
+  void *pk = nullptr, *ph = nullptr;
+  int rc = ws_get(c, WS_VOX_KERNEL, (size_t)size * sizeof(float), &pk);
+  if (rc == THZ_OK) rc = ws_get(c, WS_VOX_HIST, 65536 * sizeof(unsigned long long), &ph);
+  if (rc != THZ_OK) return rc;
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  THZ_CUDA(c, cudaMemcpyAsync(pk, kernel.data(), (size_t)size * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  rc = launch_voxel_envelope(c, c->stream, d_cube, n, P, (const float*)pk, radius, contrast, opacity_threshold, d_opacity);
+  if (rc != THZ_OK) return rc;
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (!effective_threshold) return THZ_OK;
+  // effective threshold = max_instances-th largest opacity when there are more voxels than that (:206-214);
+  // opacities are in [0, 1]: their bit patterns order like unsigned integers -> two-pass radix select
+  const int64_t total = P * n;
+  *effective_threshold = 0.0f;
+  if (total <= max_instances || max_instances < 1) return THZ_OK;
+  std::vector<unsigned long long> hist(65536);
+  unsigned prefix = 0;
+  int64_t remaining = max_instances;   // rank from the top, 1-based
+  for (int pass = 0; pass < 2; ++pass) {
+    THZ_CUDA(c, cudaMemsetAsync(ph, 0, 65536 * sizeof(unsigned long long), c->stream));
+    rc = launch_radix_hist(c, c->stream, d_opacity, total, pass, prefix, (unsigned long long*)ph);
+    if (rc != THZ_OK) return rc;
+    THZ_CUDA(c, cudaMemcpyAsync(hist.data(), ph, 65536 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    int b = 65535;
+    for (; b >= 0; --b) {
+      if ((int64_t)hist[b] >= remaining) break;
+      remaining -= (int64_t)hist[b];
+    }
+    if (b < 0) b = 0;
+    if (pass == 0) prefix = (unsigned)b;
+    else {
+      const unsigned bits = (prefix << 16) | (unsigned)b;
+      memcpy(effective_threshold, &bits, sizeof(float));
+    }
+  }
+  return THZ_OK;
+}
+
 }  // extern "C"

@@ -69,7 +69,7 @@ int get_tables(thz_ctx* c, int n, const FftTables** out);
 int ensure_scratch(thz_ctx* c, size_t bytes);
 // grow-only workspace: returns a device buffer of at least `bytes` for `slot`
 int ws_get(thz_ctx* c, int slot, size_t bytes, void** out);
-enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER };
+enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER, WS_VOX_KERNEL, WS_VOX_HIST };
 
 // thz_trace.cu
 int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P);
@@ -86,6 +86,10 @@ int launch_roi_average(thz_ctx* c, cudaStream_t s, const float* d_data, const in
                        float* d_out);
 int launch_tilt_shift(thz_ctx* c, cudaStream_t s, const float* d_in, const float* d_taper, const int* d_insert, int n,
                       int n_ext, int64_t P, float* d_out);
+int launch_voxel_envelope(thz_ctx* c, cudaStream_t s, const float* d_in, int n, int64_t P, const float* d_kernel,
+                          int radius, float contrast, float thr, float* d_out);
+int launch_radix_hist(thz_ctx* c, cudaStream_t s, const float* d_x, int64_t total, int pass, unsigned prefix,
+                      unsigned long long* d_hist);
 int launch_band_apply(thz_ctx* c, cudaStream_t s, float2* d_fft, float* d_amp, int64_t P);
 int launch_column_sums(thz_ctx* c, cudaStream_t s, const float* d_x, int64_t rows, int cols, float* d_partials,
                        int nblocks);

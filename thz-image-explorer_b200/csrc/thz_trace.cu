@@ -576,6 +576,55 @@ __global__ void k_tilt_shift(const float* __restrict__ in, const float* __restri
   }
 }
 
+// Voxel envelope of the 3-D view (src/gui/threed_plot.rs:165-204): one warp per trace; e[i] = sum_k ((x[j]^2)^contrast)
+// * g[k], j = i + k - radius inside the trace (taps accumulated in order); traces whose maximum is below the
+// opacity threshold are zeroed, the others min/max normalised.  The trace lives in shared memory.
+__global__ void k_voxel_envelope(const float* __restrict__ in, int n, int64_t P, const float* __restrict__ kernel,
+                                 int radius, float contrast, float opacity_threshold, float* __restrict__ out) {
+  extern __shared__ float vsm[];   // per warp: n powered samples + n envelope values
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* pw = vsm + (size_t)wib * 2 * n;
+  float* ev = pw + n;
+  for (int64_t p = (int64_t)blockIdx.x * wpb + wib; p < P; p += (int64_t)gridDim.x * wpb) {
+    for (int i = lane; i < n; i += 32) {
+      const float v = __ldcs(in + p * n + i);
+      pw[i] = powf(v * v, contrast);
+    }
+    __syncwarp();
+    float mx = -INFINITY, mn = INFINITY;
+    for (int i = lane; i < n; i += 32) {
+      float acc = 0.f;
+      for (int k = 0; k <= 2 * radius; ++k) {
+        const int j = i + k - radius;
+        if (j >= 0 && j < n) acc += pw[j] * __ldg(kernel + k);
+      }
+      ev[i] = acc;
+      mx = fmaxf(mx, acc);
+      mn = fminf(mn, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    const float rng = mx - mn;
+    const bool ok = (mx >= opacity_threshold) && (fabsf(rng) > 1e-6f);
+    for (int i = lane; i < n; i += 32) __stcs(out + p * n + i, ok ? (ev[i] - mn) / rng : 0.f);
+    __syncwarp();
+  }
+}
+
+// histogram of the top 16 bits (pass 0) or, among the values whose top bits equal `prefix`, of the low 16 bits
+// (pass 1) of non-negative floats: two passes give the exact k-th largest value (radix select)
+__global__ void k_radix_hist(const float* __restrict__ x, int64_t total, int pass, unsigned prefix,
+                             unsigned long long* __restrict__ hist) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned b = __float_as_uint(x[i]);
+    if (pass == 0) atomicAdd(hist + (b >> 16), 1ull);
+    else if ((b >> 16) == prefix) atomicAdd(hist + (b & 0xffffu), 1ull);
+  }
+}
+
 // partial column sums of x[rows][cols]: block b sums rows [b*rpb, (b+1)*rpb) sequentially
 __global__ void k_column_sums(const float* __restrict__ x, int64_t rows, int cols, float* __restrict__ partials) {
   const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
@@ -921,6 +970,40 @@ int launch_tilt_shift(thz_ctx* c, cudaStream_t s, const float* d_in, const float
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(c, e, "k_tilt_shift launch");
+  return THZ_OK;
+}
+
+int launch_voxel_envelope(thz_ctx* c, cudaStream_t s, const float* d_in, int n, int64_t P, const float* d_kernel,
+                          int radius, float contrast, float thr, float* d_out) {
+  if (P == 0) return THZ_OK;
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * 2 * n * sizeof(float);
+  static size_t have = 0;
+  if (smem > have) {
+    cudaError_t e = cudaFuncSetAttribute(k_voxel_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(voxel)");
+    have = smem;
+  }
+  int64_t blocks = (P + wpb - 1) / wpb;
+  const int64_t cap = (int64_t)c->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  k_voxel_envelope<<<(unsigned)blocks, wpb * 32, smem, s>>>(d_in, n, P, d_kernel, radius, contrast, thr, d_out);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_voxel_envelope launch");
+  return THZ_OK;
+}
+
+int launch_radix_hist(thz_ctx* c, cudaStream_t s, const float* d_x, int64_t total, int pass, unsigned prefix,
+                      unsigned long long* d_hist) {
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)c->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_radix_hist<<<(unsigned)blocks, 256, 0, s>>>(d_x, total, pass, prefix, d_hist);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_radix_hist launch");
   return THZ_OK;
 }
 
