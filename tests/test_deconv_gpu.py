@@ -160,3 +160,33 @@ def test_chain_host_equals_staged_calls(ctx, psfs):
     assert rel_err(out, ref_out) <= 1e-6 and rel_err(img, ref_img) <= 1e-6
     out0, img0, _ = ctx.chain(cube, None)
     assert np.array_equal(out0, fused) and np.array_equal(img0, fimg)
+
+
+def test_rl_properties(ctx, psfs):
+    """Size-independent properties of the iteration: non-negative input stays non-negative, and the
+    iteration is positively homogeneous (RL(a d) = a RL(d)), checked on a 300 x 280 image (no oracle)."""
+    psf, _ = psfs
+    bands, _ = pkg().host.Deconvolution(n_filters=8).plan(time_axis(1024), (2048, 2048), 0.5, 0.5, psf)
+    rng = np.random.default_rng(5)
+    img = (rng.uniform(0.2, 1.0, (300, 280)) + ((np.indices((300, 280)).sum(axis=0) // 10) % 2)).astype(F32)
+    for b in (bands[0], bands[3]):
+        u = ctx.richardson_lucy(img, 25, b.psf_x_np(), b.psf_y_np(), direct=bool(b.direct))
+        assert np.isfinite(u).all() and (u >= 0).all()
+        u4 = ctx.richardson_lucy((F32(4.0) * img).astype(F32), 25, b.psf_x_np(), b.psf_y_np(), direct=bool(b.direct))
+        assert rel_err(u4, F32(4.0) * u) <= 1e-5
+
+
+def test_chain_host_abort(ctx, psfs):
+    from helpers import default_multipliers
+    psf, _ = psfs
+    w, h, n = 32, 32, 256
+    cube = synthetic_cube(w, h, n, seed=3)
+    t, m_pre, band, m_post = default_multipliers(n)
+    ctx.plan_trace(n, m_pre, band, m_post)
+    bands, _ = pkg().host.Deconvolution(n_filters=4, n_iterations=500).plan(t, (w, h), 1.0, 1.0, psf)
+    flag = ctypes.c_uint8(1)
+    out = np.empty_like(cube)
+    img = np.empty((w, h), F32)
+    rc = pkg().lib.thz_chain_host(ctx.handle, cube.ctypes.data, w, h, n, bands, len(bands), out.ctypes.data,
+                                  img.ctypes.data, ctypes.addressof(flag), None, None)
+    assert rc == 1

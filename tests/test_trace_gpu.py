@@ -346,3 +346,32 @@ def test_voxel_opacity_and_threshold(ctx):
     assert abs(thr - float(rthr)) <= 2e-5
     _, thr0 = ctx.voxel_opacity(cube, 0.1, 2.0, 3.0, 9, max_instances=10 ** 9)
     assert thr0 == 0.0
+
+
+def test_row_slab_sharding_is_bit_identical(ctx):
+    """Row slabs over x (sharding.slab_bounds) processed independently give the same bits as one pass:
+    traces are independent and, with an even height, never change partner inside a packed pair."""
+    n, w, h = 2048, 10, 6
+    cube = synthetic_cube(w, h, n, seed=31)
+    t, m_pre, band, m_post = default_multipliers(n)
+    ctx.plan_trace(n, m_pre, band, m_post)
+    whole, img = ctx.trace_fused(cube)
+    sh = pkg().sharding
+    for world in (2, 4):
+        parts = [ctx.trace_fused(cube[slice(*sh.slab_bounds(w, world, r))]) for r in range(world)]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), whole)
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), img)
+
+
+def test_error_paths(ctx):
+    m = pkg()
+    L = m.lib
+    assert L.thz_plan_trace(ctx.handle, 5000, None, None, None) == -1           # > 4096 and not a power of two
+    assert b"power of two" in L.thz_last_error(ctx.handle)
+    assert L.thz_plan_trace(ctx.handle, 1, None, None, None) == -1
+    ctx.plan_trace(1024)
+    assert L.thz_trace_fused_dev(ctx.handle, None, None, None, 4) == -1          # null cube
+    assert L.thz_trace_fused_dev(ctx.handle, None, None, None, 0) == 0           # nothing to do
+    c2 = m.Context(0)
+    assert L.thz_trace_fused_dev(c2.handle, None, None, None, 4) == -4           # no plan: THZ_ESTATE
+    c2.close()
