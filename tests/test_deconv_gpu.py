@@ -190,3 +190,35 @@ def test_chain_host_abort(ctx, psfs):
     rc = pkg().lib.thz_chain_host(ctx.handle, cube.ctypes.data, w, h, n, bands, len(bands), out.ctypes.data,
                                   img.ctypes.data, ctypes.addressof(flag), None, None)
     assert rc == 1
+
+
+@pytest.mark.parametrize("n,w,h", [(512, 5, 7), (1024, 3, 5), (4096, 3, 3), (256, 4, 4)])
+def test_gain_application_matches_oracle(ctx, psfs, n, w, h):
+    """Pass C alone: out[p] = sum_b g_b[p] (fir_b * x[p]) in 'same' mode (deconvolution.rs:873-905) with random
+    per-pixel gains, odd pixel count (ragged last pair), in place.  n >= 512 runs the circular form with the
+    wrap-around edge corrections, n = 256 the zero-padded form: both must reproduce the linear convolution."""
+    psf, opsf = psfs
+    cube = synthetic_cube(w, h, n, seed=100 + n, noise=0.05)
+    # energy right up to both ends of the trace, so that the wrapped pieces are far from negligible
+    rng = np.random.default_rng(n)
+    cube[:, :, :40] += rng.standard_normal((w, h, 40)).astype(F32)
+    cube[:, :, -40:] += rng.standard_normal((w, h, 40)).astype(F32)
+    t = time_axis(n)
+    bands, _ = pkg().host.Deconvolution(n_filters=5).plan(t, (64, 64), 0.5, 0.5, psf)
+    obands, _ = orc.Deconvolution(n_filters=5).plan(t, (64, 64, n), 0.5, 0.5, opsf)
+    P = w * h
+    gains = (0.25 + 2.0 * rng.random((len(bands), P))).astype(F32)
+    ref = np.zeros((w, h, n), dtype=np.float64)
+    for i, ob in enumerate(obands):
+        ref += gains[i].reshape(w, h, 1).astype(np.float64) * orc.filter_scan(cube, ob.fir)
+    d_cube = ctx.to_device(cube)
+    d_g = ctx.to_device(gains)
+    d_img = ctx.alloc(P * 4)
+    ctx.deconv_apply_dev(d_cube.ptr, d_g.ptr, P, n, bands, d_cube.ptr, d_img.ptr)
+    out = d_cube.download((w, h, n))
+    img = d_img.download((w, h))
+    assert rel_err(out, ref) <= 2e-6
+    # the edges are where the two forms differ: check them on their own scale
+    for sl in (slice(0, 249), slice(n - 249, n)):
+        assert rel_err(out[:, :, sl], ref[:, :, sl]) <= 5e-6
+    assert rel_err(img, np.sum(ref * ref, axis=2)) <= 1e-5

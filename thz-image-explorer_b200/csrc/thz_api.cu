@@ -1,6 +1,8 @@
 // thz_api.cu -- the C ABI (include/thzgpu.h): context, plans, memory, host-pointer pipelines.
 #include "thz_internal.h"
 
+#include <cstring>
+#include <cstdlib>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -139,6 +141,7 @@ int thz_ctx_create(int device, thz_ctx** out) {
   thz_ctx* c = new thz_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* f = getenv("THZ_APPLY_FORM")) c->force_split_apply = (strcmp(f, "split") == 0);
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete c;

@@ -59,6 +59,7 @@ struct FirArgs {
   const float* we;       // [B][N/2] |H_b[2j]|^2   / M, lower-half registers
   const float* wo;       // [B][N/2] |H_b[2j+1]|^2 / M
   const float2* mod;     // [N] exp(-2 pi i n / M): modulation that selects the odd bins
+  float2* corr;          // [pairs][2][256] wrap-around corrections of the circular form (pass C)
 };
 
 template <int M>
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
 template <int N, bool ODD>
 __device__ __forceinline__ void mix_subspectrum(float2 (&z)[kE], const float2* sm, int t, const FirArgs& a,
                                                 const float* __restrict__ htab, int64_t p0, bool act0, bool act1,
-                                                bool& bad0, bool& bad1) {
+                                                bool& bad0, bool& bad1, float gmul = 0.5f) {
   constexpr int T = SGeo<N>::T;
   constexpr int LAST = Plan<N>::ns - 1;
   constexpr int RL = Plan<N>::r[LAST];
@@ -546,7 +547,7 @@ __device__ __forceinline__ void mix_subspectrum(float2 (&z)[kE], const float2* s
       float g1 = act1 ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
       if (!(fabsf(g0) <= 3.0e38f)) { bad0 = true; g0 = 0.f; }
       if (!(fabsf(g1) <= 3.0e38f)) { bad1 = true; g1 = 0.f; }
-      const float gs = 0.5f * (g0 + g1), gd = 0.5f * (g0 - g1);
+      const float gs = gmul * (g0 + g1), gd = gmul * (g0 - g1);
       const float* hq = htab + (size_t)b * N;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -732,6 +733,198 @@ __global__ void __launch_bounds__(256, 2) k_fir_edges(const FirArgs a) {
             if (v != 0.f) *e = fmaxf(v - s1, 0.f);
           }
         }
+      }
+    }
+  }
+}
+
+// ---- pass C, circular form -------------------------------------------------------------------------
+// With the zero-phase FIR (support |k| <= 249) and N >= 512 the N-point CIRCULAR convolution differs
+// from the reference's linear "same" convolution only in the first and the last 249 outputs, where the
+// pieces that the linear convolution pushes outside the window wrap around:
+//     circ[n]           = same[n]           + tail[n]   (n < 249)
+//     circ[N - 249 + m] = same[N - 249 + m] + head[m]   (m < 249)
+// head / tail are the same two length-497 convolutions the energy pass subtracts (k_fir_edges); they are
+// linear in the taps, so for the per-pixel filter sum_b g_b h_b one 512-point transform pair per edge gives
+// them exactly.  Pass C is then ONE forward and ONE inverse N-point transform per trace pair
+// (k_fir_apply_circ) plus the two small edge transforms (k_fir_edge_corr) instead of the four N-point
+// transforms of the zero-padded split form.
+//
+// k_fir_edge_corr: one warp per trace pair and edge; writes corr[pair][edge][256] (float2: the two traces
+// of the pair), edge 0 = head (applies to outputs N-249+m), edge 1 = tail (applies to outputs n).
+constexpr int kCorrStride = 256;
+constexpr int64_t kCorrChunkPairs = 131072;   // 512 MiB of corrections per chunk
+
+__global__ void __launch_bounds__(256, 2) k_fir_edge_corr(const FirArgs a) {
+  constexpr int M = 512;
+  using GEO = DGeo<M>;
+  constexpr int T = GEO::T, G = GEO::G;
+  static_assert(T == 32, "one warp per pair");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(M);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<M>::ns - 1;
+  constexpr int RL = Plan<M>::r[LAST];
+  constexpr int UL = kE / RL;
+  constexpr int kSeg = (THZ_FIR_TAPS - 1) / 2;   // 249
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t pair = item * G + g;
+    if (pair >= npairs) continue;                 // warps are independent (warp-scope barriers only)
+    const int64_t p0 = pair * 2;
+    const bool act1 = p0 + 1 < a.P;
+    for (int edge = 0; edge < 2; ++edge) {
+      const int off = edge ? a.n - kSeg : 0;
+      const float* r0 = a.x + p0 * a.n + off;
+      const float* r1 = r0 + a.n;
+      float2 z[kE];
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        const int e = t + i * T;
+        const bool in = e < kSeg;
+        z[i].x = in ? __ldg(r0 + e) : 0.f;
+        z[i].y = (act1 && in) ? __ldg(r1 + e) : 0.f;
+      }
+      fft_forward<M>(z, t, sm, a.tw512);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<M>(stage_elem<M, LAST>(t, i)))] = z[i];
+      __syncwarp();
+      // Y = S Z + D conj(Z_mirror), S = sum_b (g0+g1)/2 E_b, D = sum_b (g0-g1)/2 E_b (complex edge spectra)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float2 sacc[8], dacc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sacc[j] = dacc[j] = make_float2(0.f, 0.f);
+        for (int b = 0; b < a.B; ++b) {
+          float g0 = __ldg(a.gain + (size_t)b * a.bstride + p0);
+          float g1 = act1 ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
+          if (!(fabsf(g0) <= 3.0e38f)) g0 = 0.f;   // the main kernel marks such traces NaN
+          if (!(fabsf(g1) <= 3.0e38f)) g1 = 0.f;
+          const float gs = 0.5f * (g0 + g1), gd = 0.5f * (g0 - g1);
+          const float2* hq = a.edge + ((size_t)edge * a.B + b) * M;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i = half * 8 + j;
+            const int u = i % UL, m = i / UL;
+            const float2 h = __ldg(hq + m * (M / RL) + t + u * T);
+            sacc[j].x = fmaf(gs, h.x, sacc[j].x);
+            sacc[j].y = fmaf(gs, h.y, sacc[j].y);
+            dacc[j].x = fmaf(gd, h.x, dacc[j].x);
+            dacc[j].y = fmaf(gd, h.y, dacc[j].y);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = half * 8 + j;
+          const int k = pos_to_bin<M>(stage_elem<M, LAST>(t, i));
+          const float2 zp = sm[pad_idx((M - k) & (M - 1))];
+          const float2 zz = z[i];
+          z[i].x = sacc[j].x * zz.x - sacc[j].y * zz.y + dacc[j].x * zp.x + dacc[j].y * zp.y;
+          z[i].y = sacc[j].x * zz.y + sacc[j].y * zz.x - dacc[j].x * zp.y + dacc[j].y * zp.x;
+        }
+      }
+      fft_inverse<M>(z, t, sm, a.tw512);
+      const int lo = edge ? kSeg - 1 : 0;          // kept outputs [lo, lo + 249)
+      float2* dst = a.corr + ((size_t)pair * 2 + edge) * kCorrStride;
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        const int e = t + i * T - lo;
+        if (e >= 0 && e < kSeg) dst[e] = z[i];
+      }
+      __syncwarp();   // the next edge's first exchange follows the reads of the inverse transform
+    }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_circ(const FirArgs a) {
+  using GEO = SGeo<N>;
+  constexpr int T = GEO::T, G = GEO::G;
+  constexpr int kSeg = (THZ_FIR_TAPS - 1) / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(N));
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(N);
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<N>::ns - 1;
+  SlabPipe<N> pipe;
+  pipe.init(smem_raw, a.x, a.P, nitems);
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t pair = item * G + g;
+    const int64_t p0 = pair * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    const float* slab = pipe.acquire(item);
+    bool nz0, nz1, bad0 = false, bad1 = false;
+    float2 z[kE];
+    load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
+    fft_forward<N>(z, t, sm, a.tw);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
+    __syncthreads();
+    // he holds H / (2N): the N-point inverse needs H / N
+    mix_subspectrum<N, false>(z, sm, t, a, a.he, p0, act0, act1, bad0, bad1, 1.0f);
+    // wrap-around corrections of this thread's outputs, in flight across the inverse transform
+    const float2* cp = a.corr + (size_t)pair * 2 * kCorrStride;
+    float2 cr[kE];
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      cr[i] = make_float2(0.f, 0.f);
+      if (T >= kSeg && i != 0 && i != kE - 1) continue;   // only the first / last register can be an edge
+      const int n = t + i * T;
+      if (act0) {
+        if (n < kSeg) cr[i] = __ldg(cp + kCorrStride + n);
+        else if (n >= N - kSeg) cr[i] = __ldg(cp + (n - (N - kSeg)));
+      }
+    }
+    fft_inverse<N>(z, t, sm, a.tw);
+    const float kNaN = __int_as_float(0x7fc00000);
+    float* r0 = a.out + p0 * N + t;
+    float* r1 = r0 + N;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      const float y0 = bad0 ? kNaN : z[i].x - cr[i].x, y1 = bad1 ? kNaN : z[i].y - cr[i].y;
+      if (act0) __stcs(r0 + i * T, y0);
+      if (act1) __stcs(r1 + i * T, y1);
+      s0 = fmaf(y0, y0, s0);
+      s1 = fmaf(y1, y1, s1);
+    }
+    if (a.img != nullptr) {
+      constexpr int W = (T < 32) ? T : 32;
+#pragma unroll
+      for (int o = W / 2; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      }
+      if constexpr (T > 32) {
+        float* sc = scr + g * 32;
+        if ((t & 31) == 0) {
+          sc[2 * (t >> 5)] = s0;
+          sc[2 * (t >> 5) + 1] = s1;
+        }
+        __syncthreads();
+        if (t == 0) {
+          float sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int w = 0; w < T / 32; ++w) {
+            sa += sc[2 * w];
+            sb += sc[2 * w + 1];
+          }
+          s0 = sa;
+          s1 = sb;
+        }
+      }
+      if (t == 0) {
+        if (act0) a.img[p0] = s0;
+        if (act1) a.img[p0 + 1] = s1;
       }
     }
   }
@@ -1136,6 +1329,218 @@ __global__ void __launch_bounds__(kRlThreads, 1) k_rl_conv_persistent(const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Streaming separable RL filtering.  A CTA owns a strip of kSW output columns and a segment of
+// output rows and marches down the strip in chunks of kCR input rows: each chunk is fetched by TMA
+// (two buffers, prefetch distance two chunks), filtered along the columns into a ring of
+// column-filtered rows kept in shared memory (stored transposed, so that the row pass reads its
+// taps' axis with 128-bit loads), and the output rows whose whole row support is in the ring are
+// emitted with the fused epilogue.  Every image row is column-filtered once per segment (only the
+// WU warm-up rows of a segment are filtered twice), both passes are exactly one item per thread
+// (16 outputs x T taps), and the ring holds one chunk of slack so that one barrier per chunk suffices.
+//
+// Taps are front-padded with zeros to WU + 1 (rows) / KW + 1 (columns) entries, WU and KW being the
+// true support minus one rounded up to a multiple of 8, so that the window advances in whole
+// 8-element blocks and the last tap is a single trailing step that needs no new data.
+// ------------------------------------------------------------------------------------
+constexpr int kSW = 128;          // output columns per strip
+constexpr int kCR = 64;           // input rows per chunk
+constexpr int kStThreads = 512;   // = kCR * kSW / 16: one 16-output item per thread in both passes
+
+struct StreamArgs {
+  int Hp, Wp, pitch;
+  int WU, KW;           // warm-up rows / columns (multiples of 8)
+  int gy_off, gx_off;   // box origin = (segment row 0 - gy_off, strip column 0 - gx_off)
+  int bc;               // box columns (4 * odd, >= kSW + KW)
+  int Rg, RS;           // ring rows (multiple of 8, >= 2 kCR + WU) and ring stride in floats (4 * odd)
+  int seg_rows;         // output rows per segment (kCR * chunks - WU)
+  int col_shift;        // keeps the box start 16-byte aligned
+  const float* wx;      // [WU + 8] front-padded row taps, wx[WU] is the last tap
+  const float* wy;      // [KW + 8]
+  const float* d;
+  float* out;
+  float eps;
+};
+
+// logical window element idx in [0, 24) -> register, the three 8-groups rotate with the phase
+__device__ __forceinline__ constexpr int win_phys(int idx, int ph) { return (((idx >> 3) + ph) % 3) * 8 + (idx & 7); }
+
+template <int PH>
+__device__ __forceinline__ void tap_block(float (&acc)[16], float (&W)[24], const float4 n0, const float4 n1,
+                                          const float* __restrict__ w8) {
+  constexpr int g2 = ((2 + PH) % 3) * 8;
+  W[g2 + 0] = n0.x; W[g2 + 1] = n0.y; W[g2 + 2] = n0.z; W[g2 + 3] = n0.w;
+  W[g2 + 4] = n1.x; W[g2 + 5] = n1.y; W[g2 + 6] = n1.z; W[g2 + 7] = n1.w;
+  const float4 wa = *reinterpret_cast<const float4*>(w8), wb = *reinterpret_cast<const float4*>(w8 + 4);
+  const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = fmaf(wv[n], W[win_phys(q + n, PH)], acc[q]);
+}
+
+template <int PH>
+__device__ __forceinline__ void tap_last(float (&acc)[16], const float (&W)[24], float wl) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) acc[q] = fmaf(wl, W[win_phys(q, PH)], acc[q]);
+}
+
+// 16 outputs, T + 1 taps (T a multiple of 8).  L::next() returns the next 8 window elements.
+template <class L>
+__device__ __forceinline__ void run_taps(float (&acc)[16], L& ld, const float* __restrict__ w, int T) {
+  float W[24];
+  float4 a, b;
+  ld.next(a, b);
+  W[0] = a.x; W[1] = a.y; W[2] = a.z; W[3] = a.w; W[4] = b.x; W[5] = b.y; W[6] = b.z; W[7] = b.w;
+  ld.next(a, b);
+  W[8] = a.x; W[9] = a.y; W[10] = a.z; W[11] = a.w; W[12] = b.x; W[13] = b.y; W[14] = b.z; W[15] = b.w;
+  int nb = 0;
+  for (; nb + 24 <= T; nb += 24) {
+    ld.next(a, b);
+    tap_block<0>(acc, W, a, b, w + nb);
+    ld.next(a, b);
+    tap_block<1>(acc, W, a, b, w + nb + 8);
+    ld.next(a, b);
+    tap_block<2>(acc, W, a, b, w + nb + 16);
+  }
+  const int rem = (T - nb) >> 3;
+  const float wl = w[T];
+  if (rem == 0) {
+    tap_last<0>(acc, W, wl);
+  } else if (rem == 1) {
+    ld.next(a, b);
+    tap_block<0>(acc, W, a, b, w + nb);
+    tap_last<1>(acc, W, wl);
+  } else {
+    ld.next(a, b);
+    tap_block<0>(acc, W, a, b, w + nb);
+    ld.next(a, b);
+    tap_block<1>(acc, W, a, b, w + nb + 8);
+    tap_last<2>(acc, W, wl);
+  }
+}
+
+struct LinearLoader {   // consecutive floats of one haloed tile row
+  const float* p;
+  __device__ __forceinline__ void next(float4& a, float4& b) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+    p += 8;
+  }
+};
+
+struct RingLoader {     // consecutive ring rows of one column (transposed ring: rows are contiguous)
+  const float* col;
+  int pos, Rg;
+  __device__ __forceinline__ void next(float4& a, float4& b) {
+    a = *reinterpret_cast<const float4*>(col + pos);
+    b = *reinterpret_cast<const float4*>(col + pos + 4);
+    pos += 8;
+    if (pos >= Rg) pos -= Rg;
+  }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kStThreads, 1) k_rl_stream(const __grid_constant__ CUtensorMap tmap,
+                                                             const StreamArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const uint32_t mbar0 = smem_u32(base);                       // two barriers, 8 bytes apart
+  const int tile_floats = kCR * a.bc;
+  float* tile0 = reinterpret_cast<float*>(base + 128);
+  float* ring = tile0 + 2 * tile_floats;                       // [kSW][RS]
+  float* wxs = ring + kSW * a.RS;
+  float* wys = wxs + a.WU + 8;
+  const int tid = threadIdx.x;
+  const int col0 = blockIdx.x * kSW + a.col_shift;
+  const int seg_row0 = blockIdx.y * a.seg_rows;
+  const int rows_out = min(a.seg_rows, a.Hp - seg_row0);
+  if (rows_out <= 0) return;
+  const int n_chunks = (rows_out + a.WU + kCR - 1) / kCR;
+  const int gy0 = seg_row0 - a.gy_off, gx0 = col0 - a.gx_off;
+  const uint32_t tile_bytes = (uint32_t)(tile_floats * sizeof(float));
+  // a chunk that lies wholly above or below the image is all zeros: no copy, the ring rows are cleared
+  auto live = [&](int j) { return gy0 + kCR * j < a.Hp && gy0 + kCR * (j + 1) > 0; };
+
+  if (tid == 0) {
+    mbar_init(mbar0, 1);
+    mbar_init(mbar0 + 8, 1);
+  }
+  for (int i = tid; i < a.WU + 8; i += kStThreads) wxs[i] = a.wx[i];
+  for (int i = tid; i < a.KW + 8; i += kStThreads) wys[i] = a.wy[i];
+  __syncthreads();
+  if (tid == 0) {
+    for (int j = 0; j < 2 && j < n_chunks; ++j)
+      if (live(j)) {
+        mbar_expect_tx(mbar0 + 8 * j, tile_bytes);
+        tma_load_2d(smem_u32(tile0 + j * tile_floats), &tmap, gx0, gy0 + kCR * j, mbar0 + 8 * j);
+      }
+  }
+  uint32_t ph0 = 0, ph1 = 0;   // mbarrier phase parity per buffer
+  for (int j = 0; j < n_chunks; ++j) {
+    const int buf = j & 1;
+    const bool lv = live(j);
+    // ---- column pass: thread = (chunk row r, 16 output columns cg*16 ..) ----
+    {
+      const int r = tid & (kCR - 1), cg = tid >> 6;
+      float acc[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+      if (lv) {
+        const uint32_t mb = mbar0 + 8 * buf;
+        while (!mbar_try_wait(mb, buf ? ph1 : ph0)) {
+        }
+        if (buf) ph1 ^= 1; else ph0 ^= 1;
+        LinearLoader ld{tile0 + buf * tile_floats + r * a.bc + cg * 16};
+        run_taps(acc, ld, wys, a.KW);
+      }
+      int pos = (j * kCR + r) % a.Rg;
+      float* dst = ring + (cg * 16) * a.RS + pos;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) dst[q * a.RS] = acc[q];
+    }
+    __syncthreads();   // ring rows of chunk j are visible; tile[buf] is free
+    if (tid == 0 && j + 2 < n_chunks && live(j + 2)) {
+      mbar_expect_tx(mbar0 + 8 * buf, tile_bytes);
+      tma_load_2d(smem_u32(tile0 + buf * tile_floats), &tmap, gx0, gy0 + kCR * (j + 2), mbar0 + 8 * buf);
+    }
+    // ---- row pass: thread = (strip column c, 16 output rows) of the rows that became complete ----
+    const int lo = max(0, j * kCR - a.WU), hi = min(rows_out, (j + 1) * kCR - a.WU);
+    const int c = tid & (kSW - 1), rg = tid >> 7;
+    const int i0 = lo + rg * 16;
+    if (i0 < hi) {
+      const int gc = col0 + c;
+      const bool colok = gc >= 0 && gc < a.Wp;
+      const size_t o0 = (size_t)(seg_row0 + i0) * a.pitch + gc;
+      float ep[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        ep[q] = 0.f;
+        if (MODE != 0 && colok && i0 + q < hi) {
+          const size_t o = o0 + (size_t)q * a.pitch;
+          ep[q] = (MODE == 1) ? __ldg(a.d + o) : a.out[o];
+        }
+      }
+      float acc[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+      RingLoader ld{ring + c * a.RS, i0 % a.Rg, a.Rg};
+      run_taps(acc, ld, wxs, a.WU);
+      if (colok) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          if (i0 + q < hi) {
+            const size_t o = o0 + (size_t)q * a.pitch;
+            if constexpr (MODE == 0) a.out[o] = acc[q];
+            else if constexpr (MODE == 1) a.out[o] = ep[q] / (acc[q] + a.eps);
+            else a.out[o] = ep[q] * acc[q];
+          }
+        }
+      }
+    }
+  }
+}
+
 // numpy-"reflect" padding exactly as richardson_lucy writes it (deconvolution.rs:638-667)
 __global__ void k_reflect_pad(const float* __restrict__ img, int h, int w, int pad_y, int pad_x, float* __restrict__ out,
                               int pitch) {
@@ -1447,6 +1852,9 @@ template <int N> static int do_energy_split(thz_ctx* c, cudaStream_t s, const Fi
 template <int N> static int do_apply_split(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
   return launch_fir<N>(c, s, k_fir_apply_split<N>, a, SGeo<N>::smem_bytes);
 }
+template <int N> static int do_apply_circ(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
+  return launch_fir<N>(c, s, k_fir_apply_circ<N>, a, SGeo<N>::smem_bytes);
+}
 
 #define THZ_DISPATCH_M(m, FN, ...)                 \
   switch (m) {                                     \
@@ -1471,6 +1879,9 @@ static int dispatch_energy_split(thz_ctx* c, cudaStream_t s, int n, const FirArg
 }
 static int dispatch_apply_split(thz_ctx* c, cudaStream_t s, int n, const FirArgs& a) {
   THZ_DISPATCH_M(n, do_apply_split, c, s, a);
+}
+static int dispatch_apply_circ(thz_ctx* c, cudaStream_t s, int n, const FirArgs& a) {
+  THZ_DISPATCH_M(n, do_apply_circ, c, s, a);
 }
 
 int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
@@ -1538,7 +1949,33 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
       if (rc != THZ_OK) return rc;
       a.tw = tbn->d_tw;
       a.he = ft.d_he; a.ho = ft.d_ho; a.mod = ft.d_mod;
-      rc = dispatch_apply_split(c, s, n, a);
+      if (n >= 512 && !c->force_split_apply) {
+        // circular form: edge corrections of a chunk of pairs, then the one-transform-pair main pass
+        const FftTables* tb512 = nullptr;
+        rc = get_tables(c, 512, &tb512);
+        if (rc != THZ_OK) return rc;
+        a.tw512 = tb512->d_tw;
+        a.edge = ft.d_edge;
+        const int64_t npairs = (P + 1) / 2;
+        const int64_t chunk_pairs = std::min<int64_t>(npairs, kCorrChunkPairs);
+        void* pc = nullptr;
+        rc = ws_get(c, WS_EDGE_CORR, (size_t)chunk_pairs * 2 * kCorrStride * sizeof(float2), &pc);
+        if (rc != THZ_OK) return rc;
+        for (int64_t q0 = 0; rc == THZ_OK && q0 < npairs; q0 += chunk_pairs) {
+          const int64_t p_lo = 2 * q0, p_hi = std::min<int64_t>(P, 2 * (q0 + chunk_pairs));
+          FirArgs ac = a;
+          ac.x = d_cube + p_lo * n;
+          ac.P = p_hi - p_lo;
+          ac.gain = d_gain + p_lo;
+          ac.out = d_out + p_lo * n;
+          ac.img = d_img ? d_img + p_lo : nullptr;
+          ac.corr = (float2*)pc;
+          rc = launch_fir<512>(c, s, k_fir_edge_corr, ac);
+          if (rc == THZ_OK) rc = dispatch_apply_circ(c, s, n, ac);
+        }
+      } else {
+        rc = dispatch_apply_split(c, s, n, a);
+      }
     } else {
       rc = dispatch_apply(c, s, ft.m, a);
     }
@@ -1586,6 +2023,15 @@ struct ConvPlan {
   bool dense = false;
   float* d_w = nullptr;   // device taps: [wx (kxp) | wy (kyp)] x 2 orientations, or dense [2][kx][kyp]
   int wstride = 0;        // floats between the two orientations
+  // streaming form (k_rl_stream): used when the strip buffers fit in shared memory
+  bool streaming = false;
+  StreamArgs sa{};
+  size_t ssmem = 0;
+  dim3 sgrid;
+  float* d_ws = nullptr;  // [wx' (WU + 8) | wy' (KW + 8)] x 2 orientations
+  int swstride = 0;
+  int map_rows() const { return streaming ? kCR : a.box_rows; }
+  int map_cols() const { return streaming ? sa.bc : a.box_cols; }
 };
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -1633,10 +2079,51 @@ static int make_conv_plan(thz_ctx* c, cudaStream_t s, int Hp, int Wp, int pitch,
     }
   }
   if (cp.smem > 227 * 1024) return set_err(c, THZ_EINVAL, "PSF too large for the shared-memory tile");
+  const size_t w_tile = w.size();
+  if (!cp.dense) {
+    StreamArgs& sa = cp.sa;
+    sa.Hp = Hp; sa.Wp = Wp; sa.pitch = pitch;
+    sa.WU = round_up(kx - 1, 8);
+    sa.KW = round_up(ky - 1, 8);
+    const int padx = sa.WU - (kx - 1), pady = sa.KW - (ky - 1);
+    sa.gy_off = kx / 2 + padx;
+    sa.gx_off = ky / 2 + pady;
+    int sbc = round_up(kSW + sa.KW, 4);
+    if (((sbc / 4) & 1) == 0) sbc += 4;
+    sa.bc = sbc;
+    sa.Rg = 2 * kCR + sa.WU;
+    sa.RS = sa.Rg + 4;
+    if (((sa.RS / 4) & 1) == 0) sa.RS += 4;
+    sa.col_shift = (sa.gx_off % 4 == 0) ? 0 : (sa.gx_off % 4) - 4;
+    sa.eps = a.eps;
+    cp.ssmem = (size_t)(2 * kCR * sa.bc + kSW * sa.RS + sa.WU + 8 + sa.KW + 8) * sizeof(float) + 256;
+    cp.streaming = cp.ssmem <= 227 * 1024 && sa.bc <= 256;
+    if (cp.streaming) {
+      // segments: as many per strip as fill the SMs once, each a whole number of chunks
+      const int strips = (Wp - sa.col_shift + kSW - 1) / kSW;
+      int segs = std::max(1, c->sm_count / strips);
+      segs = std::min(segs, (Hp + kCR - 1) / kCR);
+      const int per_seg = (Hp + segs - 1) / segs;
+      const int chunks = (per_seg + sa.WU + kCR - 1) / kCR;
+      sa.seg_rows = chunks * kCR - sa.WU;
+      segs = (Hp + sa.seg_rows - 1) / sa.seg_rows;
+      cp.sgrid = dim3(strips, segs);
+      cp.swstride = sa.WU + 8 + sa.KW + 8;
+      w.resize(w_tile + 2 * cp.swstride, 0.f);
+      for (int o = 0; o < 2; ++o) {
+        const bool flip = (o == 0) ? (direct == 0) : (direct != 0);
+        float* wx = w.data() + w_tile + o * cp.swstride;
+        float* wy = wx + sa.WU + 8;
+        for (int i = 0; i < kx; ++i) wx[padx + i] = psf_x[flip ? kx - 1 - i : i];
+        for (int j = 0; j < ky; ++j) wy[pady + j] = psf_y[flip ? ky - 1 - j : j];
+      }
+    }
+  }
   void* dp = nullptr;
   int rc = ws_get(c, WS_RL_TAPS, w.size() * sizeof(float), &dp);
   if (rc != THZ_OK) return rc;
   cp.d_w = (float*)dp;
+  cp.d_ws = cp.d_w + w_tile;
   THZ_CUDA(c, cudaStreamSynchronize(s));   // the previous band's kernels are done with the taps
   THZ_CUDA(c, cudaMemcpyAsync(cp.d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   THZ_CUDA(c, cudaStreamSynchronize(s));
@@ -1657,6 +2144,25 @@ static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUt
   a.out = out;
   dim3 grid((a.Wp - a.col_shift + kTW - 1) / kTW, (a.Hp + kTH - 1) / kTH);
   cudaError_t e;
+  if (cp.streaming) {
+    StreamArgs sa = cp.sa;
+    sa.wx = cp.d_ws + (size_t)orient * cp.swstride;
+    sa.wy = sa.wx + sa.WU + 8;
+    sa.d = d;
+    sa.out = out;
+    const void* skey = (const void*)k_rl_stream<MODE>;
+    size_t& shave = c->smem_set[skey];
+    if (shave < cp.ssmem) {
+      e = cudaFuncSetAttribute(skey, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.ssmem);
+      if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl stream)");
+      shave = cp.ssmem;
+    }
+    k_rl_stream<MODE><<<cp.sgrid, kStThreads, cp.ssmem, s>>>(map, sa);
+    c->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_stream launch");
+    return THZ_OK;
+  }
   if (!cp.dense) {
     // persistent, double-buffered form: two haloed tiles + the intermediate tile
     const int tile_floats = (a.box_rows * a.box_cols + 31) & ~31;
@@ -1713,7 +2219,7 @@ int conv2d_once(thz_ctx* c, cudaStream_t s, const float* d_in, int rows, int col
   ConvPlan cp;
   int rc = make_conv_plan(c, s, rows, cols, pitch, psf_x, kx, psf_y, ky, dense, direct ? 1 : 0, cp);
   CUtensorMap map;
-  if (rc == THZ_OK) rc = make_tmap(c, &map, d_a, rows, cols, pitch, cp.a.box_rows, cp.a.box_cols);
+  if (rc == THZ_OK) rc = make_tmap(c, &map, d_a, rows, cols, pitch, cp.map_rows(), cp.map_cols());
   // orientation 0 is "the kernel as given": correlation when direct, convolution otherwise
   if (rc == THZ_OK) rc = launch_conv<0>(c, s, cp, map, 0, nullptr, d_b);
   if (rc == THZ_OK) {
@@ -1749,8 +2255,8 @@ int richardson_lucy(thz_ctx* c, cudaStream_t s, const float* d_image, int rows, 
   ConvPlan cp;
   int rc = make_conv_plan(c, s, Hp, Wp, pitch, psf_x, kx, psf_y, ky, dense, direct ? 1 : 0, cp);
   CUtensorMap map_u, map_r;
-  if (rc == THZ_OK) rc = make_tmap(c, &map_u, d_u, Hp, Wp, pitch, cp.a.box_rows, cp.a.box_cols);
-  if (rc == THZ_OK) rc = make_tmap(c, &map_r, d_r, Hp, Wp, pitch, cp.a.box_rows, cp.a.box_cols);
+  if (rc == THZ_OK) rc = make_tmap(c, &map_u, d_u, Hp, Wp, pitch, cp.map_rows(), cp.map_cols());
+  if (rc == THZ_OK) rc = make_tmap(c, &map_r, d_r, Hp, Wp, pitch, cp.map_rows(), cp.map_cols());
   bool aborted = false;
   for (int it = 0; rc == THZ_OK && it < n_iter; ++it) {
     rc = launch_conv<1>(c, s, cp, map_u, 0, d_d, d_r);          // r = d / (u (*) psf + eps)
