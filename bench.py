@@ -355,25 +355,35 @@ def run_ours(a):
     stages = {"trace_fused": {"ms": trace_ms, "kernel": f"k_trace_fused<{N}>", "algorithmic_bytes": (8 * N + 4) * P}}
     if bands is not None and world == 1:
         st = ctx.deconv_stage_ms()
-        stages["deconv_energies"] = {"ms": st["energies_ms"], "kernel": f"k_fir_energy_split<{N}> + k_fir_edges",
-                                     "algorithmic_bytes": (4 * N + 4 * B) * P}
-        stages["deconv_apply"] = {"ms": st["apply_ms"], "kernel": f"k_fir_apply_split<{N}>",
-                                  "algorithmic_bytes": (8 * N + 4 * B) * P}
-        stages["richardson_lucy"] = {"ms": st["rl_ms"], "kernel": "k_rl_conv_persistent<1|2>",
+        km = ctx.deconv_kernel_ms()
+        # per-kernel algorithmic bytes (SURVEY 8d / DESIGN.md): the spectra pass reads the cube and writes B
+        # energies per trace; the edge passes touch 2 x 249 samples per trace; the main gain pass reads and
+        # writes the cube, reads B gains and 2 x 249 corrections and writes the intensity
+        stages["deconv_energy_spectra"] = {"ms": km["energy_spectra_ms"], "kernel": f"k_fir_energy_split<{N}>",
+                                           "algorithmic_bytes": (4 * N + 4 * B) * P}
+        stages["deconv_energy_edges"] = {"ms": km["energy_edges_ms"], "kernel": "k_fir_edges",
+                                         "algorithmic_bytes": (4 * 498 + 8 * B) * P}
+        stages["deconv_apply_edges"] = {"ms": km["apply_edges_ms"], "kernel": "k_fir_edge_corr",
+                                        "algorithmic_bytes": (4 * 498 + 4 * B + 4 * 498) * P}
+        stages["deconv_apply"] = {"ms": km["apply_main_ms"], "kernel": f"k_fir_apply_circ<{N}>",
+                                  "algorithmic_bytes": (8 * N + 4 * B + 4 * 498 + 4) * P}
+        stages["richardson_lucy"] = {"ms": st["rl_ms"], "kernel": "k_rl_stream<1|2>",
                                      "iterations": st["rl_iterations"],
                                      "iters_per_s": st["rl_iterations"] / (st["rl_ms"] / 1e3) if st["rl_ms"] > 0 else None}
+        stages["stage_totals_ms"] = {"energies": st["energies_ms"], "richardson_lucy": st["rl_ms"],
+                                     "gain_application": st["apply_ms"]}
     for v in stages.values():
-        if "algorithmic_bytes" in v:
+        if "algorithmic_bytes" in v and v["ms"] > 0:
             v["gbs"] = v["algorithmic_bytes"] / (v["ms"] / 1e3) / 1e9
             v["frac_of_hbm_peak"] = v["gbs"] / peak
-    dom = max((k for k in stages if "algorithmic_bytes" in stages[k]), key=lambda k: stages[k]["ms"])
+    dom = max((k for k in stages if "gbs" in stages[k]), key=lambda k: stages[k]["ms"])
     # DRAM traffic of the same kernel from the committed ncu capture (profiles/r01_traffic.json, C5 on 1 GPU)
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
         if world == 1 and (W, H, N, B if bands is not None else 8) == (2048, 2048, 4096, 8):
             traffic = sum(v["traffic_bytes_per_launch"] for k, v in tj.items()
-                          if k.split("<")[0] in stages[dom]["kernel"])
+                          if k.split("<")[0] == stages[dom]["kernel"].split("<")[0]) or None
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "kernel": stages[dom]["kernel"], "stage": dom, "achieved": stages[dom]["gbs"],

@@ -290,6 +290,10 @@ int thz_deconvolution_dev(thz_ctx* ctx, const float* d_cube, int rows, int cols,
  * wall time the reference shows beside the filter header (src/data_thread.rs:1107, 1169-1184):
  * ms4 = {band energies, Richardson-Lucy, gain application, number of RL iterations run}. */
 int thz_deconv_stage_ms(const thz_ctx* ctx, float* ms4);
+/* Same call, per cube kernel (CUDA event pairs around each launch, read back after the call's final
+ * synchronisation; the launches stay asynchronous): ms4 = {band-energy spectra pass, band-energy edge pass, gain-application edge corrections,
+ * gain-application main pass}. */
+int thz_deconv_kernel_ms(const thz_ctx* ctx, float* ms4);
 /* Host-pointer drop-in for `Deconvolution::filter`. */
 int thz_deconvolution_host(thz_ctx* ctx, const float* cube, int rows, int cols, int n,
                            const thz_band_plan* bands, int n_bands, float* out, float* img,

@@ -145,6 +145,7 @@ def load_library():
         "thz_deconv_apply_dev": (i32, [vp, fp, fp, i64, i32, C.POINTER(BandPlanC), i32, fp, fp]),
         "thz_deconvolution_dev": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_deconv_stage_ms": (i32, [vp, fp]),
+        "thz_deconv_kernel_ms": (i32, [vp, fp]),
         "thz_chain_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_deconvolution_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_scale_blocks_dev": (i32, [vp, fp, i32, i32, i32, i32, fp]),
@@ -525,6 +526,12 @@ class Context:
         ms = np.zeros(4, np.float32)
         self._check(lib.thz_deconv_stage_ms(self.handle, ms.ctypes.data))
         return {"energies_ms": float(ms[0]), "rl_ms": float(ms[1]), "apply_ms": float(ms[2]), "rl_iterations": int(ms[3])}
+
+    def deconv_kernel_ms(self):
+        ms = np.zeros(4, np.float32)
+        self._check(lib.thz_deconv_kernel_ms(self.handle, ms.ctypes.data))
+        return {"energy_spectra_ms": float(ms[0]), "energy_edges_ms": float(ms[1]), "apply_edges_ms": float(ms[2]),
+                "apply_main_ms": float(ms[3])}
 
 
 class Chain:

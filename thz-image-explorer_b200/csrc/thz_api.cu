@@ -141,6 +141,8 @@ int thz_ctx_create(int device, thz_ctx** out) {
   thz_ctx* c = new thz_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  c->unstaged_fir = true;
+  if (const char* f = getenv("THZ_FIR_STAGING")) c->unstaged_fir = (strcmp(f, "on") != 0);
   if (const char* f = getenv("THZ_APPLY_FORM")) c->force_split_apply = (strcmp(f, "split") == 0);
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {

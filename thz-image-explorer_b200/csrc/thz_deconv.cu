@@ -338,6 +338,23 @@ __device__ __forceinline__ void load_pair_n(float2 (&v)[kE], const float* slab, 
   }
 }
 
+// unstaged variant: straight from global memory (streaming loads), leaves the shared memory to L1
+template <int N>
+__device__ __forceinline__ void load_pair_direct(float2 (&v)[kE], const float* __restrict__ x, int64_t p0, int t,
+                                                 bool act0, bool act1, bool& nz0, bool& nz1) {
+  constexpr int T = SGeo<N>::T;
+  const float* r0 = x + p0 * N + t;
+  const float* r1 = r0 + N;
+  nz0 = nz1 = false;
+#pragma unroll
+  for (int i = 0; i < kE; ++i) {
+    v[i].x = act0 ? __ldcs(r0 + i * T) : 0.f;
+    v[i].y = act1 ? __ldcs(r1 + i * T) : 0.f;
+    nz0 |= (v[i].x != 0.f);
+    nz1 |= (v[i].y != 0.f);
+  }
+}
+
 // common prologue / per-iteration staging of the split kernels
 template <int N> struct SlabPipe {
   using GEO = SGeo<N>;
@@ -401,7 +418,7 @@ __device__ __forceinline__ void parseval_terms(const float2 (&z)[kE], const floa
   }
 }
 
-template <int N>
+template <int N, bool STAGED>
 __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy_split(const FirArgs a) {
   using GEO = SGeo<N>;
   constexpr int T = GEO::T, G = GEO::G;
@@ -424,17 +441,19 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
   int parity = 0;
   (void)M;
   SlabPipe<N> pipe;
-  pipe.init(smem_raw, a.x, a.P, nitems);
+  if constexpr (STAGED) pipe.init(smem_raw, a.x, a.P, nitems);
 
   for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
     const int64_t p0 = (item * G + g) * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
-    const float* slab = pipe.acquire(item);
+    const float* slab = nullptr;
+    if constexpr (STAGED) slab = pipe.acquire(item);
     float2 z[kE];
     bool nz0, nz1, z0, z1;
     float q1e[NLOW], q2e[NLOW], q1o[NLOW], q2o[NLOW];
     // even bins
-    load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
+    if constexpr (STAGED) load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
+    else load_pair_direct<N>(z, a.x, p0, t, act0, act1, nz0, nz1);
     nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
     fft_forward<N>(z, t, sm, a.tw);
     __syncthreads();
@@ -451,7 +470,8 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
     }
     // odd bins
     bool d0, d1;
-    load_pair_n<N>(z, slab, t, g, act0, act1, d0, d1);
+    if constexpr (STAGED) load_pair_n<N>(z, slab, t, g, act0, act1, d0, d1);
+    else load_pair_direct<N>(z, a.x, p0, t, act0, act1, d0, d1);   // second read: L2
     modulate<N>(z, a.mod, t);
     fft_forward<N>(z, t, sm, a.tw);   // its first barrier orders the partner reads above before the exchange
     __syncthreads();
@@ -738,6 +758,68 @@ __global__ void __launch_bounds__(256, 2) k_fir_edges(const FirArgs a) {
   }
 }
 
+// Paired form of the mix for a full N-point spectrum with a real, even H (zero-phase FIR): the bins k and
+// N - k share S and D, so the owner of the lower-half register (k < N/2) forms S and D once and produces
+// both outputs,  Y[k] = S Z[k] + D conj(Z[N-k])  (kept)  and  Y[N-k] = S Z[N-k] + D conj(Z[k])  (written over
+// Z[N-k] in shared memory, which only this thread reads).  After a barrier every thread fetches its
+// upper-half registers.  Halves the table loads and the S / D arithmetic.  `sm` holds the spectrum in
+// natural order on entry; thread 0 also owns the self-mirrored Nyquist bin (register kE/2).
+template <int N>
+__device__ __forceinline__ void mix_paired(float2 (&z)[kE], float2* sm, int t, const FirArgs& a,
+                                           const float* __restrict__ htab, int64_t p0, bool act0, bool act1,
+                                           bool& bad0, bool& bad1, float gmul) {
+  constexpr int T = SGeo<N>::T;
+  constexpr int LAST = Plan<N>::ns - 1;
+  constexpr int RL = Plan<N>::r[LAST];
+  constexpr int UL = kE / RL;
+  constexpr int NLOW = kE / 2;
+  float sacc[NLOW], dacc[NLOW];
+#pragma unroll
+  for (int j = 0; j < NLOW; ++j) sacc[j] = dacc[j] = 0.f;
+  float sny = 0.f, dny = 0.f;
+  for (int b = 0; b < a.B; ++b) {
+    float g0 = act0 ? __ldg(a.gain + (size_t)b * a.bstride + p0) : 0.f;
+    float g1 = act1 ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
+    if (!(fabsf(g0) <= 3.0e38f)) { bad0 = true; g0 = 0.f; }
+    if (!(fabsf(g1) <= 3.0e38f)) { bad1 = true; g1 = 0.f; }
+    const float gs = gmul * (g0 + g1), gd = gmul * (g0 - g1);
+    const float* hq = htab + (size_t)b * N;
+#pragma unroll
+    for (int j = 0; j < NLOW; ++j) {
+      const int u = j % UL, m = j / UL;
+      const float h = __ldg(hq + m * (N / RL) + t + u * T);
+      sacc[j] = fmaf(gs, h, sacc[j]);
+      dacc[j] = fmaf(gd, h, dacc[j]);
+    }
+    if (t == 0) {
+      const float h = __ldg(hq + (RL / 2) * (N / RL));
+      sny = fmaf(gs, h, sny);
+      dny = fmaf(gd, h, dny);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NLOW; ++j) {
+    const int k = pos_to_bin<N>(stage_elem<N, LAST>(t, j));
+    const float2 zk = z[j];
+    if (k == 0) {
+      z[j] = make_float2((sacc[j] + dacc[j]) * zk.x, (sacc[j] - dacc[j]) * zk.y);
+    } else {
+      float2* mp = sm + pad_idx(N - k);
+      const float2 zm = *mp;
+      z[j] = make_float2(fmaf(sacc[j], zk.x, dacc[j] * zm.x), fmaf(sacc[j], zk.y, -dacc[j] * zm.y));
+      *mp = make_float2(fmaf(sacc[j], zm.x, dacc[j] * zk.x), fmaf(sacc[j], zm.y, -dacc[j] * zk.y));
+    }
+  }
+  if (t == 0) {
+    float2* np = sm + pad_idx(N / 2);
+    const float2 zn = *np;
+    *np = make_float2((sny + dny) * zn.x, (sny - dny) * zn.y);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = NLOW; i < kE; ++i) z[i] = sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))];
+}
+
 // ---- pass C, circular form -------------------------------------------------------------------------
 // With the zero-phase FIR (support |k| <= 249) and N >= 512 the N-point CIRCULAR convolution differs
 // from the reference's linear "same" convolution only in the first and the last 249 outputs, where the
@@ -793,12 +875,15 @@ __global__ void __launch_bounds__(256, 2) k_fir_edge_corr(const FirArgs a) {
 #pragma unroll
       for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<M>(stage_elem<M, LAST>(t, i)))] = z[i];
       __syncwarp();
-      // Y = S Z + D conj(Z_mirror), S = sum_b (g0+g1)/2 E_b, D = sum_b (g0-g1)/2 E_b (complex edge spectra)
+      // Y = S Z + D conj(Z_mirror), S = sum_b (g0+g1)/2 E_b, D = sum_b (g0-g1)/2 E_b (complex edge spectra).
+      // The taps are real, E_b[M-k] = conj(E_b[k]): the owner of the lower-half register forms S and D once
+      // and produces both Y[k] and Y[M-k] (see mix_paired); thread 0 also owns the Nyquist bin.
+      {
+        constexpr int NLOW = kE / 2;
+        float2 sacc[NLOW], dacc[NLOW];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float2 sacc[8], dacc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sacc[j] = dacc[j] = make_float2(0.f, 0.f);
+        for (int j = 0; j < NLOW; ++j) sacc[j] = dacc[j] = make_float2(0.f, 0.f);
+        float2 sny = make_float2(0.f, 0.f), dny = make_float2(0.f, 0.f);
         for (int b = 0; b < a.B; ++b) {
           float g0 = __ldg(a.gain + (size_t)b * a.bstride + p0);
           float g1 = act1 ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
@@ -807,25 +892,48 @@ __global__ void __launch_bounds__(256, 2) k_fir_edge_corr(const FirArgs a) {
           const float gs = 0.5f * (g0 + g1), gd = 0.5f * (g0 - g1);
           const float2* hq = a.edge + ((size_t)edge * a.B + b) * M;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int i = half * 8 + j;
-            const int u = i % UL, m = i / UL;
+          for (int j = 0; j < NLOW; ++j) {
+            const int u = j % UL, m = j / UL;
             const float2 h = __ldg(hq + m * (M / RL) + t + u * T);
             sacc[j].x = fmaf(gs, h.x, sacc[j].x);
             sacc[j].y = fmaf(gs, h.y, sacc[j].y);
             dacc[j].x = fmaf(gd, h.x, dacc[j].x);
             dacc[j].y = fmaf(gd, h.y, dacc[j].y);
           }
+          if (t == 0) {
+            const float2 h = __ldg(hq + (RL / 2) * (M / RL));
+            sny.x = fmaf(gs, h.x, sny.x);
+            sny.y = fmaf(gs, h.y, sny.y);
+            dny.x = fmaf(gd, h.x, dny.x);
+            dny.y = fmaf(gd, h.y, dny.y);
+          }
         }
+        // S a + D conj(b)
+        auto mixc = [](float2 S, float2 D, float2 za, float2 zb) {
+          return make_float2(S.x * za.x - S.y * za.y + D.x * zb.x + D.y * zb.y,
+                             S.x * za.y + S.y * za.x - D.x * zb.y + D.y * zb.x);
+        };
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int i = half * 8 + j;
-          const int k = pos_to_bin<M>(stage_elem<M, LAST>(t, i));
-          const float2 zp = sm[pad_idx((M - k) & (M - 1))];
-          const float2 zz = z[i];
-          z[i].x = sacc[j].x * zz.x - sacc[j].y * zz.y + dacc[j].x * zp.x + dacc[j].y * zp.y;
-          z[i].y = sacc[j].x * zz.y + sacc[j].y * zz.x - dacc[j].x * zp.y + dacc[j].y * zp.x;
+        for (int j = 0; j < NLOW; ++j) {
+          const int k = pos_to_bin<M>(stage_elem<M, LAST>(t, j));
+          const float2 zk = z[j];
+          if (k == 0) {
+            z[j] = mixc(sacc[j], dacc[j], zk, zk);
+          } else {
+            float2* mp = sm + pad_idx(M - k);
+            const float2 zm = *mp;
+            z[j] = mixc(sacc[j], dacc[j], zk, zm);
+            *mp = mixc(make_float2(sacc[j].x, -sacc[j].y), make_float2(dacc[j].x, -dacc[j].y), zm, zk);
+          }
         }
+        if (t == 0) {
+          float2* np = sm + pad_idx(M / 2);
+          const float2 zn = *np;
+          *np = mixc(sny, dny, zn, zn);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = NLOW; i < kE; ++i) z[i] = sm[pad_idx(pos_to_bin<M>(stage_elem<M, LAST>(t, i)))];
       }
       fft_inverse<M>(z, t, sm, a.tw512);
       const int lo = edge ? kSeg - 1 : 0;          // kept outputs [lo, lo + 249)
@@ -840,7 +948,7 @@ __global__ void __launch_bounds__(256, 2) k_fir_edge_corr(const FirArgs a) {
   }
 }
 
-template <int N>
+template <int N, bool STAGED>
 __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_circ(const FirArgs a) {
   using GEO = SGeo<N>;
   constexpr int T = GEO::T, G = GEO::G;
@@ -854,23 +962,27 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_
   const int64_t nitems = (npairs + G - 1) / G;
   constexpr int LAST = Plan<N>::ns - 1;
   SlabPipe<N> pipe;
-  pipe.init(smem_raw, a.x, a.P, nitems);
+  if constexpr (STAGED) pipe.init(smem_raw, a.x, a.P, nitems);
 
   for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int64_t pair = item * G + g;
     const int64_t p0 = pair * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
-    const float* slab = pipe.acquire(item);
     bool nz0, nz1, bad0 = false, bad1 = false;
     float2 z[kE];
-    load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
+    if constexpr (STAGED) {
+      const float* slab = pipe.acquire(item);
+      load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
+    } else {
+      load_pair_direct<N>(z, a.x, p0, t, act0, act1, nz0, nz1);
+    }
     fft_forward<N>(z, t, sm, a.tw);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
     __syncthreads();
     // he holds H / (2N): the N-point inverse needs H / N
-    mix_subspectrum<N, false>(z, sm, t, a, a.he, p0, act0, act1, bad0, bad1, 1.0f);
+    mix_paired<N>(z, sm, t, a, a.he, p0, act0, act1, bad0, bad1, 1.0f);
     // wrap-around corrections of this thread's outputs, in flight across the inverse transform
     const float2* cp = a.corr + (size_t)pair * 2 * kCorrStride;
     float2 cr[kE];
@@ -1462,12 +1574,17 @@ __global__ void __launch_bounds__(kStThreads, 1) k_rl_stream(const __grid_consta
   // a chunk that lies wholly above or below the image is all zeros: no copy, the ring rows are cleared
   auto live = [&](int j) { return gy0 + kCR * j < a.Hp && gy0 + kCR * (j + 1) > 0; };
 
+  // programmatic dependent launch: the next kernel of the iteration may be scheduled as soon as every CTA
+  // of this one is running, its prologue (barriers, taps) overlaps our tail; everything that touches the
+  // images comes after griddepcontrol.wait, which returns when the previous kernel has completed
+  asm volatile("griddepcontrol.launch_dependents;");
   if (tid == 0) {
     mbar_init(mbar0, 1);
     mbar_init(mbar0 + 8, 1);
   }
   for (int i = tid; i < a.WU + 8; i += kStThreads) wxs[i] = a.wx[i];
   for (int i = tid; i < a.KW + 8; i += kStThreads) wys[i] = a.wy[i];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   if (tid == 0) {
     for (int j = 0; j < 2 && j < n_chunks; ++j)
@@ -1480,6 +1597,24 @@ __global__ void __launch_bounds__(kStThreads, 1) k_rl_stream(const __grid_consta
   for (int j = 0; j < n_chunks; ++j) {
     const int buf = j & 1;
     const bool lv = live(j);
+    // rows that become complete with this chunk, and this thread's share of them in the row pass:
+    // thread = (strip column c, 16 output rows).  The epilogue operands are fetched now, so that their
+    // latency hides behind the column pass even when the PSF is small.
+    const int lo = max(0, j * kCR - a.WU), hi = min(rows_out, (j + 1) * kCR - a.WU);
+    const int c = tid & (kSW - 1), rg = tid >> 7;
+    const int i0 = lo + rg * 16;
+    const int gc = col0 + c;
+    const bool colok = gc >= 0 && gc < a.Wp;
+    const size_t o0 = (size_t)(seg_row0 + i0) * a.pitch + gc;
+    float ep[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      ep[q] = 0.f;
+      if (MODE != 0 && colok && i0 + q < hi) {
+        const size_t o = o0 + (size_t)q * a.pitch;
+        ep[q] = (MODE == 1) ? __ldg(a.d + o) : a.out[o];
+      }
+    }
     // ---- column pass: thread = (chunk row r, 16 output columns cg*16 ..) ----
     {
       const int r = tid & (kCR - 1), cg = tid >> 6;
@@ -1504,23 +1639,8 @@ __global__ void __launch_bounds__(kStThreads, 1) k_rl_stream(const __grid_consta
       mbar_expect_tx(mbar0 + 8 * buf, tile_bytes);
       tma_load_2d(smem_u32(tile0 + buf * tile_floats), &tmap, gx0, gy0 + kCR * (j + 2), mbar0 + 8 * buf);
     }
-    // ---- row pass: thread = (strip column c, 16 output rows) of the rows that became complete ----
-    const int lo = max(0, j * kCR - a.WU), hi = min(rows_out, (j + 1) * kCR - a.WU);
-    const int c = tid & (kSW - 1), rg = tid >> 7;
-    const int i0 = lo + rg * 16;
+    // ---- row pass ----
     if (i0 < hi) {
-      const int gc = col0 + c;
-      const bool colok = gc >= 0 && gc < a.Wp;
-      const size_t o0 = (size_t)(seg_row0 + i0) * a.pitch + gc;
-      float ep[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        ep[q] = 0.f;
-        if (MODE != 0 && colok && i0 + q < hi) {
-          const size_t o = o0 + (size_t)q * a.pitch;
-          ep[q] = (MODE == 1) ? __ldg(a.d + o) : a.out[o];
-        }
-      }
       float acc[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) acc[q] = 0.f;
@@ -1810,7 +1930,8 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
 }
 
 template <int M, typename K>
-static int launch_fir(thz_ctx* c, cudaStream_t s, K kernel, const FirArgs& a, size_t smem_override = 0) {
+static int launch_fir(thz_ctx* c, cudaStream_t s, K kernel, const FirArgs& a, size_t smem_override = 0,
+                      int carveout_pct = -1) {
   using GEO = DGeo<M>;
   const size_t smem = smem_override ? smem_override : GEO::smem_bytes;
   const void* key = (const void*)kernel;
@@ -1818,6 +1939,10 @@ static int launch_fir(thz_ctx* c, cudaStream_t s, K kernel, const FirArgs& a, si
   if (it == c->occ.end()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(smem)");
+    if (carveout_pct >= 0) {   // leave the rest of the unified L1 / shared memory to the table loads
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
+      if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(carveout)");
+    }
     int nb = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, GEO::NT, smem);
     if (e != cudaSuccess) return cuda_fail(c, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
@@ -1847,13 +1972,15 @@ template <int M> static int do_energy_total(thz_ctx* c, cudaStream_t s, const Fi
 }
 // split kernels use the N-point geometry (identical to DGeo<N>)
 template <int N> static int do_energy_split(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
-  return launch_fir<N>(c, s, k_fir_energy_split<N>, a, SGeo<N>::smem_bytes);
+  if (c->unstaged_fir) return launch_fir<N>(c, s, k_fir_energy_split<N, false>, a, SGeo<N>::base_bytes, 40);
+  return launch_fir<N>(c, s, k_fir_energy_split<N, true>, a, SGeo<N>::smem_bytes);
 }
 template <int N> static int do_apply_split(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
   return launch_fir<N>(c, s, k_fir_apply_split<N>, a, SGeo<N>::smem_bytes);
 }
 template <int N> static int do_apply_circ(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
-  return launch_fir<N>(c, s, k_fir_apply_circ<N>, a, SGeo<N>::smem_bytes);
+  if (c->unstaged_fir) return launch_fir<N>(c, s, k_fir_apply_circ<N, false>, a, SGeo<N>::base_bytes, 40);
+  return launch_fir<N>(c, s, k_fir_apply_circ<N, true>, a, SGeo<N>::smem_bytes);
 }
 
 #define THZ_DISPATCH_M(m, FN, ...)                 \
@@ -1882,6 +2009,35 @@ static int dispatch_apply_split(thz_ctx* c, cudaStream_t s, int n, const FirArgs
 }
 static int dispatch_apply_circ(thz_ctx* c, cudaStream_t s, int n, const FirArgs& a) {
   THZ_DISPATCH_M(n, do_apply_circ, c, s, a);
+}
+
+// event pair around one cube kernel while thz_deconvolution_dev collects its per-kernel breakdown; the pairs
+// are resolved after the final stream synchronisation, the launches themselves stay asynchronous
+struct KernelTimer {
+  thz_ctx* c;
+  cudaStream_t s;
+  int slot;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KernelTimer(thz_ctx* c_, cudaStream_t s_, int slot_) : c(c_), s(s_), slot(slot_) {
+    if (!c->time_kernels) return;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = nullptr; return; }
+    cudaEventRecord(e0, s);
+  }
+  void stop() {
+    if (!e0) return;
+    cudaEventRecord(e1, s);
+    c->kernel_events.push_back({slot, e0, e1});
+  }
+};
+
+static void resolve_kernel_events(thz_ctx* c) {
+  for (auto& ev : c->kernel_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.e0, ev.e1) == cudaSuccess) c->kernel_ms[ev.slot] += ms;
+    cudaEventDestroy(ev.e0);
+    cudaEventDestroy(ev.e1);
+  }
+  c->kernel_events.clear();
 }
 
 int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
@@ -1914,11 +2070,19 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
         FirArgs as = a;
         as.tw = tbn->d_tw;
         as.he = ft.d_he; as.ho = ft.d_ho; as.we = ft.d_we; as.wo = ft.d_wo; as.mod = ft.d_mod;
+        KernelTimer kt(c, s, 0);
         rc = dispatch_energy_split(c, s, n, as);
+        kt.stop();
       } else {
+        KernelTimer kt(c, s, 0);
         rc = dispatch_energy_total(c, s, ft.m, a);
+        kt.stop();
       }
-      if (rc == THZ_OK) rc = launch_fir<512>(c, s, k_fir_edges, a);
+      if (rc == THZ_OK) {
+        KernelTimer kt(c, s, 1);
+        rc = launch_fir<512>(c, s, k_fir_edges, a);
+        kt.stop();
+      }
     } else {
       rc = dispatch_energy(c, s, ft.m, a);   // short traces: B inverse transforms per pair
     }
@@ -1970,14 +2134,26 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
           ac.out = d_out + p_lo * n;
           ac.img = d_img ? d_img + p_lo : nullptr;
           ac.corr = (float2*)pc;
-          rc = launch_fir<512>(c, s, k_fir_edge_corr, ac);
-          if (rc == THZ_OK) rc = dispatch_apply_circ(c, s, n, ac);
+          {
+            KernelTimer kt(c, s, 2);
+            rc = launch_fir<512>(c, s, k_fir_edge_corr, ac);
+            kt.stop();
+          }
+          if (rc == THZ_OK) {
+            KernelTimer kt(c, s, 3);
+            rc = dispatch_apply_circ(c, s, n, ac);
+            kt.stop();
+          }
         }
       } else {
+        KernelTimer kt(c, s, 3);
         rc = dispatch_apply_split(c, s, n, a);
+        kt.stop();
       }
     } else {
+      KernelTimer kt(c, s, 3);
       rc = dispatch_apply(c, s, ft.m, a);
+      kt.stop();
     }
   }
   return rc;
@@ -2157,9 +2333,19 @@ static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUt
       if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl stream)");
       shave = cp.ssmem;
     }
-    k_rl_stream<MODE><<<cp.sgrid, kStThreads, cp.ssmem, s>>>(map, sa);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = cp.sgrid;
+    cfg.blockDim = dim3(kStThreads);
+    cfg.dynamicSmemBytes = cp.ssmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, k_rl_stream<MODE>, map, sa);
     c->launches++;
-    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_stream launch");
     return THZ_OK;
   }
@@ -2353,6 +2539,8 @@ int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, i
   float *d_energy = (float*)pe, *d_gain = (float*)pg;
   cudaEvent_t ev[4];
   for (auto& e : ev) cudaEventCreate(&e);
+  for (float& v : c->kernel_ms) v = 0.f;
+  c->time_kernels = true;
   cudaEventRecord(ev[0], c->stream);
   int rc = deconv_energies(c, c->stream, d_cube, P, n, bands, n_bands, d_energy);
   cudaEventRecord(ev[1], c->stream);
@@ -2370,7 +2558,9 @@ int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, i
   cudaEventRecord(ev[2], c->stream);
   if (rc == THZ_OK) rc = deconv_apply(c, c->stream, d_cube, d_gain, P, n, bands, n_bands, d_out, d_img);
   cudaEventRecord(ev[3], c->stream);
+  c->time_kernels = false;
   cudaStreamSynchronize(c->stream);
+  resolve_kernel_events(c);
   for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&c->stage_ms[i], ev[i], ev[i + 1]);
   c->stage_ms[3] = (float)done_iter;
   for (auto& e : ev) cudaEventDestroy(e);
@@ -2381,6 +2571,12 @@ int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, i
 int thz_deconv_stage_ms(const thz_ctx* c, float* ms4) {
   if (!c || !ms4) return THZ_EINVAL;
   for (int i = 0; i < 4; ++i) ms4[i] = c->stage_ms[i];
+  return THZ_OK;
+}
+
+int thz_deconv_kernel_ms(const thz_ctx* c, float* ms4) {
+  if (!c || !ms4) return THZ_EINVAL;
+  for (int i = 0; i < 4; ++i) ms4[i] = c->kernel_ms[i];
   return THZ_OK;
 }
 

@@ -51,7 +51,12 @@ struct thz_ctx {
   uint64_t fir_key = 0;                          // cache key of the uploaded FIR spectra (slot WS_FIR)
   int fir_m = 0;
   float stage_ms[4] = {0, 0, 0, 0};              // last thz_deconvolution_dev: energies, RL, apply, RL iterations
+  float kernel_ms[4] = {0, 0, 0, 0};             // same call, per kernel: energy spectra, energy edges, apply edges, apply main
+  bool time_kernels = false;                     // set while thz_deconvolution_dev runs: event pairs around the cube kernels
+  struct KernelEvent { int slot; cudaEvent_t e0, e1; };
+  std::vector<KernelEvent> kernel_events;        // resolved after the call's final synchronisation
   bool force_split_apply = false;                // THZ_APPLY_FORM=split: zero-padded split form for pass C (A/B checks)
+  bool unstaged_fir = true;                      // FIR passes read the cube directly so that L1 keeps the tables (THZ_FIR_STAGING=on: bulk-copy staging)
   float* d_scratch = nullptr;                    // reductions
   size_t scratch_bytes = 0;
 };
