@@ -224,12 +224,33 @@ def run_reference(a):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def bind_to_gpu_numa(index):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU, before any pinned host buffer is
+    allocated: first-touch then places the staging memory on the GPU's own NUMA node, which matters once
+    several ranks stream 50 GB/s each through the host (the e2e leg at N > 1)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_ours(a):
     import torch
     m = importlib.import_module(PKG)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa(local) if world > 1 else 0
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -304,6 +325,8 @@ def run_ours(a):
 
     ops = GpuOps() if (bands is not None and world > 1) else None
 
+    phase_s = {}
+
     def step():
         ctx.trace_fused_dev(d_in.ptr, d_out.ptr, d_img.ptr, P)
         if bands is None:
@@ -312,7 +335,7 @@ def run_ours(a):
             ctx._check(m.lib.thz_deconvolution_dev(ctx.handle, d_out.ptr, rows, H, N, bands, B, d_out.ptr,
                                                    d_img.ptr, None, None, None))
         else:
-            m.sharding.sharded_deconvolution(ops, d_out.ptr, W, H, B, dist, world, rank)
+            m.sharding.sharded_deconvolution(ops, d_out.ptr, W, H, B, dist, world, rank, timings=phase_s)
 
     launches0 = None
     for _ in range(a.warmup):
@@ -326,12 +349,14 @@ def run_ours(a):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
     barrier()
     ev[0].record(stream)
+    phase_s.clear()
     for i in range(a.steps):
         step()
         ev[i + 1].record(stream)
     ctx.sync()
     barrier()
     launches = ctx.launches - launches0
+    phases_ms = {k: 1e3 * v / a.steps for k, v in phase_s.items()} if world > 1 else None
     per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
     total_ms = ev[0].elapsed_time(ev[a.steps])
     clocks = sampler.stop() if rank == 0 else None
@@ -413,11 +438,13 @@ def run_ours(a):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "partition": f"row slabs over x, {world} rank(s)",
+                       "host_affinity": (f"rank pinned to the {numa_cpus} cores local to its GPU (NVML)"
+                                         if numa_cpus else "default"),
                        "l2": "inputs larger than L2 (cube >> 126 MB), no flush needed",
                        "stages": ["trace pass (fused)"] + (["deconvolution: band energies, Richardson-Lucy "
                                                            f"({n_rl_iter} iterations over {len(bands)} bands), "
                                                            "gain application"] if bands is not None else [])},
-            "stage_breakdown": stages, "chain_roofline": chain,
+            "stage_breakdown": stages, "rank0_phases_ms": phases_ms, "chain_roofline": chain,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))

@@ -60,6 +60,12 @@ struct FirArgs {
   const float* wo;       // [B][N/2] |H_b[2j+1]|^2 / M
   const float2* mod;     // [N] exp(-2 pi i n / M): modulation that selects the odd bins
   float2* corr;          // [pairs][2][256] wrap-around corrections of the circular form (pass C)
+  // band-interleaved copies of the lower-half tables (one 128-bit load serves four bands), Bp = B rounded up to 4
+  int Bp;
+  const float* we4;      // [Bp/4][N/2][4]
+  const float* wo4;      // [Bp/4][N/2][4]
+  const float* he4;      // [Bp/4][N/2][4]  H_b[2j] / M, lower-half registers
+  const float* hny4;     // [Bp]       H_b[N] / M (Nyquist of the N-point spectrum)
 };
 
 template <int M>
@@ -483,23 +489,25 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
     for (int b0 = 0; b0 < a.B; b0 += 4) {
       float e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
-        const int b = b0 + bb;
-        if (b < a.B) {
-          const float* we = a.we + (size_t)b * (N / 2);
-          const float* wo = a.wo + (size_t)b * (N / 2);
+      for (int j = 0; j < NLOW; ++j) {
+        const int u = j % UL, m = j / UL;
+        const size_t o = ((size_t)(b0 >> 2) * (N / 2) + (m * (N / RL) + t + u * T)) * 4;
+        const float4 w_e = __ldg(reinterpret_cast<const float4*>(a.we4 + o));
+        const float4 w_o = __ldg(reinterpret_cast<const float4*>(a.wo4 + o));
+        const float we_[4] = {w_e.x, w_e.y, w_e.z, w_e.w}, wo_[4] = {w_o.x, w_o.y, w_o.z, w_o.w};
 #pragma unroll
-          for (int j = 0; j < NLOW; ++j) {
-            const int u = j % UL, m = j / UL;
-            const float w_e = __ldg(we + m * (N / RL) + t + u * T);
-            const float w_o = __ldg(wo + m * (N / RL) + t + u * T);
-            e1[bb] = fmaf(w_e, q1e[j], e1[bb]);
-            e2[bb] = fmaf(w_e, q2e[j], e2[bb]);
-            e1[bb] = fmaf(w_o, q1o[j], e1[bb]);
-            e2[bb] = fmaf(w_o, q2o[j], e2[bb]);
-          }
-          if (t == 0) {
-            const float w = __ldg(a.wnyq + b);
+        for (int bb = 0; bb < 4; ++bb) {
+          e1[bb] = fmaf(we_[bb], q1e[j], e1[bb]);
+          e2[bb] = fmaf(we_[bb], q2e[j], e2[bb]);
+          e1[bb] = fmaf(wo_[bb], q1o[j], e1[bb]);
+          e2[bb] = fmaf(wo_[bb], q2o[j], e2[bb]);
+        }
+      }
+      if (t == 0) {
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          if (b0 + bb < a.B) {
+            const float w = __ldg(a.wnyq + b0 + bb);
             e1[bb] = fmaf(w, ny1, e1[bb]);
             e2[bb] = fmaf(w, ny2, e2[bb]);
           }
@@ -777,24 +785,39 @@ __device__ __forceinline__ void mix_paired(float2 (&z)[kE], float2* sm, int t, c
 #pragma unroll
   for (int j = 0; j < NLOW; ++j) sacc[j] = dacc[j] = 0.f;
   float sny = 0.f, dny = 0.f;
-  for (int b = 0; b < a.B; ++b) {
-    float g0 = act0 ? __ldg(a.gain + (size_t)b * a.bstride + p0) : 0.f;
-    float g1 = act1 ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
-    if (!(fabsf(g0) <= 3.0e38f)) { bad0 = true; g0 = 0.f; }
-    if (!(fabsf(g1) <= 3.0e38f)) { bad1 = true; g1 = 0.f; }
-    const float gs = gmul * (g0 + g1), gd = gmul * (g0 - g1);
-    const float* hq = htab + (size_t)b * N;
+  (void)htab;
+  for (int b0 = 0; b0 < a.B; b0 += 4) {
+    float gs[4], gd[4];
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const int b = b0 + bb;
+      float g0 = (act0 && b < a.B) ? __ldg(a.gain + (size_t)b * a.bstride + p0) : 0.f;
+      float g1 = (act1 && b < a.B) ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
+      if (!(fabsf(g0) <= 3.0e38f)) { bad0 = true; g0 = 0.f; }
+      if (!(fabsf(g1) <= 3.0e38f)) { bad1 = true; g1 = 0.f; }
+      gs[bb] = gmul * (g0 + g1);
+      gd[bb] = gmul * (g0 - g1);
+    }
 #pragma unroll
     for (int j = 0; j < NLOW; ++j) {
       const int u = j % UL, m = j / UL;
-      const float h = __ldg(hq + m * (N / RL) + t + u * T);
-      sacc[j] = fmaf(gs, h, sacc[j]);
-      dacc[j] = fmaf(gd, h, dacc[j]);
+      const float4 h4 = __ldg(reinterpret_cast<const float4*>(
+          a.he4 + ((size_t)(b0 >> 2) * (N / 2) + (m * (N / RL) + t + u * T)) * 4));
+      const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        sacc[j] = fmaf(gs[bb], h[bb], sacc[j]);
+        dacc[j] = fmaf(gd[bb], h[bb], dacc[j]);
+      }
     }
     if (t == 0) {
-      const float h = __ldg(hq + (RL / 2) * (N / RL));
-      sny = fmaf(gs, h, sny);
-      dny = fmaf(gd, h, dny);
+      const float4 h4 = __ldg(reinterpret_cast<const float4*>(a.hny4 + b0));
+      const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        sny = fmaf(gs[bb], h[bb], sny);
+        dny = fmaf(gd[bb], h[bb], dny);
+      }
     }
   }
 #pragma unroll
@@ -1455,15 +1478,16 @@ __global__ void __launch_bounds__(kRlThreads, 1) k_rl_conv_persistent(const __gr
 // true support minus one rounded up to a multiple of 8, so that the window advances in whole
 // 8-element blocks and the last tap is a single trailing step that needs no new data.
 // ------------------------------------------------------------------------------------
-constexpr int kSW = 128;          // output columns per strip
 constexpr int kCR = 64;           // input rows per chunk
-constexpr int kStThreads = 512;   // = kCR * kSW / 16: one 16-output item per thread in both passes
+// SW = output columns per strip (128: one 512-thread CTA per SM; 64: 256 threads, two CTAs per SM when the
+// buffers fit twice, so that one CTA computes while the other sits at its barrier); SW * kCR / 16 threads:
+// one 16-output item per thread in both passes
 
 struct StreamArgs {
   int Hp, Wp, pitch;
   int WU, KW;           // warm-up rows / columns (multiples of 8)
   int gy_off, gx_off;   // box origin = (segment row 0 - gy_off, strip column 0 - gx_off)
-  int bc;               // box columns (4 * odd, >= kSW + KW)
+  int bc;               // box columns (4 * odd, >= SW + KW)
   int Rg, RS;           // ring rows (multiple of 8, >= 2 kCR + WU) and ring stride in floats (4 * odd)
   int seg_rows;         // output rows per segment (kCR * chunks - WU)
   int col_shift;        // keeps the box start 16-byte aligned
@@ -1552,9 +1576,10 @@ struct RingLoader {     // consecutive ring rows of one column (transposed ring:
   }
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(kStThreads, 1) k_rl_stream(const __grid_constant__ CUtensorMap tmap,
-                                                             const StreamArgs a) {
+template <int MODE, int SW>
+__global__ void __launch_bounds__(SW * 4, (SW == 64) ? 2 : 1) k_rl_stream(const __grid_constant__ CUtensorMap tmap,
+                                                                         const StreamArgs a) {
+  constexpr int kSW = SW, kStThreads = SW * 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const uint32_t mbar0 = smem_u32(base);                       // two barriers, 8 bytes apart
@@ -1601,7 +1626,7 @@ __global__ void __launch_bounds__(kStThreads, 1) k_rl_stream(const __grid_consta
     // thread = (strip column c, 16 output rows).  The epilogue operands are fetched now, so that their
     // latency hides behind the column pass even when the PSF is small.
     const int lo = max(0, j * kCR - a.WU), hi = min(rows_out, (j + 1) * kCR - a.WU);
-    const int c = tid & (kSW - 1), rg = tid >> 7;
+    const int c = tid & (kSW - 1), rg = tid / kSW;
     const int i0 = lo + rg * 16;
     const int gc = col0 + c;
     const bool colok = gc >= 0 && gc < a.Wp;
@@ -1771,6 +1796,8 @@ struct FirTables {
   bool split = false;
   float *d_he = nullptr, *d_ho = nullptr, *d_we = nullptr, *d_wo = nullptr;
   float2* d_mod = nullptr;
+  int Bp = 0;
+  float *d_we4 = nullptr, *d_wo4 = nullptr, *d_he4 = nullptr, *d_hny4 = nullptr;   // band-interleaved
 };
 
 // spectra / 512 of the first (edge 0) and last (edge 1) 249 taps at 512 points, register order of Plan<512>
@@ -1835,7 +1862,10 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
   int nsh, rh[4];
   // the split kernels stage 64 KB of input + the exchange buffer: n <= 4096 keeps two CTAs per SM
   const bool split = (nh == n) && nh >= 256 && nh <= 4096 && plan_of_m(nh, nsh, rh);
-  const size_t n_split = split ? ((size_t)2 * B * nh + (size_t)2 * B * (nh / 2) + (size_t)2 * nh) : 0;
+  const int Bp = (B + 3) & ~3;
+  const size_t n_split_base = split ? ((size_t)2 * B * nh + (size_t)2 * B * (nh / 2) + (size_t)2 * nh) : 0;
+  const size_t n_il = split ? ((size_t)3 * (nh / 2) * Bp + Bp) : 0;   // we4, wo4, he4, hny4
+  const size_t n_split = n_split_base + n_il;
   int rc = ws_get(c, WS_FIR, (n_hq + n_wq + n_ny + n_edge + n_split) * sizeof(float), &dp);
   if (rc != THZ_OK) return rc;
   ft.d_hq = (float*)dp;
@@ -1849,6 +1879,11 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
     ft.d_we = ft.d_ho + (size_t)B * nh;
     ft.d_wo = ft.d_we + (size_t)B * (nh / 2);
     ft.d_mod = reinterpret_cast<float2*>(ft.d_wo + (size_t)B * (nh / 2));
+    ft.Bp = Bp;
+    ft.d_we4 = ft.d_he + n_split_base;
+    ft.d_wo4 = ft.d_we4 + (size_t)(nh / 2) * Bp;
+    ft.d_he4 = ft.d_wo4 + (size_t)(nh / 2) * Bp;
+    ft.d_hny4 = ft.d_he4 + (size_t)(nh / 2) * Bp;
   }
   ft.m = m;
   ft.B = B;
@@ -1911,6 +1946,18 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
             wo[o] = ho[o] * ho[o] * (float)m;
           }
         }
+      float* il = all.data() + n_hq + n_wq + n_ny + n_edge + n_split_base;
+      float* we4 = il;
+      float* wo4 = we4 + (size_t)(nh / 2) * Bp;
+      float* he4 = wo4 + (size_t)(nh / 2) * Bp;
+      float* hny4 = he4 + (size_t)(nh / 2) * Bp;
+      for (int o = 0; o < nh / 2; ++o) {   // [band group of 4][register-order index][band within the group]
+        const size_t q = ((size_t)(b >> 2) * (nh / 2) + o) * 4 + (b & 3);
+        we4[q] = we[o];
+        wo4[q] = wo[o];
+        he4[q] = he[o];
+      }
+      hny4[b] = he[(size_t)(RLh / 2) * (nh / RLh)];
     }
   }
   if (split) {
@@ -2070,6 +2117,7 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
         FirArgs as = a;
         as.tw = tbn->d_tw;
         as.he = ft.d_he; as.ho = ft.d_ho; as.we = ft.d_we; as.wo = ft.d_wo; as.mod = ft.d_mod;
+        as.Bp = ft.Bp; as.we4 = ft.d_we4; as.wo4 = ft.d_wo4;
         KernelTimer kt(c, s, 0);
         rc = dispatch_energy_split(c, s, n, as);
         kt.stop();
@@ -2113,6 +2161,7 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
       if (rc != THZ_OK) return rc;
       a.tw = tbn->d_tw;
       a.he = ft.d_he; a.ho = ft.d_ho; a.mod = ft.d_mod;
+      a.Bp = ft.Bp; a.he4 = ft.d_he4; a.hny4 = ft.d_hny4;
       if (n >= 512 && !c->force_split_apply) {
         // circular form: edge corrections of a chunk of pairs, then the one-transform-pair main pass
         const FftTables* tb512 = nullptr;
@@ -2201,6 +2250,7 @@ struct ConvPlan {
   int wstride = 0;        // floats between the two orientations
   // streaming form (k_rl_stream): used when the strip buffers fit in shared memory
   bool streaming = false;
+  int sw = 128;           // strip width of the streaming form
   StreamArgs sa{};
   size_t ssmem = 0;
   dim3 sgrid;
@@ -2264,20 +2314,29 @@ static int make_conv_plan(thz_ctx* c, cudaStream_t s, int Hp, int Wp, int pitch,
     const int padx = sa.WU - (kx - 1), pady = sa.KW - (ky - 1);
     sa.gy_off = kx / 2 + padx;
     sa.gx_off = ky / 2 + pady;
-    int sbc = round_up(kSW + sa.KW, 4);
-    if (((sbc / 4) & 1) == 0) sbc += 4;
-    sa.bc = sbc;
     sa.Rg = 2 * kCR + sa.WU;
     sa.RS = sa.Rg + 4;
     if (((sa.RS / 4) & 1) == 0) sa.RS += 4;
     sa.col_shift = (sa.gx_off % 4 == 0) ? 0 : (sa.gx_off % 4) - 4;
     sa.eps = a.eps;
-    cp.ssmem = (size_t)(2 * kCR * sa.bc + kSW * sa.RS + sa.WU + 8 + sa.KW + 8) * sizeof(float) + 256;
+    auto box_cols = [&](int sw) {
+      int v = round_up(sw + sa.KW, 4);
+      if (((v / 4) & 1) == 0) v += 4;
+      return v;
+    };
+    auto smem_of = [&](int sw) {
+      return (size_t)(2 * kCR * box_cols(sw) + sw * sa.RS + sa.WU + 8 + sa.KW + 8) * sizeof(float) + 256;
+    };
+    // two 64-column CTAs per SM when both fit (each CTA also pays 1 KB of driver-reserved shared memory)
+    cp.sw = (2 * (smem_of(64) + 1024) <= 228 * 1024) ? 64 : 128;
+    sa.bc = box_cols(cp.sw);
+    cp.ssmem = smem_of(cp.sw);
     cp.streaming = cp.ssmem <= 227 * 1024 && sa.bc <= 256;
     if (cp.streaming) {
-      // segments: as many per strip as fill the SMs once, each a whole number of chunks
-      const int strips = (Wp - sa.col_shift + kSW - 1) / kSW;
-      int segs = std::max(1, c->sm_count / strips);
+      // segments: as many per strip as fill the resident CTA slots once, each a whole number of chunks
+      const int strips = (Wp - sa.col_shift + cp.sw - 1) / cp.sw;
+      const int slots = c->sm_count * (cp.sw == 64 ? 2 : 1);
+      int segs = std::max(1, slots / strips);
       segs = std::min(segs, (Hp + kCR - 1) / kCR);
       const int per_seg = (Hp + segs - 1) / segs;
       const int chunks = (per_seg + sa.WU + kCR - 1) / kCR;
@@ -2326,24 +2385,27 @@ static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUt
     sa.wy = sa.wx + sa.WU + 8;
     sa.d = d;
     sa.out = out;
-    const void* skey = (const void*)k_rl_stream<MODE>;
-    size_t& shave = c->smem_set[skey];
-    if (shave < cp.ssmem) {
-      e = cudaFuncSetAttribute(skey, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.ssmem);
-      if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl stream)");
-      shave = cp.ssmem;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = cp.sgrid;
-    cfg.blockDim = dim3(kStThreads);
-    cfg.dynamicSmemBytes = cp.ssmem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, k_rl_stream<MODE>, map, sa);
+    auto launch = [&](auto kernel, int threads) -> cudaError_t {
+      const void* skey = (const void*)kernel;
+      size_t& shave = c->smem_set[skey];
+      if (shave < cp.ssmem) {
+        cudaError_t e2 = cudaFuncSetAttribute(skey, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.ssmem);
+        if (e2 != cudaSuccess) return e2;
+        shave = cp.ssmem;
+      }
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = cp.sgrid;
+      cfg.blockDim = dim3(threads);
+      cfg.dynamicSmemBytes = cp.ssmem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, kernel, map, sa);
+    };
+    e = (cp.sw == 64) ? launch(k_rl_stream<MODE, 64>, 256) : launch(k_rl_stream<MODE, 128>, 512);
     c->launches++;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_stream launch");

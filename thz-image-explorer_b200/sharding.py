@@ -45,21 +45,40 @@ def gather_band_images(e_slab: torch.Tensor, width: int, height: int, dist, worl
     return full
 
 
-def sharded_deconvolution(ops, slab, width: int, height: int, n_bands: int, dist, world: int, rank: int):
+def sharded_deconvolution(ops, slab, width: int, height: int, n_bands: int, dist, world: int, rank: int,
+                          timings: dict | None = None):
     """Deconvolution of this rank's slab.
 
     ops.energies(slab)            -> tensor [B][rows_r * H]
     ops.rl_gain(band, image_WxH)  -> tensor [W * H]  (gain image of one band)
     ops.apply(slab, gains_slab)   -> whatever the backend returns for the filtered slab
+
+    `timings`, when given, receives the wall-clock seconds of the phases of this rank (the ops synchronise).
     """
+    import time
+
+    def lap(name, t0):
+        if timings is not None:
+            if e_slab.is_cuda:
+                torch.cuda.synchronize()
+            timings[name] = timings.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
+    t = time.perf_counter()
     e_slab = ops.energies(slab)
+    t = lap("energies", t)
     e_full = gather_band_images(e_slab, width, height, dist, world)
+    t = lap("gather_energies", t)
     g_full = torch.zeros_like(e_full)
     for b in range(n_bands):
         if band_owner(b, world) == rank:
             g_full[b] = ops.rl_gain(b, e_full[b].reshape(width, height)).reshape(-1)
+    t = lap("richardson_lucy_own_bands", t)
     if world > 1:
         dist.all_reduce(g_full)
+    t = lap("reduce_gains_incl_wait", t)
     x0, x1 = slab_bounds(width, world, rank)
     g_slab = g_full[:, x0 * height: x1 * height].contiguous()
-    return ops.apply(slab, g_slab)
+    out = ops.apply(slab, g_slab)
+    lap("gain_application", t)
+    return out
