@@ -326,6 +326,8 @@ def run_ours(a):
     ops = GpuOps() if (bands is not None and world > 1) else None
 
     phase_s = {}
+    # measured per-kernel cost is ~16 us fixed + ~0.16 us per tap of the two 1-D passes (2048 x 2048 image)
+    band_costs = [b.n_iter * (100 + b.kx + b.ky) for b in bands] if bands is not None else None
 
     def step():
         ctx.trace_fused_dev(d_in.ptr, d_out.ptr, d_img.ptr, P)
@@ -335,7 +337,8 @@ def run_ours(a):
             ctx._check(m.lib.thz_deconvolution_dev(ctx.handle, d_out.ptr, rows, H, N, bands, B, d_out.ptr,
                                                    d_img.ptr, None, None, None))
         else:
-            m.sharding.sharded_deconvolution(ops, d_out.ptr, W, H, B, dist, world, rank, timings=phase_s)
+            m.sharding.sharded_deconvolution(ops, d_out.ptr, W, H, B, dist, world, rank, timings=phase_s,
+                                             band_costs=band_costs)
 
     launches0 = None
     for _ in range(a.warmup):

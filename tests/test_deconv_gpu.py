@@ -52,6 +52,27 @@ def test_conv2d_both_orientations(ctx, shape, kx, ky):
         assert rel_err(orc.fft_convolve2d(img, psf), conv.astype(F32)) < 1e-4
 
 
+@pytest.mark.parametrize("shape,kx,ky", [((700, 300), 31, 29),     # several segments per strip, 64-column strips
+                                         ((90, 1100), 9, 65),      # many strips, one chunk of rows
+                                         ((513, 129), 5, 3),       # ragged last strip / last segment
+                                         ((300, 260), 95, 65),     # buffers fit once: 128-column strips
+                                         ((200, 200), 127, 121)])  # too large for the strip buffers: tile kernel
+def test_conv2d_strip_geometry(ctx, shape, kx, ky):
+    """The streaming strip kernel (k_rl_stream) over image / PSF shapes that exercise every branch of its
+    plan: strip width 64 or 128, warm-up rows, chunks that lie wholly below the image, the fallback."""
+    from scipy.signal import correlate2d
+    rng = np.random.default_rng(kx * 1000 + ky)
+    img = rng.uniform(0.1, 1.0, shape).astype(F32)
+    px, py = _gauss(kx, 0.6, max(kx / 4, 0.8)), _gauss(ky, -0.9, max(ky / 4, 0.8))
+    # separable reference in f64: rows then columns, zero boundary, 'same' (deconvolution.rs:476-530)
+    tmp = correlate2d(img.astype(np.float64), px.astype(np.float64)[:, None], mode="same")
+    corr = correlate2d(tmp, py.astype(np.float64)[None, :], mode="same")
+    tmp = correlate2d(img.astype(np.float64), px[::-1].astype(np.float64)[:, None], mode="same")
+    conv = correlate2d(tmp, py[::-1].astype(np.float64)[None, :], mode="same")
+    assert rel_err(ctx.conv2d(img, px, py, direct=True), corr) < 5e-6
+    assert rel_err(ctx.conv2d(img, px, py, direct=False), conv) < 5e-6
+
+
 @pytest.mark.parametrize("band_idx,n_iter", [(0, 30), (1, 60), (2, 127), (4, 13)])
 def test_richardson_lucy_matches_oracle(ctx, psfs, band_idx, n_iter):
     """richardson_lucy + clamp + gain against the oracle, which takes the same convolve2d branch the
@@ -222,3 +243,38 @@ def test_gain_application_matches_oracle(ctx, psfs, n, w, h):
     for sl in (slice(0, 249), slice(n - 249, n)):
         assert rel_err(out[:, :, sl], ref[:, :, sl]) <= 5e-6
     assert rel_err(img, np.sum(ref * ref, axis=2)) <= 1e-5
+
+
+def test_gain_application_forms_agree(psfs, monkeypatch):
+    """The circular form of pass C (default), the zero-padded split form (THZ_APPLY_FORM=split) and the
+    bulk-copy-staged variants (THZ_FIR_STAGING=on) are three routes to the same linear convolution."""
+    psf, _ = psfs
+    w, h, n = 6, 5, 2048
+    cube = synthetic_cube(w, h, n, seed=77, noise=0.05)
+    rng = np.random.default_rng(5)
+    cube[:, :, :60] += rng.standard_normal((w, h, 60)).astype(F32)
+    cube[:, :, -60:] += rng.standard_normal((w, h, 60)).astype(F32)
+    bands, _ = pkg().host.Deconvolution(n_filters=8).plan(time_axis(n), (64, 64), 0.5, 0.5, psf)
+    P = w * h
+    gains = (0.25 + 2.0 * rng.random((len(bands), P))).astype(F32)
+    outs, energies = [], []
+    for env in ({}, {"THZ_APPLY_FORM": "split"}, {"THZ_FIR_STAGING": "on"}):
+        for k in ("THZ_APPLY_FORM", "THZ_FIR_STAGING"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c = pkg().Context(0)
+        try:
+            d_cube, d_g, d_out = c.to_device(cube), c.to_device(gains), c.alloc(cube.nbytes)
+            d_img, d_e = c.alloc(P * 4), c.alloc(len(bands) * P * 4)
+            c.deconv_energies_dev(d_cube.ptr, P, n, bands, d_e.ptr)
+            c.deconv_apply_dev(d_cube.ptr, d_g.ptr, P, n, bands, d_out.ptr, d_img.ptr)
+            outs.append((d_out.download((w, h, n)), d_img.download((w, h))))
+            energies.append(d_e.download((len(bands), P)))
+        finally:
+            c.close()
+    for out, img in outs[1:]:
+        assert rel_err(out, outs[0][0]) <= 2e-6
+        assert rel_err(img, outs[0][1]) <= 1e-5
+    for e in energies[1:]:
+        assert rel_err(e, energies[0]) <= 1e-5

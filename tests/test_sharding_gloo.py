@@ -59,10 +59,23 @@ def _worker(rank, world, port, q):
         sh = pkg().sharding
         cube, t, opsf, bands = _setup()
         x0, x1 = sh.slab_bounds(W, world, rank)
-        out = sh.sharded_deconvolution(OracleOps(bands), cube[x0:x1], W, H, NB, dist, world, rank)
+        costs = [b.n_iter * (100 + b.psf.shape[0] + b.psf.shape[1]) for b in bands]
+        out = sh.sharded_deconvolution(OracleOps(bands), cube[x0:x1], W, H, NB, dist, world, rank, band_costs=costs)
         q.put((rank, x0, x1, out))
     finally:
         dist.destroy_process_group()
+
+
+def test_band_assignment_balances_iteration_counts():
+    sh = pkg().sharding
+    costs = [423 * 204, 251 * 160, 127 * 132, 46 * 118, 13 * 114, 4 * 114, 3 * 114, 1 * 114]   # C5 plan
+    for world in (1, 2, 3, 4, 8):
+        own = sh.assign_bands(costs, world)
+        assert sorted(set(own)) == list(range(min(world, len(costs)))) and len(own) == len(costs)
+        load = [sum(c for c, o in zip(costs, own) if o == r) for r in range(world)]
+        assert max(load) == costs[0] if world > 1 else True     # band 0 alone bounds the makespan
+    assert sh.assign_bands(costs, 2) == [0, 1, 1, 1, 1, 1, 1, 1]
+    assert sh.assign_bands([], 4) == []
 
 
 def test_slab_bounds_cover_the_image():

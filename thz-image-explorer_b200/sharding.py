@@ -26,6 +26,20 @@ def band_owner(band: int, world: int) -> int:
     return band % world
 
 
+def assign_bands(costs, world: int):
+    """Owner rank of every band: longest-processing-time-first on the given per-band costs (deterministic, so
+    every rank computes the same table).  Richardson-Lucy iteration counts fall steeply with frequency
+    (423, 251, 127, ... at C5), so round-robin leaves the rank of band 0 with the small bands as well."""
+    order = sorted(range(len(costs)), key=lambda b: (-float(costs[b]), b))
+    load = [0.0] * world
+    owner = [0] * len(costs)
+    for b in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[b] = r
+        load[r] += float(costs[b])
+    return owner
+
+
 def gather_band_images(e_slab: torch.Tensor, width: int, height: int, dist, world: int) -> torch.Tensor:
     """e_slab [B][rows_r * H] on every rank -> [B][W * H] on every rank (uneven slabs allowed)."""
     B = e_slab.shape[0]
@@ -46,7 +60,7 @@ def gather_band_images(e_slab: torch.Tensor, width: int, height: int, dist, worl
 
 
 def sharded_deconvolution(ops, slab, width: int, height: int, n_bands: int, dist, world: int, rank: int,
-                          timings: dict | None = None):
+                          timings: dict | None = None, band_costs=None):
     """Deconvolution of this rank's slab.
 
     ops.energies(slab)            -> tensor [B][rows_r * H]
@@ -54,6 +68,8 @@ def sharded_deconvolution(ops, slab, width: int, height: int, n_bands: int, dist
     ops.apply(slab, gains_slab)   -> whatever the backend returns for the filtered slab
 
     `timings`, when given, receives the wall-clock seconds of the phases of this rank (the ops synchronise).
+    `band_costs` (one number per band, e.g. iterations x taps) balances the bands over the ranks; without it
+    band b runs on rank b % world.
     """
     import time
 
@@ -70,8 +86,9 @@ def sharded_deconvolution(ops, slab, width: int, height: int, n_bands: int, dist
     e_full = gather_band_images(e_slab, width, height, dist, world)
     t = lap("gather_energies", t)
     g_full = torch.zeros_like(e_full)
+    owners = assign_bands(band_costs, world) if band_costs is not None else [band_owner(b, world) for b in range(n_bands)]
     for b in range(n_bands):
-        if band_owner(b, world) == rank:
+        if owners[b] == rank:
             g_full[b] = ops.rl_gain(b, e_full[b].reshape(width, height)).reshape(-1)
     t = lap("richardson_lucy_own_bands", t)
     if world > 1:
