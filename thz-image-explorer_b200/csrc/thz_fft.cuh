@@ -171,8 +171,21 @@ __device__ __forceinline__ void load_tw(float2 (&w)[kE], int t, const float2* __
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = (t + u * T) & (S - 1);
+#ifdef THZ_TW_POWERS
+      // only the rows q = 1, 2, 4, 8 are fetched (a quarter of the table stays hot in L1), the other powers
+      // are products of two fetched ones
+#pragma unroll
+      for (int q = 1; q < R; q <<= 1) w[u + U * q] = __ldg(&tw[(q - 1) * S + j]);
+#pragma unroll
+      for (int q = 3; q < R; ++q)
+        if ((q & (q - 1)) != 0) {
+          const int hi = (q >= 8) ? 8 : (q >= 4) ? 4 : 2;
+          w[u + U * q] = cmul(w[u + U * hi], w[u + U * (q - hi)]);
+        }
+#else
 #pragma unroll
       for (int q = 1; q < R; ++q) w[u + U * q] = __ldg(&tw[(q - 1) * S + j]);
+#endif
     }
   }
 }

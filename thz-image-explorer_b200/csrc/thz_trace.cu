@@ -177,7 +177,7 @@ __device__ __forceinline__ void store_pair(float2 (&v)[kE], const TraceArgs& a, 
 // ------------------------------------------------------------------------------------
 // fused chain: one read and one write of the cube
 // ------------------------------------------------------------------------------------
-template <int N>
+template <int N, bool STAGED>
 __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(const TraceArgs a) {
   using GEO = Geo<N>;
   constexpr int T = GEO::T, G = GEO::G;
@@ -198,14 +198,15 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(
   float* slab[2] = {reinterpret_cast<float*>(smem_raw + GEO::stage_off),
                     reinterpret_cast<float*>(smem_raw + GEO::stage_off) + GEO::kSlabFloats};
   BulkStager stager;
-  stager.init(reinterpret_cast<uint64_t*>(smem_raw + GEO::stage_off + 2 * (size_t)GEO::kSlabFloats * sizeof(float)));
+  if constexpr (STAGED)
+    stager.init(reinterpret_cast<uint64_t*>(smem_raw + GEO::stage_off + 2 * (size_t)GEO::kSlabFloats * sizeof(float)));
   auto slab_bytes = [&](int64_t it) -> uint32_t {
     const int64_t first = it * G * 2;
     int64_t cnt = a.P - first;
     if (cnt > 2 * G) cnt = 2 * G;
     return (uint32_t)(cnt * N * sizeof(float));
   };
-  if (threadIdx.x == 0 && (int64_t)blockIdx.x < nitems)
+  if (STAGED && threadIdx.x == 0 && (int64_t)blockIdx.x < nitems)
     stager.issue(0, slab[0], a.in + (int64_t)blockIdx.x * G * 2 * N, slab_bytes(blockIdx.x));
   uint32_t it_count = 0;
 
@@ -217,13 +218,18 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(
     const int64_t next = item + gridDim.x;
     // the refill below overwrites the slab every group read one iteration ago; groups that fit in a
     // warp only synchronise with __syncwarp() inside the transforms, so order them here
-    if constexpr (T <= 32) __syncthreads();
-    if (threadIdx.x == 0 && next < nitems)
-      stager.issue(buf ^ 1, slab[buf ^ 1], a.in + next * G * 2 * N, slab_bytes(next));
-    stager.wait(buf, (it_count >> 1) & 1);
     float2 v[kE];
     bool nz0, nz1, z0, z1;
-    load_pair_staged<N>(v, a, slab[buf], t, g, act0, act1, nz0, nz1);
+    if constexpr (STAGED) {
+      if constexpr (T <= 32) __syncthreads();
+      if (threadIdx.x == 0 && next < nitems)
+        stager.issue(buf ^ 1, slab[buf ^ 1], a.in + next * G * 2 * N, slab_bytes(next));
+      stager.wait(buf, (it_count >> 1) & 1);
+      load_pair_staged<N>(v, a, slab[buf], t, g, act0, act1, nz0, nz1);
+    } else {
+      (void)buf; (void)next;
+      load_pair<N>(v, a, t, act0, act1, p0, nz0, nz1);
+    }
     nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
     // band-pass in digit-reversed order: register (u, m) <-> position (t + u*T)*RL + m, hq is stored
     // [m][beta] so that a warp reads consecutive floats; fetched while the last exchange is in flight
@@ -772,7 +778,8 @@ int build_hq(int n, const float* band, std::vector<float>& hq) {
 }
 
 template <int N, typename K>
-static int launch_geo(thz_ctx* c, cudaStream_t s, K kernel, const TraceArgs& a, bool staged = false) {
+static int launch_geo(thz_ctx* c, cudaStream_t s, K kernel, const TraceArgs& a, bool staged = false,
+                      int carveout_pct = -1) {
   using GEO = Geo<N>;
   const size_t smem = staged ? GEO::smem_bytes_staged : GEO::smem_bytes;
   const void* key = (const void*)kernel;
@@ -780,6 +787,10 @@ static int launch_geo(thz_ctx* c, cudaStream_t s, K kernel, const TraceArgs& a, 
   if (it == c->occ.end()) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(smem)");
+    if (carveout_pct >= 0) {   // leave the rest of the unified L1 / shared memory to the twiddle and multiplier tables
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
+      if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(carveout)");
+    }
     int nb = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, GEO::NT, smem);
     if (e != cudaSuccess) return cuda_fail(c, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
@@ -812,7 +823,8 @@ static int launch_geo(thz_ctx* c, cudaStream_t s, K kernel, const TraceArgs& a, 
   }
 
 template <int N> static int do_fused(thz_ctx* c, cudaStream_t s, const TraceArgs& a) {
-  return launch_geo<N>(c, s, k_trace_fused<N>, a, true);
+  if (c->unstaged_fir) return launch_geo<N>(c, s, k_trace_fused<N, false>, a, false, 40);
+  return launch_geo<N>(c, s, k_trace_fused<N, true>, a, true);
 }
 template <int N> static int do_forward(thz_ctx* c, cudaStream_t s, const TraceArgs& a) {
   return launch_geo<N>(c, s, k_trace_forward<N>, a);
