@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
     float q1e[NLOW], q2e[NLOW], q1o[NLOW], q2o[NLOW];
     // even bins
     if constexpr (STAGED) load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
-    else load_pair_direct<N>(z, a.x, p0, t, act0, act1, nz0, nz1);
+    else load_pair_direct<N>(z, a.x, p0, t, act0, act1, nz0, nz1);   // (an L2 prefetch of the next pair costs 4 % here)
     nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
     fft_forward<N>(z, t, sm, a.tw);
     __syncthreads();
@@ -1009,6 +1009,12 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_
       const float* slab = pipe.acquire(item);
       load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
     } else {
+      const int64_t next = item + gridDim.x;
+      if (next < nitems) {
+        int64_t cnt = a.P - next * G * 2;
+        if (cnt > 2 * G) cnt = 2 * G;
+        prefetch_l2_slab(a.x + next * G * 2 * N, cnt * N);
+      }
       load_pair_direct<N>(z, a.x, p0, t, act0, act1, nz0, nz1);
     }
     fft_forward<N>(z, t, sm, a.tw);

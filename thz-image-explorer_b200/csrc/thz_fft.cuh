@@ -283,6 +283,15 @@ template <bool WARP> __device__ __forceinline__ void scoped_sync() {
 }
 template <int N> __device__ __forceinline__ void group_sync() { scoped_sync<(N / kE <= 32)>(); }
 
+// Pull the slab of the NEXT work item into L2 while the current one is transformed: one 128-byte line per
+// thread and step, no registers or shared memory held (the register-resident transforms cannot keep a second
+// item in flight, and a shared-memory double buffer evicts the tables from L1).
+__device__ __forceinline__ void prefetch_l2_slab(const float* base, int64_t floats) {
+  const int64_t lines = (floats + 31) >> 5;
+  for (int64_t l = threadIdx.x; l < lines; l += blockDim.x)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 5)));
+}
+
 struct NoHook {
   __device__ __forceinline__ void operator()() const {}
 };

@@ -227,7 +227,12 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(
       stager.wait(buf, (it_count >> 1) & 1);
       load_pair_staged<N>(v, a, slab[buf], t, g, act0, act1, nz0, nz1);
     } else {
-      (void)buf; (void)next;
+      (void)buf;
+      if (next < nitems) {
+        int64_t cnt = a.P - next * G * 2;
+        if (cnt > 2 * G) cnt = 2 * G;
+        prefetch_l2_slab(a.in + next * G * 2 * N, cnt * N);
+      }
       load_pair<N>(v, a, t, act0, act1, p0, nz0, nz1);
     }
     nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
