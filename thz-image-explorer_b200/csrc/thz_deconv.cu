@@ -498,67 +498,92 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
     __syncthreads();
     parseval_terms<N, true>(z, sm, t, q1o, q2o);
     __syncthreads();   // partner reads done: the buffer becomes reduction scratch
-    for (int b0 = 0; b0 < a.B; b0 += 4) {
-      float e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
+    // eight bands per round: e[2*bb + trace]; the 16 partial sums of a warp are reduced by a halving tree
+    // (16 shuffles instead of 80), then across the warps through shared memory
+    for (int b0 = 0; b0 < a.B; b0 += 8) {
+      float e[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) e[k] = 0.f;
 #pragma unroll
       for (int j = 0; j < NLOW; ++j) {
         const int u = j % UL, m = j / UL;
-        const size_t o = ((size_t)(b0 >> 2) * (N / 2) + (m * (N / RL) + t + u * T)) * 4;
-        const float4 w_e = __ldg(reinterpret_cast<const float4*>(a.we4 + o));
-        const float4 w_o = __ldg(reinterpret_cast<const float4*>(a.wo4 + o));
-        const float we_[4] = {w_e.x, w_e.y, w_e.z, w_e.w}, wo_[4] = {w_o.x, w_o.y, w_o.z, w_o.w};
+        const int idx = m * (N / RL) + t + u * T;
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          e1[bb] = fmaf(we_[bb], q1e[j], e1[bb]);
-          e2[bb] = fmaf(we_[bb], q2e[j], e2[bb]);
-          e1[bb] = fmaf(wo_[bb], q1o[j], e1[bb]);
-          e2[bb] = fmaf(wo_[bb], q2o[j], e2[bb]);
+        for (int h = 0; h < 2; ++h) {
+          if (b0 + 4 * h < a.Bp) {
+            const size_t o = ((size_t)((b0 >> 2) + h) * (N / 2) + idx) * 4;
+            const float4 w_e = __ldg(reinterpret_cast<const float4*>(a.we4 + o));
+            const float4 w_o = __ldg(reinterpret_cast<const float4*>(a.wo4 + o));
+            const float we_[4] = {w_e.x, w_e.y, w_e.z, w_e.w}, wo_[4] = {w_o.x, w_o.y, w_o.z, w_o.w};
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+              const int k = 2 * (4 * h + bb);
+              e[k] = fmaf(we_[bb], q1e[j], e[k]);
+              e[k + 1] = fmaf(we_[bb], q2e[j], e[k + 1]);
+              e[k] = fmaf(wo_[bb], q1o[j], e[k]);
+              e[k + 1] = fmaf(wo_[bb], q2o[j], e[k + 1]);
+            }
+          }
         }
       }
       if (t == 0) {
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
+        for (int bb = 0; bb < 8; ++bb) {
           if (b0 + bb < a.B) {
             const float w = __ldg(a.wnyq + b0 + bb);
-            e1[bb] = fmaf(w, ny1, e1[bb]);
-            e2[bb] = fmaf(w, ny2, e2[bb]);
+            e[2 * bb] = fmaf(w, ny1, e[2 * bb]);
+            e[2 * bb + 1] = fmaf(w, ny2, e[2 * bb + 1]);
           }
         }
       }
+      if constexpr (W == 32) {
+        // after the step with lane offset `off` a lane keeps the upper half of its values when its `off` bit is
+        // set: lane l ends with the warp total of value l >> 1
+        const int lane = t & 31;
 #pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
+        for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+          const bool up = (lane & off) != 0;
 #pragma unroll
-        for (int o = W / 2; o > 0; o >>= 1) {
-          e1[bb] += __shfl_xor_sync(0xffffffffu, e1[bb], o);
-          e2[bb] += __shfl_xor_sync(0xffffffffu, e2[bb], o);
-        }
-      }
-      if constexpr (T > 32) {
-        if ((t & 31) == 0) {
-#pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            red[((t >> 5) * 4 + bb) * 2] = e1[bb];
-            red[((t >> 5) * 4 + bb) * 2 + 1] = e2[bb];
+          for (int k = 0; k < half; ++k) {
+            const float send = up ? e[k] : e[k + half];
+            const float keep = up ? e[k + half] : e[k];
+            e[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
           }
         }
-        __syncthreads();
-        if (t < 8) {
-          float acc = 0.f;
-          for (int w = 0; w < NW; ++w) acc += red[(w * 4 + (t >> 1)) * 2 + (t & 1)];
-          const int b = b0 + (t >> 1);
-          const bool second = (t & 1) != 0;
-          if (b < a.B && (second ? act1 : act0))
-            a.energy[(size_t)b * a.bstride + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : acc;
+        e[0] += __shfl_xor_sync(0xffffffffu, e[0], 1);
+        if constexpr (T > 32) {
+          if ((lane & 1) == 0) red[(t >> 5) * 16 + (lane >> 1)] = e[0];
+          __syncthreads();
+          if (t < 16) {   // thread t sums value t = (band t/2, trace t%2) over the warps
+            float acc = 0.f;
+            for (int w = 0; w < NW; ++w) acc += red[w * 16 + t];
+            const int bnd = b0 + (t >> 1);
+            const bool second = (t & 1) != 0;
+            if (bnd < a.B && (second ? act1 : act0))
+              a.energy[(size_t)bnd * a.bstride + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : acc;
+          }
+          __syncthreads();
+        } else {
+          // one warp per pair: lane l holds value l >> 1
+          const int v = lane >> 1, bnd = b0 + (v >> 1);
+          const bool second = (v & 1) != 0;
+          if ((lane & 1) == 0 && bnd < a.B && (second ? act1 : act0))
+            a.energy[(size_t)bnd * a.bstride + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : e[0];
         }
-        __syncthreads();
       } else {
+        // groups narrower than a warp (N < 512): plain butterfly inside the group
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+#pragma unroll
+          for (int o = W / 2; o > 0; o >>= 1) e[k] += __shfl_xor_sync(0xffffffffu, e[k], o);
+        }
         if (t == 0) {
 #pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            const int b = b0 + bb;
-            if (b < a.B) {
-              if (act0) a.energy[(size_t)b * a.bstride + p0] = z0 ? 0.f : e1[bb];
-              if (act1) a.energy[(size_t)b * a.bstride + p0 + 1] = z1 ? 0.f : e2[bb];
+          for (int bb = 0; bb < 8; ++bb) {
+            const int bnd = b0 + bb;
+            if (bnd < a.B) {
+              if (act0) a.energy[(size_t)bnd * a.bstride + p0] = z0 ? 0.f : e[2 * bb];
+              if (act1) a.energy[(size_t)bnd * a.bstride + p0 + 1] = z1 ? 0.f : e[2 * bb + 1];
             }
           }
         }
