@@ -749,55 +749,71 @@ __global__ void __launch_bounds__(256, 2) k_fir_edges(const FirArgs a) {
   for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int64_t p0 = (item * G + g) * 2;
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
-    for (int edge = 0; edge < 2; ++edge) {
-      const int off = edge ? a.n - kSeg : 0;
-      const float* r0 = a.x + p0 * a.n + off;
-      const float* r1 = r0 + a.n;
-      float2 z[kE];
+    // eight bands per round: acc[2*bb + trace] collects head + tail energy of band bg + bb over this lane's
+    // outputs; one halving shuffle tree per round instead of a butterfly per band and edge
+    for (int bg = 0; bg < a.B; bg += 8) {
+      float acc[16];
 #pragma unroll
-      for (int i = 0; i < kE; ++i) {
-        const int e = t + i * T;
-        const bool in = e < kSeg;
-        z[i].x = (act0 && in) ? __ldg(r0 + e) : 0.f;
-        z[i].y = (act1 && in) ? __ldg(r1 + e) : 0.f;
-      }
-      fft_forward<M>(z, t, sm, a.tw512);
-      const int lo = edge ? kSeg - 1 : 0, hi = edge ? 2 * kSeg - 1 : kSeg;   // kept outputs [lo, hi)
-      for (int b = 0; b < a.B; ++b) {
-        const float2* hq = a.edge + ((size_t)edge * a.B + b) * M;
-        float2 w[kE];
-#pragma unroll
-        for (int i = 0; i < kE; ++i) {
-          const int u = i % UL, m = i / UL;
-          w[i] = cmul(z[i], __ldg(hq + m * (M / RL) + t + u * T));
-        }
-        fft_inverse<M>(w, t, sm, a.tw512);
-        float s0 = 0.f, s1 = 0.f;
+      for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+      for (int edge = 0; edge < 2; ++edge) {
+        const int off = edge ? a.n - kSeg : 0;
+        const float* r0 = a.x + p0 * a.n + off;
+        const float* r1 = r0 + a.n;
+        float2 z[kE];
 #pragma unroll
         for (int i = 0; i < kE; ++i) {
           const int e = t + i * T;
-          if (e >= lo && e < hi) {
-            s0 = fmaf(w[i].x, w[i].x, s0);
-            s1 = fmaf(w[i].y, w[i].y, s1);
-          }
+          const bool in = e < kSeg;
+          z[i].x = (act0 && in) ? __ldg(r0 + e) : 0.f;
+          z[i].y = (act1 && in) ? __ldg(r1 + e) : 0.f;
         }
+        fft_forward<M>(z, t, sm, a.tw512);
+        const int lo = edge ? kSeg - 1 : 0, hi = edge ? 2 * kSeg - 1 : kSeg;   // kept outputs [lo, hi)
+#pragma unroll 1
+        for (int bb = 0; bb < 8; ++bb) {   // rolled: acc is indexed at run time (a 64-byte local array, L1 resident)
+          const int b = bg + bb;
+          if (b < a.B) {
+            const float2* hq = a.edge + ((size_t)edge * a.B + b) * M;
+            float2 w[kE];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        }
-        if (t == 0) {   // only this warp touches the pair's entries; exact zeros (dead pixels) stay zero
-          if (act0) {
-            float* e = a.energy + (size_t)b * a.bstride + p0;
-            const float v = *e;
-            if (v != 0.f) *e = fmaxf(v - s0, 0.f);
+            for (int i = 0; i < kE; ++i) {
+              const int u = i % UL, m = i / UL;
+              w[i] = cmul(z[i], __ldg(hq + m * (M / RL) + t + u * T));
+            }
+            fft_inverse<M>(w, t, sm, a.tw512);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < kE; ++i) {
+              const int e = t + i * T;
+              if (e >= lo && e < hi) {
+                s0 = fmaf(w[i].x, w[i].x, s0);
+                s1 = fmaf(w[i].y, w[i].y, s1);
+              }
+            }
+            acc[2 * bb] += s0;
+            acc[2 * bb + 1] += s1;
           }
-          if (act1) {
-            float* e = a.energy + (size_t)b * a.bstride + p0 + 1;
-            const float v = *e;
-            if (v != 0.f) *e = fmaxf(v - s1, 0.f);
-          }
         }
+      }
+      // lane l ends with the warp total of value l >> 1 = (band bg + (l >> 2), trace (l >> 1) & 1)
+#pragma unroll
+      for (int half = 8, o = 16; half >= 1; half >>= 1, o >>= 1) {
+        const bool up = (t & o) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+          const float send = up ? acc[k] : acc[k + half];
+          const float keep = up ? acc[k + half] : acc[k];
+          acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+      const int v = t >> 1, b = bg + (v >> 1);
+      const bool second = (v & 1) != 0;
+      if ((t & 1) == 0 && b < a.B && (second ? act1 : act0)) {
+        // only this warp touches the pair's entries; exact zeros (dead pixels) stay zero
+        float* e = a.energy + (size_t)b * a.bstride + p0 + (second ? 1 : 0);
+        const float cur = *e;
+        if (cur != 0.f) *e = fmaxf(cur - acc[0], 0.f);
       }
     }
   }
