@@ -253,7 +253,9 @@ int thz_deconv_plan_bands(const thz_psf* psf, const thz_deconv_params* params, c
                           int img_rows, int img_cols, int has_dxdy, float dx, float dy, thz_band_plan* bands);
 
 /* Band energies: E[b][p] = sum_t (h_b * x[p])[t]^2 with the "same" alignment of `convolve1d`
- * (src/filters/deconvolution.rs:266-317, 574-609, 963-966).  d_energy is [n_bands][P]. */
+ * (src/filters/deconvolution.rs:266-317, 574-609, 963-966).  d_energy is [n_bands][P].
+ * Trace lengths: any n in [2, 7943] (zero-padded transform of the next power of two >= n + 249; powers of two
+ * from 512 on run the N-point split / circular forms) and n = 8192 (N-point forms only). */
 int thz_deconv_energies_dev(thz_ctx* ctx, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
                             int n_bands, float* d_energy);
 /* `richardson_lucy` (src/filters/deconvolution.rs:620-712) on one [rows][cols] image with a

@@ -95,7 +95,7 @@ def test_richardson_lucy_matches_oracle(ctx, psfs, band_idx, n_iter):
         assert rel_err(ud, ref) <= TOL_MAP
 
 
-@pytest.mark.parametrize("n", [256, 1024, 2048])
+@pytest.mark.parametrize("n", [256, 1024, 2048, 8192])
 def test_band_energies_match_oracle(ctx, psfs, n):
     psf, opsf = psfs
     w, h = 5, 7
@@ -213,11 +213,12 @@ def test_chain_host_abort(ctx, psfs):
     assert rc == 1
 
 
-@pytest.mark.parametrize("n,w,h", [(512, 5, 7), (1024, 3, 5), (4096, 3, 3), (256, 4, 4)])
+@pytest.mark.parametrize("n,w,h", [(512, 5, 7), (1024, 3, 5), (4096, 3, 3), (256, 4, 4), (8192, 3, 1)])
 def test_gain_application_matches_oracle(ctx, psfs, n, w, h):
     """Pass C alone: out[p] = sum_b g_b[p] (fir_b * x[p]) in 'same' mode (deconvolution.rs:873-905) with random
     per-pixel gains, odd pixel count (ragged last pair), in place.  n >= 512 runs the circular form with the
-    wrap-around edge corrections, n = 256 the zero-padded form: both must reproduce the linear convolution."""
+    wrap-around edge corrections, n = 256 the zero-padded form: both must reproduce the linear convolution.
+    n = 8192 is the largest trace length: no monolithic 16384-point plan exists, only the N-point forms."""
     psf, opsf = psfs
     cube = synthetic_cube(w, h, n, seed=100 + n, noise=0.05)
     # energy right up to both ends of the trace, so that the wrapped pieces are far from negligible

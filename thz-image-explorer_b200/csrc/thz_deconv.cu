@@ -1845,7 +1845,24 @@ static int build_fir_hq(int m, const float* fir, std::vector<float>& hq) {
   return THZ_OK;
 }
 
+// the same spectrum in natural bin order (k in [0, m)), for transform sizes without a monolithic plan
+static void fir_spectrum_natural(int m, const float* fir, std::vector<float>& hnat) {
+  const int taps = THZ_FIR_TAPS, half = (taps - 1) / 2;
+  std::vector<double> ctab(m);
+  for (int i = 0; i < m; ++i) ctab[i] = cos(2.0 * M_PI * (double)i / (double)m);
+  hnat.assign(m, 0.f);
+  for (int k = 0; k <= m / 2; ++k) {
+    double acc = (double)fir[half];
+    for (int j = 1; j <= half; ++j)
+      acc += ((double)fir[half + j] + (double)fir[half - j]) * ctab[(int)(((long)j * k) & (m - 1))];
+    const float v = (float)(acc / (double)m);
+    hnat[k] = v;
+    if (k != 0 && k != m / 2) hnat[m - k] = v;
+  }
+}
+
 struct FirTables {
+  bool mono = true;        // a monolithic m-point plan exists (hq / wq tables are filled)
   int m = 0, B = 0;
   float* d_hq = nullptr;   // workspace slot WS_FIR, cached across calls while the taps do not change
   float* d_wq = nullptr;   // [B][m/2]
@@ -1908,19 +1925,23 @@ static uint64_t fnv1a(const void* p, size_t n, uint64_t h) {
 
 static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_plan* bands, int B, FirTables& ft) {
   const int m = fir_fft_size(n);
-  int ns, r[4];
-  if (!plan_of_m(m, ns, r)) return set_err(c, THZ_EINVAL, "trace too long for the FIR transform (n + 249 must be <= 8192)");
+  int ns = 0, r[4] = {0, 0, 0, 0};
+  const bool mono = plan_of_m(m, ns, r);
+  // n = 8192 (m = 16384) has no monolithic plan: it runs on the split / circular forms only
+  if (!mono && !(m == 2 * n && n == 8192))
+    return set_err(c, THZ_EINVAL, "trace too long for the FIR transform (n must be <= 7943 or exactly 8192)");
+  ft.mono = mono;
   uint64_t key = 0xcbf29ce484222325ull;
   for (int b = 0; b < B; ++b) key = fnv1a(bands[b].fir, sizeof(bands[b].fir), key);
   key = fnv1a(&m, sizeof m, key);
   void* dp = nullptr;
   // layout (floats): hq [B][m] | wq [B][m/2] | wnyq [B, padded to 4] | edge [2][B][512] float2
-  const size_t n_hq = (size_t)B * m, n_wq = (size_t)B * (m / 2), n_ny = (size_t)((B + 3) & ~3);
+  const size_t n_hq = mono ? (size_t)B * m : 0, n_wq = mono ? (size_t)B * (m / 2) : 0, n_ny = (size_t)((B + 3) & ~3);
   const size_t n_edge = (size_t)2 * B * 512 * 2;
   const int nh = m / 2;
   int nsh, rh[4];
-  // the split kernels stage 64 KB of input + the exchange buffer: n <= 4096 keeps two CTAs per SM
-  const bool split = (nh == n) && nh >= 256 && nh <= 4096 && plan_of_m(nh, nsh, rh);
+  // split / circular forms: N-point geometry (two CTAs per SM up to n = 4096, one 512-thread CTA at 8192)
+  const bool split = (nh == n) && nh >= 256 && nh <= 8192 && plan_of_m(nh, nsh, rh);
   const int Bp = (B + 3) & ~3;
   const size_t n_split_base = split ? ((size_t)2 * B * nh + (size_t)2 * B * (nh / 2) + (size_t)2 * nh) : 0;
   const size_t n_il = split ? ((size_t)3 * (nh / 2) * Bp + Bp) : 0;   // we4, wo4, he4, hny4
@@ -1948,15 +1969,19 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
   ft.B = B;
   if (c->fir_key == key && c->fir_m == m) return THZ_OK;
   std::vector<float> all(n_hq + n_wq + n_ny + n_edge + n_split, 0.f), one;
-  const int RLs = r[ns - 1];
+  const int RLs = mono ? r[ns - 1] : 1;
   for (int b = 0; b < B; ++b) {
-    if (build_fir_hq(m, bands[b].fir, one) != THZ_OK) return set_err(c, THZ_EINVAL, "bad FIR transform size");
-    std::copy(one.begin(), one.end(), all.begin() + (size_t)b * m);
-    // Parseval weights |H|^2 / m = (H/m)^2 * m for the lower-half registers (last-stage digit < RL/2):
-    // they are the first m/2 entries of the [digit][beta] register-order table
-    for (int i = 0; i < m / 2; ++i) all[n_hq + (size_t)b * (m / 2) + i] = one[i] * one[i] * (float)m;
-    // Nyquist bin: register (digit RL/2, beta 0)
-    const float hn = one[(size_t)(RLs / 2) * (m / RLs)];
+    std::vector<float> hnat;
+    fir_spectrum_natural(m, bands[b].fir, hnat);
+    if (mono) {
+      if (build_fir_hq(m, bands[b].fir, one) != THZ_OK) return set_err(c, THZ_EINVAL, "bad FIR transform size");
+      std::copy(one.begin(), one.end(), all.begin() + (size_t)b * m);
+      // Parseval weights |H|^2 / m = (H/m)^2 * m for the lower-half registers (last-stage digit < RL/2):
+      // they are the first m/2 entries of the [digit][beta] register-order table
+      for (int i = 0; i < m / 2; ++i) all[n_hq + (size_t)b * (m / 2) + i] = one[i] * one[i] * (float)m;
+    }
+    // Nyquist bin of the m-point spectrum
+    const float hn = hnat[m / 2];
     all[n_hq + n_wq + b] = hn * hn * (float)m;
     std::vector<float2> head, tail;
     build_edge_tables(bands[b].fir, head, tail);
@@ -1965,22 +1990,7 @@ static int upload_fir_tables(thz_ctx* c, cudaStream_t s, int n, const thz_band_p
     memcpy(eh, head.data(), 512 * sizeof(float2));
     memcpy(et, tail.data(), 512 * sizeof(float2));
     if (split) {
-      // natural-order H / m from the register-order table of the m-point plan, then the even / odd
-      // sub-spectra in the register order of the (m/2)-point plan
-      std::vector<float> hnat(m);
-      for (int beta = 0; beta < m / RLs; ++beta)
-        for (int mm = 0; mm < RLs; ++mm) {
-          int pp = beta * RLs + mm, k = 0, w = 1, L = m;
-          for (int s2 = 0; s2 < ns; ++s2) {
-            const int S = L / r[s2];
-            const int q = pp / S;
-            pp -= q * S;
-            k += q * w;
-            w *= r[s2];
-            L = S;
-          }
-          hnat[k] = one[(size_t)mm * (m / RLs) + beta];
-        }
+      // the even / odd sub-spectra of the natural-order H / m, in the register order of the (m/2)-point plan
       const int RLh = rh[nsh - 1];
       float* he = all.data() + n_hq + n_wq + n_ny + n_edge + (size_t)b * nh;
       float* ho = he + (size_t)B * nh;
@@ -2157,10 +2167,10 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
   int rc = upload_fir_tables(c, s, n, bands, B, ft);
   if (rc != THZ_OK) return rc;
   const FftTables* tb = nullptr;
-  rc = get_tables(c, ft.m, &tb);
+  if (ft.mono) rc = get_tables(c, ft.m, &tb);
   if (rc == THZ_OK) {
     FirArgs a{};
-    a.x = d_cube; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.energy = d_energy; a.tw = tb->d_tw;
+    a.x = d_cube; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.energy = d_energy; a.tw = tb ? tb->d_tw : nullptr;
     a.bstride = bstride;
     a.wq = ft.d_wq; a.wnyq = ft.d_wnyq; a.edge = ft.d_edge;
     if (n >= 512 && ft.m >= n + THZ_FIR_TAPS - 1) {
@@ -2208,12 +2218,12 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
   int rc = upload_fir_tables(c, s, n, bands, B, ft);
   if (rc != THZ_OK) return rc;
   const FftTables* tb = nullptr;
-  rc = get_tables(c, ft.m, &tb);
+  if (ft.mono) rc = get_tables(c, ft.m, &tb);
   if (rc == THZ_OK) {
     FirArgs a{};
     a.x = d_cube; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.gain = d_gain; a.out = d_out; a.img = d_img;
     a.bstride = bstride;
-    a.tw = tb->d_tw;
+    a.tw = tb ? tb->d_tw : nullptr;
     if (ft.split) {
       const FftTables* tbn = nullptr;
       rc = get_tables(c, n, &tbn);
