@@ -274,6 +274,14 @@ int thz_plan_trace(thz_ctx* c, int n, const float* m_pre, const float* band, con
   p.n = n;
   p.has_pre = m_pre != nullptr;
   p.has_post = m_post != nullptr;
+  auto ends_only = [n](const float* m) {
+    if (!m || n < 64 || (n & (n - 1)) != 0) return false;
+    for (int i = n / 16; i < n - n / 16; ++i)
+      if (m[i] != 1.0f) return false;
+    return true;
+  };
+  p.pre_ends_only = ends_only(m_pre);
+  p.post_ends_only = ends_only(m_post);
   p.has_band = band != nullptr;
   if (m_pre && (rc = upload_vec(c, &p.d_m_pre, m_pre, n)) != THZ_OK) return rc;
   if (m_post && (rc = upload_vec(c, &p.d_m_post, m_post, n)) != THZ_OK) return rc;

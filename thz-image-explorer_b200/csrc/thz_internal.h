@@ -23,6 +23,8 @@ struct TracePlan {
   float* d_band = nullptr;      // [n/2+1] or null
   float* d_hq = nullptr;        // [n] band (or ones) / n in last-stage register order (fused kernel)
   bool has_pre = false, has_post = false, has_band = false;
+  // the multiplier is exactly 1 on [n/16, n - n/16): only the first and the last register of a thread need it
+  bool pre_ends_only = false, post_ends_only = false;
   // traces whose length is not a power of two go through the chirp-z kernels (thz_bluestein.cu)
   int blue_m = 0;               // power-of-two transform size (>= 2n - 1), 0 = power-of-two plan
   float2* d_chirp = nullptr;    // [n]

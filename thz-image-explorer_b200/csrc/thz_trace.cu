@@ -40,6 +40,8 @@ struct TraceArgs {
   float* img;             // [P] or null
   const float* m_pre;     // [N] or null
   const float* m_post;    // [N] or null
+  int pre_ends, post_ends; // multiplier is exactly 1 away from the first / last N/16 samples (windows and gates
+                           // usually are): multiplying by 1.0f is the identity, so only registers 0 and kE-1 load it
   const float* hq;        // [N] (band / N) in last-stage register order
   const float* band;      // [F] or null
   const float2* tw;
@@ -101,11 +103,20 @@ __device__ __forceinline__ void load_pair(float2 (&v)[kE], const TraceArgs& a, i
     nz1 |= (v[i].y != 0.f);
   }
   if (a.m_pre != nullptr) {
+    if (a.pre_ends) {
 #pragma unroll
-    for (int i = 0; i < kE; ++i) {
-      const float m = __ldg(a.m_pre + t + i * T);
-      v[i].x *= m;
-      v[i].y *= m;
+      for (int i = 0; i < kE; i += kE - 1) {
+        const float m = __ldg(a.m_pre + t + i * T);
+        v[i].x *= m;
+        v[i].y *= m;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        const float m = __ldg(a.m_pre + t + i * T);
+        v[i].x *= m;
+        v[i].y *= m;
+      }
     }
   }
 }
@@ -126,11 +137,20 @@ __device__ __forceinline__ void load_pair_staged(float2 (&v)[kE], const TraceArg
     nz1 |= (v[i].y != 0.f);
   }
   if (a.m_pre != nullptr) {
+    if (a.pre_ends) {
 #pragma unroll
-    for (int i = 0; i < kE; ++i) {
-      const float m = __ldg(a.m_pre + t + i * T);
-      v[i].x *= m;
-      v[i].y *= m;
+      for (int i = 0; i < kE; i += kE - 1) {
+        const float m = __ldg(a.m_pre + t + i * T);
+        v[i].x *= m;
+        v[i].y *= m;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        const float m = __ldg(a.m_pre + t + i * T);
+        v[i].x *= m;
+        v[i].y *= m;
+      }
     }
   }
 }
@@ -148,11 +168,20 @@ __device__ __forceinline__ void store_pair(float2 (&v)[kE], const TraceArgs& a, 
     }
   }
   if (use_post) {
+    if (a.post_ends) {
 #pragma unroll
-    for (int i = 0; i < kE; ++i) {
-      const float m = __ldg(a.m_post + t + i * T);
-      v[i].x *= m;
-      v[i].y *= m;
+      for (int i = 0; i < kE; i += kE - 1) {
+        const float m = __ldg(a.m_post + t + i * T);
+        v[i].x *= m;
+        v[i].y *= m;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        const float m = __ldg(a.m_post + t + i * T);
+        v[i].x *= m;
+        v[i].y *= m;
+      }
     }
   }
   float* r0 = a.out + p0 * N + t;
@@ -867,6 +896,8 @@ int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_o
   a.img = d_img;
   a.m_pre = c->plan.has_pre ? c->plan.d_m_pre : nullptr;
   a.m_post = c->plan.has_post ? c->plan.d_m_post : nullptr;
+  a.pre_ends = c->plan.pre_ends_only ? 1 : 0;
+  a.post_ends = c->plan.post_ends_only ? 1 : 0;
   a.hq = c->plan.d_hq;
   THZ_DISPATCH_N(c->plan.n, do_fused, c, s, a);
 }
@@ -889,6 +920,7 @@ int launch_trace_forward(thz_ctx* c, cudaStream_t s, const float* d_in, float* d
   a.amp = d_amp;
   a.phase = d_phase;
   a.m_pre = c->plan.has_pre ? c->plan.d_m_pre : nullptr;
+  a.pre_ends = c->plan.pre_ends_only ? 1 : 0;
   THZ_DISPATCH_N(c->plan.n, do_forward, c, s, a);
 }
 
@@ -909,6 +941,7 @@ int launch_trace_inverse(thz_ctx* c, cudaStream_t s, const float2* d_fft, bool u
   a.img = d_img;
   a.band = (use_band && c->plan.has_band) ? c->plan.d_band : nullptr;
   a.m_post = (use_post && c->plan.has_post) ? c->plan.d_m_post : nullptr;
+  a.post_ends = c->plan.post_ends_only ? 1 : 0;
   THZ_DISPATCH_N(c->plan.n, do_inverse, c, s, a);
 }
 
