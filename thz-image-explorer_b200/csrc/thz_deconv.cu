@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
     fft_forward<N>(z, t, sm, a.tw);
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
+    for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];   // mirrors of lower-half bins are upper-half registers
     __syncthreads();
     nz_resolve<T>(g, parity, nzbuf, z0, z1);
     parseval_terms<N, false>(z, sm, t, q1e, q2e);
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
     fft_forward<N>(z, t, sm, a.tw);   // its first barrier orders the partner reads above before the exchange
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
+    for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];   // mirrors of lower-half bins are upper-half registers
     __syncthreads();
     parseval_terms<N, true>(z, sm, t, q1o, q2o);
     __syncthreads();   // partner reads done: the buffer becomes reduction scratch
@@ -1061,7 +1061,7 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_
     fft_forward<N>(z, t, sm, a.tw);
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
+    for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];   // mirrors of lower-half bins are upper-half registers
     __syncthreads();
     // he holds H / (2N): the N-point inverse needs H / N
     mix_paired<N>(z, sm, t, a, a.he, p0, act0, act1, bad0, bad1, 1.0f);
