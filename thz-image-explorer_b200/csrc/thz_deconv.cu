@@ -949,7 +949,7 @@ __global__ void __launch_bounds__(256, 2) k_fir_edge_corr(const FirArgs a) {
       fft_forward<M>(z, t, sm, a.tw512);
       __syncwarp();
 #pragma unroll
-      for (int i = 0; i < kE; ++i) sm[pad_idx(pos_to_bin<M>(stage_elem<M, LAST>(t, i)))] = z[i];
+      for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<M>(stage_elem<M, LAST>(t, i)))] = z[i];
       __syncwarp();
       // Y = S Z + D conj(Z_mirror), S = sum_b (g0+g1)/2 E_b, D = sum_b (g0-g1)/2 E_b (complex edge spectra).
       // The taps are real, E_b[M-k] = conj(E_b[k]): the owner of the lower-half register forms S and D once
