@@ -479,6 +479,12 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
     for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];   // mirrors of lower-half bins are upper-half registers
     __syncthreads();
     nz_resolve<T>(g, parity, nzbuf, z0, z1);
+    // odd bins: the second read of the pair (L2) is issued before the even-bin terms are formed, so that its
+    // latency overlaps them
+    float2 zo[kE];
+    bool d0, d1;
+    if constexpr (STAGED) load_pair_n<N>(zo, slab, t, g, act0, act1, d0, d1);
+    else load_pair_direct<N>(zo, a.x, p0, t, act0, act1, d0, d1);
     parseval_terms<N, false>(z, sm, t, q1e, q2e);
     float ny1 = 0.f, ny2 = 0.f;   // bin M/2 = even index N/2: register (u = 0, digit RL/2) of thread 0
     if (t == 0) {
@@ -486,17 +492,13 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
       ny1 = zz.x * zz.x;
       ny2 = zz.y * zz.y;
     }
-    // odd bins
-    bool d0, d1;
-    if constexpr (STAGED) load_pair_n<N>(z, slab, t, g, act0, act1, d0, d1);
-    else load_pair_direct<N>(z, a.x, p0, t, act0, act1, d0, d1);   // second read: L2
-    modulate<N>(z, a.mod, t);
-    fft_forward<N>(z, t, sm, a.tw);   // its first barrier orders the partner reads above before the exchange
+    modulate<N>(zo, a.mod, t);
+    fft_forward<N>(zo, t, sm, a.tw);   // its first barrier orders the partner reads above before the exchange
     __syncthreads();
 #pragma unroll
-    for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];   // mirrors of lower-half bins are upper-half registers
+    for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = zo[i];   // mirrors of lower-half bins are upper-half registers
     __syncthreads();
-    parseval_terms<N, true>(z, sm, t, q1o, q2o);
+    parseval_terms<N, true>(zo, sm, t, q1o, q2o);
     __syncthreads();   // partner reads done: the buffer becomes reduction scratch
     // eight bands per round: e[2*bb + trace]; the 16 partial sums of a warp are reduced by a halving tree
     // (16 shuffles instead of 80), then across the warps through shared memory
