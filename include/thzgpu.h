@@ -238,6 +238,9 @@ typedef struct {
 #define THZ_SKIP_NO_PSF 3        /* (src/filters/deconvolution.rs:781-812, 873-885)         */
 #define THZ_SKIP_TOO_SMALL 4
 #define THZ_SKIP_PSF_TOO_LARGE 5
+/* NOT a reference skip: a band's PSF extends over more than THZ_MAX_PSF pixels per axis (the reference has no
+ * cap).  The C++ / Rust hosts surface it through last_error instead of silently passing the data through. */
+#define THZ_SKIP_PSF_UNSUPPORTED 6
 
 /* `create_filter_bank` (src/filters/deconvolution.rs:160-211): n_filters x 499 Kaiser FIR
  * taps (designed in f64, stored as f32) and the log-spaced centre frequencies. */

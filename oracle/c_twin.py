@@ -12,7 +12,7 @@ _LIB = None
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "_ref", "libthzoracle.so")
+        path = os.path.join(_HERE, "_twin", "libthzoracle.so")
         if not os.path.exists(path):   # build() compiles it; do it on demand for a bare `pytest`
             import subprocess
             subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)

@@ -155,6 +155,31 @@ def test_chain_with_downscaling(ctx):
     assert rel_err(ch.slot(7)["data"], ref[7].data) <= TOL_TRACE
 
 
+def test_run_fused_honours_scale_factor(ctx, psf_npz_path):
+    """run_fused with scale_factor = 2 == the staged run: the first chain slot (`scaling`, math_tools.rs:242-310)
+    block-averages the cube and doubles dx / dy before anything else; the fused kernels and the deconvolution
+    plan must see the scaled cube (an earlier build fed them the raw one)."""
+    m = pkg()
+    n, w, h = 256, 72, 64
+    cube = synthetic_cube(w, h, n, seed=18, noise=0.02)
+    t = time_axis(n)
+    ch = m.Chain(ctx)
+    ch.set_config(scale_factor=2)
+    ch.open(t, cube, 0.5, 0.5)
+    ch.set_active("Deconvolution", True)
+    ch.set_param("Deconvolution", "n_filters", 4)
+    ch.set_param("Deconvolution", "n_iterations", 10)
+    ch.set_psf(m.host.PSF.load(psf_npz_path))
+    ch.run(1)
+    ch.run(ch.slot_of("Deconvolution"), run_deconvolution=True)
+    ch.shape = (w // 2, h // 2, n)
+    s8 = ch.slot(8)
+    assert s8["data"].shape == (w // 2, h // 2, n)
+    out, img = ch.run_fused(run_deconvolution=True)
+    assert out.shape == s8["data"].shape
+    assert rel_err(out, s8["data"]) <= 1e-4 and rel_err(img, s8["img"]) <= 1e-4
+
+
 def test_chain_driver_non_power_of_two(ctx, psf_npz_path):
     """The whole driver (stage by stage and fused, with deconvolution) on N = 1000 samples."""
     m = pkg()

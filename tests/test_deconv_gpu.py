@@ -279,3 +279,41 @@ def test_gain_application_forms_agree(psfs, monkeypatch):
         assert rel_err(img, outs[0][1]) <= 1e-5
     for e in energies[1:]:
         assert rel_err(e, energies[0]) <= 1e-5
+
+
+def test_chain_host_many_chunks_on_three_streams(psfs, monkeypatch):
+    """thz_chain_host pipelines its chunks over three streams; the wrap-around corrections of pass C live in a
+    per-stream workspace (a shared one would let chunk i+1 overwrite what chunk i still reads).  A 16 KiB chunk
+    size forces 30+ chunks per pass on a small cube; the result must equal the unchunked staged calls, and the
+    first / last 249 samples (where the corrections act) are compared on their own scale."""
+    from helpers import default_multipliers
+    psf, _ = psfs
+    w, h, n = 24, 20, 1024
+    cube = synthetic_cube(w, h, n, seed=21, noise=0.05)
+    rng = np.random.default_rng(8)
+    cube[:, :, :60] += rng.standard_normal((w, h, 60)).astype(F32)
+    cube[:, :, -60:] += rng.standard_normal((w, h, 60)).astype(F32)
+    t = time_axis(n)
+    bands, why = pkg().host.Deconvolution(n_filters=5, n_iterations=8).plan(t, (w, h), 1.0, 1.0, psf)
+    assert why is None
+    results = []
+    for chunk in (None, str(16 * 1024)):
+        if chunk is None:
+            monkeypatch.delenv("THZ_CHAIN_CHUNK_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("THZ_CHAIN_CHUNK_BYTES", chunk)
+        c = pkg().Context(0)
+        try:
+            c.plan_trace(n, None, None, None)     # no gates: the trace ends keep their energy
+            for _ in range(3):                    # the race, if any, is timing dependent
+                out, img, rc = c.chain(cube, bands)
+                assert rc == 0
+                results.append((out, img))
+        finally:
+            c.close()
+    ref_out, ref_img = results[0]
+    for out, img in results[1:]:
+        assert rel_err(out, ref_out) <= 1e-6
+        for sl in (slice(0, 249), slice(n - 249, n)):
+            assert rel_err(out[:, :, sl], ref_out[:, :, sl]) <= 2e-6
+        assert rel_err(img, ref_img) <= 1e-5

@@ -322,6 +322,9 @@ class Deconvolution : public Filter {
                                          (int)input.width, (int)input.height, has ? 1 : 0, has ? *input.dx : 0.f,
                                          has ? *input.dy : 0.f, bands.data());
     if (rc != THZ_OK) {   // the reference logs and returns input.clone() (:781-812, 873-885)
+      if (rc == THZ_SKIP_PSF_UNSUPPORTED || rc < 0)
+        env.last_error = "Deconvolution skipped: PSF extent above THZ_MAX_PSF pixels or bad parameters (library limit, "
+                         "the reference would have run)";
       progress(std::nullopt);
       return out;
     }
@@ -440,7 +443,9 @@ int ChainDriver::run(size_t start_idx, bool run_deconvolution) {
       if (!deconv) run_deconvolution = false;   // data_thread.rs:1139-1150 (cleared by any earlier filter)
       if (active && !(deconv && !run_deconvolution)) {
         ProgressLock progress = [this](std::optional<float> p) { last_progress = p; };
+        f->env.last_error.clear();
         fd[out_idx] = f->filter(fd[in_idx], gui_settings, progress, abort_flag);
+        if (!f->env.last_error.empty()) last_error = f->env.last_error;
         f->show_data(fd[out_idx]);
         filter_computation_time[id] = std::chrono::steady_clock::now() - t0;
       } else {
@@ -467,7 +472,13 @@ int ChainDriver::run(size_t start_idx, bool run_deconvolution) {
 }
 
 int ChainDriver::run_fused(bool run_deconvolution) {
-  const ScannedImageFilterData& s0 = filter_data_pipeline[0];
+  // the first chain slot is `scaling` (math_tools.rs:242-310): with scale_factor > 1 the fused kernels run on the
+  // block-mean cube, with its dimensions and dx * s, dy * s, exactly as the staged run does
+  ScannedImageFilterData scaled;
+  const bool do_scale = config.scale_factor > 1 && filter_data_pipeline[0].width / (size_t)config.scale_factor > 0 &&
+                        filter_data_pipeline[0].height / (size_t)config.scale_factor > 0;
+  if (do_scale) scaled = scaling(ctx_, filter_data_pipeline[0], config);
+  const ScannedImageFilterData& s0 = do_scale ? scaled : filter_data_pipeline[0];
   const size_t n = s0.n(), P = s0.pixels();
   if (!gpu_size_ok(n)) { last_error = "unsupported trace length"; return THZ_EINVAL; }
   auto active = [&](const std::string& name) {
@@ -515,6 +526,10 @@ int ChainDriver::run_fused(bool run_deconvolution) {
                                           (int)s0.width, (int)s0.height, has ? 1 : 0, has ? *s0.dx : 0.f,
                                           has ? *s0.dy : 0.f, bands.data());
     if (prc == THZ_OK) n_bands = d->n_filters;   // otherwise the reference returns the filter's input
+    else if (prc == THZ_SKIP_PSF_UNSUPPORTED || prc < 0) {
+      last_error = "Deconvolution: PSF extent above THZ_MAX_PSF pixels or bad parameters (library limit)";
+      return prc < 0 ? prc : THZ_EINVAL;
+    }
   }
   struct Cb {
     ChainDriver* self;

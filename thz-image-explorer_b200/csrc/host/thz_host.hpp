@@ -78,6 +78,8 @@ using ProgressLock = std::function<void(std::optional<float>)>;   // Arc<RwLock<
 
 struct FilterEnv {
   thz_ctx* ctx = nullptr;   // process-global in the Rust shim: filters are cloned on every update
+  std::string last_error;   // what the Rust shim would `log::error!` (set when a filter passes its input through
+                            // for a reason the reference does not have, e.g. a PSF above THZ_MAX_PSF)
 };
 // std::atomic<bool> has the one-byte layout of Rust's AtomicBool; the C ABI polls it as a byte
 static_assert(sizeof(std::atomic<bool>) == 1, "abort flag must be one byte");

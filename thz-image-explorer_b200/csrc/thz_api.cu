@@ -144,6 +144,10 @@ int thz_ctx_create(int device, thz_ctx** out) {
   c->unstaged_fir = true;
   if (const char* f = getenv("THZ_FIR_STAGING")) c->unstaged_fir = (strcmp(f, "on") != 0);
   if (const char* f = getenv("THZ_APPLY_FORM")) c->force_split_apply = (strcmp(f, "split") == 0);
+  if (const char* f = getenv("THZ_CHAIN_CHUNK_BYTES")) {
+    const long long v = atoll(f);
+    if (v >= 4096) c->host_chunk_bytes = (size_t)v;
+  }
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete c;

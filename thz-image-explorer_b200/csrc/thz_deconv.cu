@@ -2209,8 +2209,11 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
   return rc;
 }
 
+// `lane` selects the wrap-around correction workspace: calls that are in flight on different streams at the same
+// time (the chunk pipeline of thz_chain_host) must not share one (k_fir_edge_corr of chunk i+1 would overwrite
+// what k_fir_apply_circ of chunk i still reads).  Lane 0 = the context's compute stream, 1 + k = hstream[k].
 int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d_gain, int64_t P, int n,
-                 const thz_band_plan* bands, int B, float* d_out, float* d_img, int64_t bstride = 0) {
+                 const thz_band_plan* bands, int B, float* d_out, float* d_img, int64_t bstride = 0, int lane = 0) {
   if (bstride == 0) bstride = P;
   if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
   if (P == 0) return THZ_OK;
@@ -2243,7 +2246,7 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
         const int64_t npairs = (P + 1) / 2;
         const int64_t chunk_pairs = std::min<int64_t>(npairs, kCorrChunkPairs);
         void* pc = nullptr;
-        rc = ws_get(c, WS_EDGE_CORR, (size_t)chunk_pairs * 2 * kCorrStride * sizeof(float2), &pc);
+        rc = ws_get(c, WS_EDGE_CORR + lane, (size_t)chunk_pairs * 2 * kCorrStride * sizeof(float2), &pc);
         if (rc != THZ_OK) return rc;
         for (int64_t q0 = 0; rc == THZ_OK && q0 < npairs; q0 += chunk_pairs) {
           const int64_t p_lo = 2 * q0, p_hi = std::min<int64_t>(P, 2 * (q0 + chunk_pairs));
@@ -2763,7 +2766,7 @@ int thz_chain_host(thz_ctx* c, const float* cube, int rows, int cols, int n, con
     rc = upload_fir_tables(c, c->stream, n, bands, n_bands, ft);
     if (rc != THZ_OK) return rc;
   }
-  int64_t ct = ((int64_t)256 << 20) / ((int64_t)n * 4);   // 256 MiB chunks, whole pairs
+  int64_t ct = (int64_t)c->host_chunk_bytes / ((int64_t)n * 4);   // 256 MiB chunks (THZ_CHAIN_CHUNK_BYTES), whole pairs
   ct &= ~(int64_t)1;
   if (ct < 2) ct = 2;
   int i = 0;
@@ -2798,7 +2801,7 @@ int thz_chain_host(thz_ctx* c, const float* cube, int rows, int cols, int n, con
       const int64_t np = std::min(ct, P - p);
       cudaStream_t s = c->hstream[i % kHostStreams];
       float* d = d_cube + p * n;
-      rc = deconv_apply(c, s, d, d_gain + p, np, n, bands, n_bands, d, d_img + p, P);
+      rc = deconv_apply(c, s, d, d_gain + p, np, n, bands, n_bands, d, d_img + p, P, 1 + i % kHostStreams);
       if (rc == THZ_OK)
         THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
     }

@@ -231,7 +231,7 @@ int thz_deconv_plan_bands(const thz_psf* psf, const thz_deconv_params* prm, cons
     const int vx = (int)floorf(x_maxv), vy = (int)floorf(y_maxv);
     b.kx = 2 * vx + 1;
     b.ky = 2 * vy + 1;
-    if (b.kx > THZ_MAX_PSF || b.ky > THZ_MAX_PSF) return THZ_EINVAL;
+    if (b.kx > THZ_MAX_PSF || b.ky > THZ_MAX_PSF) return THZ_SKIP_PSF_UNSUPPORTED;   // library limit, not a reference skip
     for (int v = -vx; v <= vx; ++v) b.psf_x[v + vx] = (v >= -hx && v <= hx) ? gx[v + hx] / gx_max : 0.0f;
     for (int v = -vy; v <= vy; ++v) b.psf_y[v + vy] = (v >= -hy && v <= hy) ? gy[v + hy] / gy_max : 0.0f;
     b.n_iter = (int)floorf((b.wx - w_min) / (w_max - w_min) * ((float)prm->n_iterations - 1.0f) + 1.0f);

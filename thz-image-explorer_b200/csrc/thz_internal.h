@@ -59,6 +59,7 @@ struct thz_ctx {
   std::vector<KernelEvent> kernel_events;        // resolved after the call's final synchronisation
   bool force_split_apply = false;                // THZ_APPLY_FORM=split: zero-padded split form for pass C (A/B checks)
   bool unstaged_fir = true;                      // FIR passes read the cube directly so that L1 keeps the tables (THZ_FIR_STAGING=on: bulk-copy staging)
+  size_t host_chunk_bytes = (size_t)256 << 20;   // chunk of the host-pointer pipelines (THZ_CHAIN_CHUNK_BYTES, tests shrink it)
   float* d_scratch = nullptr;                    // reductions
   size_t scratch_bytes = 0;
 };
@@ -77,7 +78,8 @@ int get_tables(thz_ctx* c, int n, const FftTables** out);
 int ensure_scratch(thz_ctx* c, size_t bytes);
 // grow-only workspace: returns a device buffer of at least `bytes` for `slot`
 int ws_get(thz_ctx* c, int slot, size_t bytes, void** out);
-enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER, WS_VOX_KERNEL, WS_VOX_HIST, WS_EDGE_CORR };
+enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER, WS_VOX_KERNEL, WS_VOX_HIST,
+       WS_EDGE_CORR /* + lane, lanes 0 .. kHostStreams */, WS_EDGE_CORR_LAST = WS_EDGE_CORR + kHostStreams, WS_END };
 
 // thz_trace.cu
 int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P);
