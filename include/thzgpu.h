@@ -64,6 +64,11 @@ int thz_sync(thz_ctx* ctx);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 int64_t thz_launch_count(const thz_ctx* ctx);
 
+/* FP32 issue-rate microbenchmark on this device (SURVEY.md 8d asks for the fp32 FMA peak measured in the same run
+ * as the Richardson-Lucy FLOP fraction).  mode 0 FFMA, 1 packed fma.rn.f32x2, 2 FADD, 3 packed add, 4 FMUL,
+ * 5 packed mul; result in lane-operations per second (an FMA counts once: multiply by 2 for FLOP/s). */
+int thz_fp32_rate(thz_ctx* ctx, int mode, double* lane_ops_per_s);
+
 int thz_dev_alloc(thz_ctx* ctx, size_t bytes, void** d_ptr);
 int thz_dev_free(thz_ctx* ctx, void* d_ptr);
 int thz_dev_memset(thz_ctx* ctx, void* d_ptr, int value, size_t bytes);
@@ -299,6 +304,10 @@ int thz_deconv_stage_ms(const thz_ctx* ctx, float* ms4);
  * synchronisation; the launches stay asynchronous): ms4 = {band-energy spectra pass, band-energy edge pass, gain-application edge corrections,
  * gain-application main pass}. */
 int thz_deconv_kernel_ms(const thz_ctx* ctx, float* ms4);
+/* Event pairs around the cube kernels of every call between begin and end (same four slots as
+ * thz_deconv_kernel_ms); end synchronises the context. */
+int thz_kernel_timing_begin(thz_ctx* ctx);
+int thz_kernel_timing_end(thz_ctx* ctx, float* ms4 /* nullable */);
 /* Host-pointer drop-in for `Deconvolution::filter`. */
 int thz_deconvolution_host(thz_ctx* ctx, const float* cube, int rows, int cols, int n,
                            const thz_band_plan* bands, int n_bands, float* out, float* img,
@@ -311,6 +320,78 @@ int thz_deconvolution_host(thz_ctx* ctx, const float* cube, int rows, int cols, 
 int thz_chain_host(thz_ctx* ctx, const float* cube, int rows, int cols, int n, const thz_band_plan* bands,
                    int n_bands, float* out, float* img, const volatile uint8_t* abort_flag,
                    thz_progress_fn progress, void* progress_user);
+
+/* thz_chain_host in two calls, for a host that runs the middle part itself (one process per GPU with
+ * thz_slab_rl in between): begin = H2D chunks, fused trace pass, band energies (returns the device pointers of the
+ * energies [n_bands][rows*cols] and of the gain buffer of the same shape); end = gain application, D2H chunks,
+ * intensity map.  With n_bands = 0 begin already downloads the filtered cube and end only fetches the map. */
+int thz_chain_host_begin(thz_ctx* ctx, const float* cube, int rows, int cols, int n, const thz_band_plan* bands,
+                         int n_bands, float* out, float** d_energy, float** d_gain);
+int thz_chain_host_end(thz_ctx* ctx, int rows, int cols, int n, const thz_band_plan* bands, int n_bands, float* out,
+                       float* img);
+
+/* ------------------------------------------------ several GPUs: row slabs ------------------ */
+/* The cube is cut into contiguous row slabs over axis 0 (x), the axis the reference parallelises over
+ * (src/math_tools.rs:333-340); the three cube passes are slab-local.  `richardson_lucy`
+ * (src/filters/deconvolution.rs:620-712) runs on the same slabs of the reflect-padded band image: each rank
+ * iterates its own rows, and the kx/2 boundary rows of `u` (before the first filtering of an iteration, :686-690)
+ * and of the relative blur (before the second, :700-706) are stored straight into the neighbours' halo rows
+ * over NVLink by the filtering kernels themselves, followed by a version flag; only the CTAs that read halo rows
+ * wait for it.  No gather of the band images and no all-reduce of the gains: everything stays slab-local.
+ *
+ * One thz_slab per rank.  Ranks may be processes (one per GPU: exchange the 64-byte handles of
+ * thz_slab_export() with any host transport and call thz_slab_connect_ipc) or live in one process
+ * (thz_slab_connect_local; see also thz_group_* below, which drives all GPUs from one calling thread).
+ *
+ * thz_slab_plan is COLLECTIVE: every rank calls it with the same arguments while all ranks are idle, and a host
+ * barrier separates it from the first thz_slab_rl (the arena holding the halos and flags is zeroed).  *changed:
+ * 0 = same plan as before, 1 = new plan in the old arena, 2 = new arena (export + connect again).
+ * row_bounds[world + 1]: image rows of rank r are [row_bounds[r], row_bounds[r + 1]).  Every slab must be
+ * thicker than three PSF half-heights (THZ_EINVAL otherwise: use fewer ranks for that image). */
+#define THZ_IPC_HANDLE_BYTES 64
+typedef struct thz_slab thz_slab;
+int thz_slab_create(thz_ctx* ctx, int rank, int world, thz_slab** out);
+void thz_slab_destroy(thz_slab* slab);
+int thz_slab_plan(thz_slab* slab, const int* row_bounds, int cols, const thz_band_plan* bands, int n_bands,
+                  int* changed);
+int thz_slab_export(thz_slab* slab, void* handle /* THZ_IPC_HANDLE_BYTES */);
+int thz_slab_connect_ipc(thz_slab* slab, const void* handles /* [world][THZ_IPC_HANDLE_BYTES], by rank */);
+int thz_slab_connect_local(thz_slab* slab, thz_slab* up /* rank - 1 or NULL */, thz_slab* down /* rank + 1 or NULL */);
+int thz_slab_set_stream(thz_slab* slab, void* cuda_stream /* NULL = the context's stream */);
+/* All bands of the plan on this rank's rows: d_energy [n_bands][bstride] (band energies of the slab, row-major
+ * [rows_r][cols]) -> d_gain [n_bands][bstride] = sqrt(max(u, 0) / d), optionally the clamped estimate itself.
+ * Asynchronous on the slab's stream; the abort flag is not polled in this form (a rank that stopped launching
+ * would leave its neighbours waiting): abort between the phases instead. */
+int thz_slab_rl(thz_slab* slab, const float* d_energy, int64_t bstride, float* d_gain, float* d_deconvolved);
+/* The same run for n ranks that share ONE device (tests; hosts with fewer GPUs than slabs): all kernels go to
+ * one stream in dependency order. */
+int thz_slab_rl_serial(thz_slab* const* ranks, int n, const float* const* d_energy, const int64_t* bstride,
+                       float* const* d_gain, float* const* d_deconvolved);
+/* Synchronises the slab's stream; THZ_ECUDA when a halo wait timed out (a neighbour died). */
+int thz_slab_status(thz_slab* slab);
+
+/* One calling thread, several GPUs (the reference drives the chain from its single data thread,
+ * src/data_thread.rs:162-174, 1090-1228).  A group owns one context and one slab per listed device, enables peer
+ * access between neighbours, and runs each phase with one short-lived launching thread per device.  Listing the
+ * same device several times emulates the slabs on one GPU (tests). */
+typedef struct thz_group thz_group;
+int thz_group_create(const int* devices, int n_devices, thz_group** out);
+void thz_group_destroy(thz_group* group);
+int thz_group_size(const thz_group* group);
+thz_ctx* thz_group_ctx(thz_group* group, int rank);
+const char* thz_group_last_error(const thz_group* group);
+/* row_bounds[size + 1] of the partition the group uses for an image of `rows` rows */
+int thz_group_row_bounds(const thz_group* group, int rows, int* row_bounds);
+/* Halo-exchanged Richardson-Lucy of host band images energy[n_bands][rows][cols] -> gain[n_bands][rows][cols] */
+int thz_group_rl_host(thz_group* group, const float* energy, int rows, int cols, const thz_band_plan* bands,
+                      int n_bands, float* gain);
+/* thz_chain_host over all devices of the group: the multipliers of thz_plan_trace, then (n_bands > 0)
+ * `Deconvolution::filter`; host cube [rows][cols][n] in, filtered / deconvolved cube and intensity map out
+ * (out may alias cube).  Every device uploads, filters and downloads its own row slab; the abort flag is polled
+ * between the phases. */
+int thz_group_chain_host(thz_group* group, const float* cube, int rows, int cols, int n, const float* m_pre,
+                         const float* band, const float* m_post, const thz_band_plan* bands, int n_bands, float* out,
+                         float* img, const volatile uint8_t* abort_flag, thz_progress_fn progress, void* progress_user);
 
 /* ------------------------------------------------------- trace pass, host pointers ----- */
 /* Same operators on host arrays (the reference's `ScannedImageFilterData` lives in host

@@ -13,7 +13,7 @@ name is not a Python identifier).
 """
 from __future__ import annotations
 
-from .binding import (Chain, Context, DeviceBuffer, ThzError, lib, library_path, load_library,  # noqa: F401
+from .binding import (Chain, Context, DeviceBuffer, Group, Slab, ThzError, lib, library_path, load_library,  # noqa: F401
                       DECLARED_SYMBOLS)
 from . import host  # noqa: F401,E402
 from . import sharding  # noqa: F401,E402

@@ -178,6 +178,29 @@ def load_library():
         "thz_chain_slot": (i32, [vp, i32] + [C.POINTER(vp)] * 8 + [C.POINTER(i32), C.POINTER(i32)]),
         "thz_chain_fused_result": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "thz_chain_filter_ms": (C.c_double, [vp, C.c_char_p]),
+        "thz_slab_create": (i32, [vp, i32, i32, C.POINTER(vp)]),
+        "thz_slab_destroy": (None, [vp]),
+        "thz_slab_plan": (i32, [vp, C.POINTER(i32), i32, C.POINTER(BandPlanC), i32, C.POINTER(i32)]),
+        "thz_slab_export": (i32, [vp, vp]),
+        "thz_slab_connect_ipc": (i32, [vp, vp]),
+        "thz_slab_connect_local": (i32, [vp, vp, vp]),
+        "thz_slab_set_stream": (i32, [vp, vp]),
+        "thz_slab_rl": (i32, [vp, fp, i64, fp, fp]),
+        "thz_slab_rl_serial": (i32, [C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp)]),
+        "thz_slab_status": (i32, [vp]),
+        "thz_kernel_timing_begin": (i32, [vp]),
+        "thz_kernel_timing_end": (i32, [vp, fp]),
+        "thz_chain_host_begin": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, C.POINTER(vp), C.POINTER(vp)]),
+        "thz_chain_host_end": (i32, [vp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp]),
+        "thz_fp32_rate": (i32, [vp, i32, C.POINTER(C.c_double)]),
+        "thz_group_create": (i32, [C.POINTER(i32), i32, C.POINTER(vp)]),
+        "thz_group_destroy": (None, [vp]),
+        "thz_group_size": (i32, [vp]),
+        "thz_group_ctx": (vp, [vp, i32]),
+        "thz_group_last_error": (C.c_char_p, [vp]),
+        "thz_group_row_bounds": (i32, [vp, i32, C.POINTER(i32)]),
+        "thz_group_rl_host": (i32, [vp, fp, i32, i32, C.POINTER(BandPlanC), i32, fp]),
+        "thz_group_chain_host": (i32, [vp, fp, i32, i32, i32, fp, fp, fp, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_trace_fused_host": (i32, [vp, fp, fp, fp, i64]),
         "thz_trace_forward_host": (i32, [vp, fp, fp, fp, fp, fp, i64]),
         "thz_trace_inverse_host": (i32, [vp, fp, i32, i32, fp, fp, i64]),
@@ -522,6 +545,12 @@ class Context:
                                               C.cast(C.byref(thr), C.c_void_p)))
         return d_o.download(cube.shape), float(thr.value)
 
+    def fp32_rate(self, mode=0):
+        """thz_fp32_rate: lane operations per second of FFMA (0), packed FFMA2 (1), FADD (2), FADD2 (3), FMUL (4), FMUL2 (5)."""
+        v = C.c_double()
+        self._check(lib.thz_fp32_rate(self.handle, int(mode), C.byref(v)))
+        return v.value
+
     def deconv_stage_ms(self):
         ms = np.zeros(4, np.float32)
         self._check(lib.thz_deconv_stage_ms(self.handle, ms.ctypes.data))
@@ -532,6 +561,128 @@ class Context:
         self._check(lib.thz_deconv_kernel_ms(self.handle, ms.ctypes.data))
         return {"energy_spectra_ms": float(ms[0]), "energy_edges_ms": float(ms[1]), "apply_edges_ms": float(ms[2]),
                 "apply_main_ms": float(ms[3])}
+
+
+class Slab:
+    """One rank's share of the row-slab Richardson-Lucy (thz_slab_*): the halo rows travel as peer stores over
+    NVLink inside the filtering kernels.  `plan` is collective (same arguments on every rank, all ranks idle)."""
+
+    IPC_BYTES = 64
+
+    def __init__(self, ctx: Context, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        h = C.c_void_p()
+        ctx._check(lib.thz_slab_create(ctx.handle, self.rank, self.world, C.byref(h)))
+        self.handle = h.value
+
+    def close(self):
+        if self.handle and self.ctx.handle is not None:
+            lib.thz_slab_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def plan(self, row_bounds, cols, bands) -> int:
+        rb = (C.c_int * (self.world + 1))(*[int(v) for v in row_bounds])
+        ch = C.c_int(0)
+        self.ctx._check(lib.thz_slab_plan(self.handle, rb, int(cols), bands, len(bands), C.byref(ch)))
+        return ch.value
+
+    def export(self) -> bytes:
+        buf = (C.c_ubyte * self.IPC_BYTES)()
+        self.ctx._check(lib.thz_slab_export(self.handle, C.addressof(buf)))
+        return bytes(buf)
+
+    def connect_ipc(self, handles_by_rank):
+        blob = b"".join(handles_by_rank)
+        assert len(blob) == self.world * self.IPC_BYTES
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self.ctx._check(lib.thz_slab_connect_ipc(self.handle, C.addressof(buf)))
+
+    def connect_local(self, up: "Slab | None", down: "Slab | None"):
+        self.ctx._check(lib.thz_slab_connect_local(self.handle, up.handle if up else None, down.handle if down else None))
+
+    def rl(self, d_energy, bstride, d_gain, d_deconv=None):
+        self.ctx._check(lib.thz_slab_rl(self.handle, d_energy, int(bstride), d_gain, d_deconv))
+
+    def status(self):
+        self.ctx._check(lib.thz_slab_status(self.handle))
+
+    @staticmethod
+    def rl_serial(slabs, d_energy, bstride, d_gain, d_deconv=None):
+        """All ranks on ONE device, one stream, dependency order (single-GPU emulation of the exchange)."""
+        n = len(slabs)
+        hs = (C.c_void_p * n)(*[s.handle for s in slabs])
+        es = (C.c_void_p * n)(*d_energy)
+        gs = (C.c_void_p * n)(*d_gain)
+        us = (C.c_void_p * n)(*(d_deconv if d_deconv is not None else [None] * n))
+        bs = (C.c_int64 * n)(*[int(b) for b in bstride])
+        slabs[0].ctx._check(lib.thz_slab_rl_serial(hs, n, es, bs, gs, us))
+
+
+class Group:
+    """Several GPUs behind one calling thread (thz_group_*): row slabs, halo-exchanged Richardson-Lucy."""
+
+    def __init__(self, devices):
+        self.handle = None
+        dv = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = lib.thz_group_create(dv, len(devices), C.byref(h))
+        if rc != THZ_OK:
+            raise ThzError(rc, (lib.thz_last_error(None) or b"").decode())
+        self.handle = h.value
+        self.size = len(devices)
+
+    def _check(self, rc):
+        if rc not in (THZ_OK, THZ_ABORTED):
+            raise ThzError(rc, (lib.thz_group_last_error(self.handle) or b"").decode())
+        return rc
+
+    def close(self):
+        if self.handle is not None:
+            lib.thz_group_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def row_bounds(self, rows):
+        b = (C.c_int * (self.size + 1))()
+        self._check(lib.thz_group_row_bounds(self.handle, int(rows), b))
+        return list(b)
+
+    def rl(self, energy, bands):
+        """energy [B][rows][cols] host array -> gains of the same shape."""
+        e = _f32c(energy)
+        nb, rows, cols = e.shape
+        assert nb == len(bands)
+        g = np.empty_like(e)
+        self._check(lib.thz_group_rl_host(self.handle, e.ctypes.data, rows, cols, bands, nb, g.ctypes.data))
+        return g
+
+    def chain(self, cube, m_pre=None, band=None, m_post=None, bands=None):
+        cube = _f32c(cube)
+        rows, cols, n = cube.shape
+        out = np.empty_like(cube)
+        img = np.empty((rows, cols), np.float32)
+        vecs = [None if v is None else _f32c(v) for v in (m_pre, band, m_post)]
+        rc = self._check(lib.thz_group_chain_host(
+            self.handle, cube.ctypes.data, rows, cols, n, *[_ptr(v) for v in vecs], bands,
+            len(bands) if bands is not None else 0, out.ctypes.data, img.ctypes.data, None, None, None))
+        return out, img, rc
 
 
 class Chain:

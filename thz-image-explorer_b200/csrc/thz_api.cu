@@ -782,3 +782,90 @@ int thz_voxel_opacity_dev(thz_ctx* c, const float* d_cube, int n, int64_t P, flo
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// FP32 issue-rate microbenchmark ("fp32 FMA peak to be measured by a microbenchmark in the same
+// run"): the denominator of the Richardson-Lucy FLOP fraction and the evidence behind the choice between scalar
+// and packed (f32x2) arithmetic in the transform kernels.  Every thread runs 16 independent dependency chains.
+// mode 0: FFMA (three register operands)   1: fma.rn.f32x2 (packed, two lanes per instruction)
+//      2: FADD                             3: add.rn.f32x2         4: FMUL      5: mul.rn.f32x2
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fp32_rate(float* out, int iters, float a, float b) {
+  constexpr bool PACKED = (MODE & 1) != 0;
+  // per-thread (vector-register) operands, as in a butterfly: a uniform-register operand would time a cheaper form
+  a += out[threadIdx.x] * 0.0f;
+  b += out[threadIdx.x + 256] * 0.0f;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = a + (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 4; ++rep) {
+      if constexpr (!PACKED) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if constexpr (MODE == 0) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(a), "f"(b));
+          else if constexpr (MODE == 2) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(acc[i]) : "f"(b));
+          else asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(acc[i]) : "f"(a));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          unsigned long long v, ca, cb;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(acc[2 * i]), "f"(acc[2 * i + 1]));
+          asm("mov.b64 %0, {%1, %1};" : "=l"(ca) : "f"(a));
+          asm("mov.b64 %0, {%1, %1};" : "=l"(cb) : "f"(b));
+          if constexpr (MODE == 1) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(ca), "l"(cb));
+          else if constexpr (MODE == 3) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(cb));
+          else asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(ca));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i]), "=f"(acc[2 * i + 1]) : "l"(v));
+        }
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += acc[i];
+  if (s == 12345.678f) out[0] = s;   // never true: keeps the chains alive
+}
+
+extern "C" int thz_fp32_rate(thz_ctx* c, int mode, double* lane_ops_per_s) {
+  CHECK_CTX(c);
+  if (!lane_ops_per_s || mode < 0 || mode > 5) return set_err(c, THZ_EINVAL, "bad mode");
+  void* scratch = nullptr;
+  int rc = ws_get(c, WS_MULT, 4096, &scratch);
+  if (rc != THZ_OK) return rc;
+  const int iters = 4096, threads = 256, blocks = c->sm_count * 8;
+  auto launch = [&](int it) {
+    switch (mode) {
+      case 0: k_fp32_rate<0><<<blocks, threads, 0, c->stream>>>((float*)scratch, it, 1.0000001f, 1e-9f); break;
+      case 1: k_fp32_rate<1><<<blocks, threads, 0, c->stream>>>((float*)scratch, it, 1.0000001f, 1e-9f); break;
+      case 2: k_fp32_rate<2><<<blocks, threads, 0, c->stream>>>((float*)scratch, it, 1.0000001f, 1e-9f); break;
+      case 3: k_fp32_rate<3><<<blocks, threads, 0, c->stream>>>((float*)scratch, it, 1.0000001f, 1e-9f); break;
+      case 4: k_fp32_rate<4><<<blocks, threads, 0, c->stream>>>((float*)scratch, it, 1.0000001f, 1e-9f); break;
+      default: k_fp32_rate<5><<<blocks, threads, 0, c->stream>>>((float*)scratch, it, 1.0000001f, 1e-9f); break;
+    }
+    c->launches++;
+  };
+  launch(64);   // warm-up
+  cudaEvent_t e0, e1;
+  THZ_CUDA(c, cudaEventCreate(&e0));
+  THZ_CUDA(c, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0, c->stream);
+    launch(iters);
+    cudaEventRecord(e1, c->stream);
+    THZ_CUDA(c, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  // per thread and iteration: 4 reps x 16 instructions; a packed instruction works on two lanes
+  const double lanes = (double)blocks * threads * (double)iters * 4.0 * 16.0 * ((mode & 1) ? 2.0 : 1.0);
+  *lane_ops_per_s = lanes / ((double)best * 1e-3);
+  return THZ_OK;
+}

@@ -29,6 +29,7 @@
 
 #include <math.h>
 #include <algorithm>
+#include <type_traits>
 
 namespace thz {
 
@@ -1208,585 +1209,6 @@ __global__ void __launch_bounds__(DGeo<M>::NT, DGeo<M>::kMinBlocks) k_fir_apply(
 }
 
 // ------------------------------------------------------------------------------------
-// Richardson-Lucy: TMA-staged tiled 2-D filtering
-// ------------------------------------------------------------------------------------
-constexpr int kTH = 64, kTW = 64;          // output tile
-constexpr int kMidStride = 68;             // 4 * odd -> conflict-free 128-bit rows
-constexpr int kMaxTaps = 256;              // padded taps per axis
-
-struct ConvArgs {
-  int Hp, Wp, pitch;      // padded-domain image [Hp][pitch], valid width Wp
-  int kx, ky;             // taps along rows (axis 0) and columns (axis 1), both odd
-  int kxp, kyp;           // taps padded to a multiple of 8
-  int box_rows, box_cols; // TMA box: kTH + kx - 1 rows, >= kTW + kyp - 1 columns (4 * odd)
-  const float* wx;        // [kxp] row-direction taps (correlation order), zero padded
-  const float* wy;        // [kyp]
-  const float* wdense;    // [kx][kyp] dense taps (dense kernel) or null
-  const float* d;         // mode 1: relative blur numerator (padded image)
-  float* out;             // mode 0: conv result; mode 1: r = d / (conv + eps); mode 2: u *= conv (in place)
-  float eps;
-  int col_shift;          // tile-grid column offset that keeps the TMA box start 16-byte aligned
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-      : "=r"(ok)
-      : "r"(mbar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(mbar)
-      : "memory");
-}
-
-// correlation: out[i][j] = sum_m sum_n in[i + m - kx/2][j + n - ky/2] * wx[m] * wy[n]
-// MODE 0: out = c;  MODE 1: out = d / (c + eps);  MODE 2: out *= c
-template <int MODE, bool DENSE>
-__global__ void __launch_bounds__(256, 2) k_rl_conv(const __grid_constant__ CUtensorMap tmap, const ConvArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // TMA destinations must be 128-byte aligned: align by hand (the launch adds 128 bytes of slack),
-  // the mbarrier lives in the first 16 bytes of the aligned block
-  unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  uint64_t* mbar_ptr = reinterpret_cast<uint64_t*>(base);
-  float* tile = reinterpret_cast<float*>(base + 128);                     // [box_rows][box_cols]
-  const int tile_floats = a.box_rows * a.box_cols;
-  float* mid = tile + ((tile_floats + 31) & ~31);                         // [box_rows][kMidStride]
-  float* wxs = mid + (DENSE ? 0 : a.box_rows * kMidStride);
-  float* wys = wxs + (DENSE ? 0 : a.kxp);                                 // separable: [kxp] then [kyp]
-  const uint32_t mbar = smem_u32(mbar_ptr);
-  // TMA needs a 16-byte aligned box start: the innermost coordinate col0 - ky/2 must be a multiple of
-  // 4 floats, so the tile grid is shifted left by col_shift in {0, -3, -2, -1} columns
-  const int row0 = blockIdx.y * kTH, col0 = blockIdx.x * kTW + a.col_shift;
-
-  if (threadIdx.x == 0) mbar_init(mbar, 1);
-  if constexpr (DENSE) {
-    for (int i = threadIdx.x; i < a.kx * a.kyp; i += blockDim.x) wxs[i] = a.wdense[i];
-  } else {
-    for (int i = threadIdx.x; i < a.kxp; i += blockDim.x) wxs[i] = a.wx[i];
-    for (int i = threadIdx.x; i < a.kyp; i += blockDim.x) wys[i] = a.wy[i];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(mbar, (uint32_t)(tile_floats * sizeof(float)));
-    tma_load_2d(smem_u32(tile), &tmap, col0 - a.ky / 2, row0 - a.kx / 2, mbar);
-  }
-  while (!mbar_try_wait(mbar, 0)) {
-  }
-
-  const int bc = a.box_cols;
-  if constexpr (!DENSE) {
-    // pass 1: filter along columns (axis 1).  item = (tile row r, group of 8 output columns)
-    const int nitems = a.box_rows * (kTW / 8);
-    for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
-      const int r = it % a.box_rows, cg = it / a.box_rows;
-      const float* src = tile + r * bc + cg * 8;
-      float acc[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-      float win[16];
-      {
-        const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
-        win[0] = v0.x; win[1] = v0.y; win[2] = v0.z; win[3] = v0.w;
-        win[4] = v1.x; win[5] = v1.y; win[6] = v1.z; win[7] = v1.w;
-      }
-      for (int nb = 0; nb < a.kyp; nb += 8) {
-        const float4 v0 = *reinterpret_cast<const float4*>(src + nb + 8);
-        const float4 v1 = *reinterpret_cast<const float4*>(src + nb + 12);
-        win[8] = v0.x; win[9] = v0.y; win[10] = v0.z; win[11] = v0.w;
-        win[12] = v1.x; win[13] = v1.y; win[14] = v1.z; win[15] = v1.w;
-        const float4 w0 = *reinterpret_cast<const float4*>(wys + nb), w1 = *reinterpret_cast<const float4*>(wys + nb + 4);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int n = 0; n < 8; ++n)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[n], win[q + n], acc[q]);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) win[q] = win[q + 8];
-      }
-      float* dst = mid + r * kMidStride + cg * 8;
-      *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
-    __syncthreads();
-  }
-  // pass 2: filter along rows (axis 0).  item = (output column c, group of 8 output rows)
-  {
-    const int nitems = kTW * (kTH / 8);
-    for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
-      const int c = it % kTW, rg = it / kTW;
-      float acc[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-      if constexpr (!DENSE) {
-        const float* src = mid + (rg * 8) * kMidStride + c;
-        float win[16];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) win[q] = src[q * kMidStride];
-        for (int mb = 0; mb < a.kxp; mb += 8) {
-          // rows beyond the box are multiplied by zero taps; clamp the address instead of reading them
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int rr = rg * 8 + mb + 8 + q;
-            win[8 + q] = (rr < a.box_rows) ? mid[rr * kMidStride + c] : 0.f;
-          }
-          const float4 w0 = *reinterpret_cast<const float4*>(wxs + mb), w1 = *reinterpret_cast<const float4*>(wxs + mb + 4);
-          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int n = 0; n < 8; ++n)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[n], win[q + n], acc[q]);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) win[q] = win[q + 8];
-        }
-      } else {
-        // dense taps: out[r][c] = sum_m sum_n tile[r + m][c + n] w[m][n]; 8 consecutive rows per item,
-        // tap rows outermost so that one tap value serves 8 accumulators
-        for (int m = 0; m < a.kx + 7; ++m) {
-          // input row rg*8 + m contributes to output row q with tap row m - q
-          const float* srow = tile + (rg * 8 + m) * bc + c;
-          if (rg * 8 + m >= a.box_rows) break;
-          for (int n = 0; n < a.ky; ++n) {
-            const float v = srow[n];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int mq = m - q;
-              if (mq >= 0 && mq < a.kx) acc[q] = fmaf(v, wxs[mq * a.kyp + n], acc[q]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int gr = row0 + rg * 8 + q, gc = col0 + c;
-        if (gr < a.Hp && gc >= 0 && gc < a.Wp) {
-          const size_t o = (size_t)gr * a.pitch + gc;
-          if constexpr (MODE == 0) a.out[o] = acc[q];
-          else if constexpr (MODE == 1) a.out[o] = a.d[o] / (acc[q] + a.eps);
-          else a.out[o] = a.out[o] * acc[q];
-        }
-      }
-    }
-  }
-}
-
-
-// ------------------------------------------------------------------------------------
-// Persistent separable RL filtering: one CTA per SM loops over the 64x64 output tiles; the haloed
-// input tile of the NEXT tile is fetched by TMA into the other buffer while the current one is
-// filtered (column pass -> row pass -> fused epilogue).  512 threads: 880 column-pass items
-// (row, 8 columns), 512 row-pass items (column, 8 rows).
-// ------------------------------------------------------------------------------------
-constexpr int kRlThreads = 512;
-
-template <int MODE>
-__global__ void __launch_bounds__(kRlThreads, 1) k_rl_conv_persistent(const __grid_constant__ CUtensorMap tmap,
-                                                                      const ConvArgs a, int tiles_x, int tiles_y) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  uint64_t* mbar_ptr = reinterpret_cast<uint64_t*>(base);   // two barriers
-  const int tile_floats = (a.box_rows * a.box_cols + 31) & ~31;
-  float* tile0 = reinterpret_cast<float*>(base + 128);
-  float* tile1 = tile0 + tile_floats;
-  float* mid = tile1 + tile_floats;                           // [box_rows][kMidStride]
-  float* wxs = mid + a.box_rows * kMidStride;
-  float* wys = wxs + a.kxp;
-  const uint32_t mbar[2] = {smem_u32(mbar_ptr), smem_u32(mbar_ptr + 1)};
-  const int ntiles = tiles_x * tiles_y;
-  const uint32_t tile_bytes = (uint32_t)(a.box_rows * a.box_cols * sizeof(float));
-
-  if (threadIdx.x == 0) {
-    mbar_init(mbar[0], 1);
-    mbar_init(mbar[1], 1);
-  }
-  for (int i = threadIdx.x; i < a.kxp; i += blockDim.x) wxs[i] = a.wx[i];
-  for (int i = threadIdx.x; i < a.kyp; i += blockDim.x) wys[i] = a.wy[i];
-  __syncthreads();
-  auto origin = [&](int tidx, int& row0, int& col0) {
-    row0 = (tidx / tiles_x) * kTH;
-    col0 = (tidx % tiles_x) * kTW + a.col_shift;
-  };
-  if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) {
-    int r0, c0;
-    origin(blockIdx.x, r0, c0);
-    mbar_expect_tx(mbar[0], tile_bytes);
-    tma_load_2d(smem_u32(tile0), &tmap, c0 - a.ky / 2, r0 - a.kx / 2, mbar[0]);
-  }
-  const int bc = a.box_cols;
-  uint32_t it = 0;
-  for (int tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x, ++it) {
-    const int buf = it & 1;
-    float* tile = buf ? tile1 : tile0;
-    int row0, col0;
-    origin(tidx, row0, col0);
-    const int nxt = tidx + gridDim.x;
-    if (threadIdx.x == 0 && nxt < ntiles) {   // the other buffer was last read before the barrier that ended
-      int r0, c0;                              // the previous iteration
-      origin(nxt, r0, c0);
-      mbar_expect_tx(mbar[buf ^ 1], tile_bytes);
-      tma_load_2d(smem_u32(buf ? tile0 : tile1), &tmap, c0 - a.ky / 2, r0 - a.kx / 2, mbar[buf ^ 1]);
-    }
-    // epilogue operands: fetch early so that their latency hides behind the column pass
-    const int c = threadIdx.x % kTW, rg = threadIdx.x / kTW;
-    float ep[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int gr = row0 + rg * 8 + q, gc = col0 + c;
-      ep[q] = 0.f;
-      if (MODE != 0 && gr < a.Hp && gc >= 0 && gc < a.Wp) {
-        const size_t o = (size_t)gr * a.pitch + gc;
-        ep[q] = (MODE == 1) ? __ldg(a.d + o) : a.out[o];
-      }
-    }
-    while (!mbar_try_wait(mbar[buf], (it >> 1) & 1)) {
-    }
-    // column pass (axis 1)
-    const int nitems = a.box_rows * (kTW / 8);
-    for (int itx = threadIdx.x; itx < nitems; itx += blockDim.x) {
-      const int r = itx % a.box_rows, cg = itx / a.box_rows;
-      const float* src = tile + r * bc + cg * 8;
-      float acc[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-      float win[16];
-      {
-        const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
-        win[0] = v0.x; win[1] = v0.y; win[2] = v0.z; win[3] = v0.w;
-        win[4] = v1.x; win[5] = v1.y; win[6] = v1.z; win[7] = v1.w;
-      }
-      for (int nb = 0; nb < a.kyp; nb += 8) {
-        const float4 v0 = *reinterpret_cast<const float4*>(src + nb + 8);
-        const float4 v1 = *reinterpret_cast<const float4*>(src + nb + 12);
-        win[8] = v0.x; win[9] = v0.y; win[10] = v0.z; win[11] = v0.w;
-        win[12] = v1.x; win[13] = v1.y; win[14] = v1.z; win[15] = v1.w;
-        const float4 w0 = *reinterpret_cast<const float4*>(wys + nb), w1 = *reinterpret_cast<const float4*>(wys + nb + 4);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int n = 0; n < 8; ++n)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[n], win[q + n], acc[q]);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) win[q] = win[q + 8];
-      }
-      float* dst = mid + r * kMidStride + cg * 8;
-      *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
-    __syncthreads();
-    // row pass (axis 0): one item per thread
-    {
-      float acc[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-      const float* src = mid + (rg * 8) * kMidStride + c;
-      float win[16];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) win[q] = src[q * kMidStride];
-      for (int mb = 0; mb < a.kxp; mb += 8) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int rr = rg * 8 + mb + 8 + q;
-          win[8 + q] = (rr < a.box_rows) ? mid[rr * kMidStride + c] : 0.f;
-        }
-        const float4 w0 = *reinterpret_cast<const float4*>(wxs + mb), w1 = *reinterpret_cast<const float4*>(wxs + mb + 4);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int n = 0; n < 8; ++n)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] = fmaf(wv[n], win[q + n], acc[q]);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) win[q] = win[q + 8];
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int gr = row0 + rg * 8 + q, gc = col0 + c;
-        if (gr < a.Hp && gc >= 0 && gc < a.Wp) {
-          const size_t o = (size_t)gr * a.pitch + gc;
-          if constexpr (MODE == 0) a.out[o] = acc[q];
-          else if constexpr (MODE == 1) a.out[o] = ep[q] / (acc[q] + a.eps);
-          else a.out[o] = ep[q] * acc[q];
-        }
-      }
-    }
-    __syncthreads();   // tile[buf] and mid are free again
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// Streaming separable RL filtering.  A CTA owns a strip of kSW output columns and a segment of
-// output rows and marches down the strip in chunks of kCR input rows: each chunk is fetched by TMA
-// (two buffers, prefetch distance two chunks), filtered along the columns into a ring of
-// column-filtered rows kept in shared memory (stored transposed, so that the row pass reads its
-// taps' axis with 128-bit loads), and the output rows whose whole row support is in the ring are
-// emitted with the fused epilogue.  Every image row is column-filtered once per segment (only the
-// WU warm-up rows of a segment are filtered twice), both passes are exactly one item per thread
-// (16 outputs x T taps), and the ring holds one chunk of slack so that one barrier per chunk suffices.
-//
-// Taps are front-padded with zeros to WU + 1 (rows) / KW + 1 (columns) entries, WU and KW being the
-// true support minus one rounded up to a multiple of 8, so that the window advances in whole
-// 8-element blocks and the last tap is a single trailing step that needs no new data.
-// ------------------------------------------------------------------------------------
-constexpr int kCR = 64;           // input rows per chunk
-// SW = output columns per strip (128: one 512-thread CTA per SM; 64: 256 threads, two CTAs per SM when the
-// buffers fit twice, so that one CTA computes while the other sits at its barrier); SW * kCR / 16 threads:
-// one 16-output item per thread in both passes
-
-struct StreamArgs {
-  int Hp, Wp, pitch;
-  int WU, KW;           // warm-up rows / columns (multiples of 8)
-  int gy_off, gx_off;   // box origin = (segment row 0 - gy_off, strip column 0 - gx_off)
-  int bc;               // box columns (4 * odd, >= SW + KW)
-  int Rg, RS;           // ring rows (multiple of 8, >= 2 kCR + WU) and ring stride in floats (4 * odd)
-  int seg_rows;         // output rows per segment (kCR * chunks - WU)
-  int col_shift;        // keeps the box start 16-byte aligned
-  const float* wx;      // [WU + 8] front-padded row taps, wx[WU] is the last tap
-  const float* wy;      // [KW + 8]
-  const float* d;
-  float* out;
-  float eps;
-};
-
-// logical window element idx in [0, 24) -> register, the three 8-groups rotate with the phase
-__device__ __forceinline__ constexpr int win_phys(int idx, int ph) { return (((idx >> 3) + ph) % 3) * 8 + (idx & 7); }
-
-template <int PH>
-__device__ __forceinline__ void tap_block(float (&acc)[16], float (&W)[24], const float4 n0, const float4 n1,
-                                          const float* __restrict__ w8) {
-  constexpr int g2 = ((2 + PH) % 3) * 8;
-  W[g2 + 0] = n0.x; W[g2 + 1] = n0.y; W[g2 + 2] = n0.z; W[g2 + 3] = n0.w;
-  W[g2 + 4] = n1.x; W[g2 + 5] = n1.y; W[g2 + 6] = n1.z; W[g2 + 7] = n1.w;
-  const float4 wa = *reinterpret_cast<const float4*>(w8), wb = *reinterpret_cast<const float4*>(w8 + 4);
-  const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-  for (int n = 0; n < 8; ++n)
-#pragma unroll
-    for (int q = 0; q < 16; ++q) acc[q] = fmaf(wv[n], W[win_phys(q + n, PH)], acc[q]);
-}
-
-template <int PH>
-__device__ __forceinline__ void tap_last(float (&acc)[16], const float (&W)[24], float wl) {
-#pragma unroll
-  for (int q = 0; q < 16; ++q) acc[q] = fmaf(wl, W[win_phys(q, PH)], acc[q]);
-}
-
-// 16 outputs, T + 1 taps (T a multiple of 8).  L::next() returns the next 8 window elements.
-template <class L>
-__device__ __forceinline__ void run_taps(float (&acc)[16], L& ld, const float* __restrict__ w, int T) {
-  float W[24];
-  float4 a, b;
-  ld.next(a, b);
-  W[0] = a.x; W[1] = a.y; W[2] = a.z; W[3] = a.w; W[4] = b.x; W[5] = b.y; W[6] = b.z; W[7] = b.w;
-  ld.next(a, b);
-  W[8] = a.x; W[9] = a.y; W[10] = a.z; W[11] = a.w; W[12] = b.x; W[13] = b.y; W[14] = b.z; W[15] = b.w;
-  int nb = 0;
-  for (; nb + 24 <= T; nb += 24) {
-    ld.next(a, b);
-    tap_block<0>(acc, W, a, b, w + nb);
-    ld.next(a, b);
-    tap_block<1>(acc, W, a, b, w + nb + 8);
-    ld.next(a, b);
-    tap_block<2>(acc, W, a, b, w + nb + 16);
-  }
-  const int rem = (T - nb) >> 3;
-  const float wl = w[T];
-  if (rem == 0) {
-    tap_last<0>(acc, W, wl);
-  } else if (rem == 1) {
-    ld.next(a, b);
-    tap_block<0>(acc, W, a, b, w + nb);
-    tap_last<1>(acc, W, wl);
-  } else {
-    ld.next(a, b);
-    tap_block<0>(acc, W, a, b, w + nb);
-    ld.next(a, b);
-    tap_block<1>(acc, W, a, b, w + nb + 8);
-    tap_last<2>(acc, W, wl);
-  }
-}
-
-struct LinearLoader {   // consecutive floats of one haloed tile row
-  const float* p;
-  __device__ __forceinline__ void next(float4& a, float4& b) {
-    a = *reinterpret_cast<const float4*>(p);
-    b = *reinterpret_cast<const float4*>(p + 4);
-    p += 8;
-  }
-};
-
-struct RingLoader {     // consecutive ring rows of one column (transposed ring: rows are contiguous)
-  const float* col;
-  int pos, Rg;
-  __device__ __forceinline__ void next(float4& a, float4& b) {
-    a = *reinterpret_cast<const float4*>(col + pos);
-    b = *reinterpret_cast<const float4*>(col + pos + 4);
-    pos += 8;
-    if (pos >= Rg) pos -= Rg;
-  }
-};
-
-template <int MODE, int SW>
-__global__ void __launch_bounds__(SW * 4, (SW == 64) ? 2 : 1) k_rl_stream(const __grid_constant__ CUtensorMap tmap,
-                                                                         const StreamArgs a) {
-  constexpr int kSW = SW, kStThreads = SW * 4;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  const uint32_t mbar0 = smem_u32(base);                       // two barriers, 8 bytes apart
-  const int tile_floats = kCR * a.bc;
-  float* tile0 = reinterpret_cast<float*>(base + 128);
-  float* ring = tile0 + 2 * tile_floats;                       // [kSW][RS]
-  float* wxs = ring + kSW * a.RS;
-  float* wys = wxs + a.WU + 8;
-  const int tid = threadIdx.x;
-  const int col0 = blockIdx.x * kSW + a.col_shift;
-  const int seg_row0 = blockIdx.y * a.seg_rows;
-  const int rows_out = min(a.seg_rows, a.Hp - seg_row0);
-  if (rows_out <= 0) return;
-  const int n_chunks = (rows_out + a.WU + kCR - 1) / kCR;
-  const int gy0 = seg_row0 - a.gy_off, gx0 = col0 - a.gx_off;
-  const uint32_t tile_bytes = (uint32_t)(tile_floats * sizeof(float));
-  // a chunk that lies wholly above or below the image is all zeros: no copy, the ring rows are cleared
-  auto live = [&](int j) { return gy0 + kCR * j < a.Hp && gy0 + kCR * (j + 1) > 0; };
-
-  // programmatic dependent launch: the next kernel of the iteration may be scheduled as soon as every CTA
-  // of this one is running, its prologue (barriers, taps) overlaps our tail; everything that touches the
-  // images comes after griddepcontrol.wait, which returns when the previous kernel has completed
-  asm volatile("griddepcontrol.launch_dependents;");
-  if (tid == 0) {
-    mbar_init(mbar0, 1);
-    mbar_init(mbar0 + 8, 1);
-  }
-  for (int i = tid; i < a.WU + 8; i += kStThreads) wxs[i] = a.wx[i];
-  for (int i = tid; i < a.KW + 8; i += kStThreads) wys[i] = a.wy[i];
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  __syncthreads();
-  if (tid == 0) {
-    for (int j = 0; j < 2 && j < n_chunks; ++j)
-      if (live(j)) {
-        mbar_expect_tx(mbar0 + 8 * j, tile_bytes);
-        tma_load_2d(smem_u32(tile0 + j * tile_floats), &tmap, gx0, gy0 + kCR * j, mbar0 + 8 * j);
-      }
-  }
-  uint32_t ph0 = 0, ph1 = 0;   // mbarrier phase parity per buffer
-  for (int j = 0; j < n_chunks; ++j) {
-    const int buf = j & 1;
-    const bool lv = live(j);
-    // rows that become complete with this chunk, and this thread's share of them in the row pass:
-    // thread = (strip column c, 16 output rows).  The epilogue operands are fetched now, so that their
-    // latency hides behind the column pass even when the PSF is small.
-    const int lo = max(0, j * kCR - a.WU), hi = min(rows_out, (j + 1) * kCR - a.WU);
-    const int c = tid & (kSW - 1), rg = tid / kSW;
-    const int i0 = lo + rg * 16;
-    const int gc = col0 + c;
-    const bool colok = gc >= 0 && gc < a.Wp;
-    const size_t o0 = (size_t)(seg_row0 + i0) * a.pitch + gc;
-    float ep[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      ep[q] = 0.f;
-      if (MODE != 0 && colok && i0 + q < hi) {
-        const size_t o = o0 + (size_t)q * a.pitch;
-        ep[q] = (MODE == 1) ? __ldg(a.d + o) : a.out[o];
-      }
-    }
-    // ---- column pass: thread = (chunk row r, 16 output columns cg*16 ..) ----
-    {
-      const int r = tid & (kCR - 1), cg = tid >> 6;
-      float acc[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-      if (lv) {
-        const uint32_t mb = mbar0 + 8 * buf;
-        while (!mbar_try_wait(mb, buf ? ph1 : ph0)) {
-        }
-        if (buf) ph1 ^= 1; else ph0 ^= 1;
-        LinearLoader ld{tile0 + buf * tile_floats + r * a.bc + cg * 16};
-        run_taps(acc, ld, wys, a.KW);
-      }
-      int pos = (j * kCR + r) % a.Rg;
-      float* dst = ring + (cg * 16) * a.RS + pos;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) dst[q * a.RS] = acc[q];
-    }
-    __syncthreads();   // ring rows of chunk j are visible; tile[buf] is free
-    if (tid == 0 && j + 2 < n_chunks && live(j + 2)) {
-      mbar_expect_tx(mbar0 + 8 * buf, tile_bytes);
-      tma_load_2d(smem_u32(tile0 + buf * tile_floats), &tmap, gx0, gy0 + kCR * (j + 2), mbar0 + 8 * buf);
-    }
-    // ---- row pass ----
-    if (i0 < hi) {
-      float acc[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-      RingLoader ld{ring + c * a.RS, i0 % a.Rg, a.Rg};
-      run_taps(acc, ld, wxs, a.WU);
-      if (colok) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          if (i0 + q < hi) {
-            const size_t o = o0 + (size_t)q * a.pitch;
-            if constexpr (MODE == 0) a.out[o] = acc[q];
-            else if constexpr (MODE == 1) a.out[o] = ep[q] / (acc[q] + a.eps);
-            else a.out[o] = ep[q] * acc[q];
-          }
-        }
-      }
-    }
-  }
-}
-
-// numpy-"reflect" padding exactly as richardson_lucy writes it (deconvolution.rs:638-667)
-__global__ void k_reflect_pad(const float* __restrict__ img, int h, int w, int pad_y, int pad_x, float* __restrict__ out,
-                              int pitch) {
-  const int Hp = h + 2 * pad_y, Wp = w + 2 * pad_x;
-  const int64_t total = (int64_t)Hp * Wp;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / Wp), c = (int)(i % Wp);
-    int sr, sc;
-    if (r < pad_y) sr = pad_y - r;
-    else if (r >= pad_y + h) sr = h - 2 - (r - pad_y - h);
-    else sr = r - pad_y;
-    if (c < pad_x) sc = pad_x - c;
-    else if (c >= pad_x + w) sc = w - 2 - (c - pad_x - w);
-    else sc = c - pad_x;
-    out[(size_t)r * pitch + c] = img[(size_t)sr * w + sc];
-  }
-}
-
-// crop, clamp >= 0, gain = sqrt(u / d)  (deconvolution.rs:708, 975, 990-993)
-__global__ void k_rl_finish(const float* __restrict__ u, int pitch, int pad_y, int pad_x, int h, int w,
-                            const float* __restrict__ d_img, float* __restrict__ deconv, float* __restrict__ gain) {
-  const int64_t total = (int64_t)h * w;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / w), c = (int)(i % w);
-    const float v = fmaxf(u[(size_t)(r + pad_y) * pitch + c + pad_x], 0.0f);
-    if (deconv) deconv[i] = v;
-    if (gain) gain[i] = sqrtf(v / d_img[i]);
-  }
-}
-
-__global__ void k_copy2d(const float* __restrict__ src, int rows, int cols, int spitch, float* __restrict__ dst,
-                         int dpitch) {
-  const int64_t total = (int64_t)rows * cols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cols), c = (int)(i % cols);
-    dst[(size_t)r * dpitch + c] = src[(size_t)r * spitch + c];
-  }
-}
-
-// ------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------
 static int fir_fft_size(int n) {
@@ -2159,7 +1581,7 @@ static void resolve_kernel_events(thz_ctx* c) {
 }
 
 int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
-                    int B, float* d_energy, int64_t bstride = 0) {
+                    int B, float* d_energy, int64_t bstride) {
   if (bstride == 0) bstride = P;
   if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
   if (P == 0) return THZ_OK;
@@ -2213,7 +1635,7 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
 // time (the chunk pipeline of thz_chain_host) must not share one (k_fir_edge_corr of chunk i+1 would overwrite
 // what k_fir_apply_circ of chunk i still reads).  Lane 0 = the context's compute stream, 1 + k = hstream[k].
 int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d_gain, int64_t P, int n,
-                 const thz_band_plan* bands, int B, float* d_out, float* d_img, int64_t bstride = 0, int lane = 0) {
+                 const thz_band_plan* bands, int B, float* d_out, float* d_img, int64_t bstride, int lane) {
   if (bstride == 0) bstride = P;
   if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
   if (P == 0) return THZ_OK;
@@ -2282,325 +1704,77 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
   return rc;
 }
 
-// ---- TMA descriptor -----------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode(thz_ctx* c) {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
-    set_err(c, THZ_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    return nullptr;
-  }
-  fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
-  return fn;
-}
 
-static int make_tmap(thz_ctx* c, CUtensorMap* map, const float* base, int Hp, int Wp, int pitch, int box_rows,
-                     int box_cols) {
-  auto enc = get_encode(c);
-  if (!enc) return THZ_ECUDA;
-  cuuint64_t dims[2] = {(cuuint64_t)Wp, (cuuint64_t)Hp};
-  cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    char buf[128];
-    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-    return set_err(c, THZ_ECUDA, buf);
-  }
-  return THZ_OK;
-}
-
-struct ConvPlan {
-  ConvArgs a{};
-  size_t smem = 0;
-  bool dense = false;
-  float* d_w = nullptr;   // device taps: [wx (kxp) | wy (kyp)] x 2 orientations, or dense [2][kx][kyp]
-  int wstride = 0;        // floats between the two orientations
-  // streaming form (k_rl_stream): used when the strip buffers fit in shared memory
-  bool streaming = false;
-  int sw = 128;           // strip width of the streaming form
-  StreamArgs sa{};
-  size_t ssmem = 0;
-  dim3 sgrid;
-  float* d_ws = nullptr;  // [wx' (WU + 8) | wy' (KW + 8)] x 2 orientations
-  int swstride = 0;
-  int map_rows() const { return streaming ? kCR : a.box_rows; }
-  int map_cols() const { return streaming ? sa.bc : a.box_cols; }
-};
-
-static int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-// taps for conv #1 (u (*) psf) and conv #2 (r (*) mirror) as correlation taps
-static int make_conv_plan(thz_ctx* c, cudaStream_t s, int Hp, int Wp, int pitch, const float* psf_x, int kx,
-                          const float* psf_y, int ky, const float* dense, int direct, ConvPlan& cp) {
-  if (kx < 1 || ky < 1 || (kx & 1) == 0 || (ky & 1) == 0) return set_err(c, THZ_EINVAL, "PSF extents must be odd");
-  if (kx > THZ_MAX_PSF || ky > THZ_MAX_PSF) return set_err(c, THZ_EINVAL, "PSF larger than THZ_MAX_PSF");
-  ConvArgs& a = cp.a;
-  a.Hp = Hp; a.Wp = Wp; a.pitch = pitch; a.kx = kx; a.ky = ky;
-  a.kxp = round_up(kx, 8);
-  a.kyp = round_up(ky, 8);
-  a.box_rows = kTH + kx - 1;
-  int bc = kTW + a.kyp + 8;             // pass 1 reads up to column cg*8 + kyp + 15
-  bc = round_up(bc, 4);
-  if (((bc / 4) & 1) == 0) bc += 4;     // 4 * odd: conflict-free 128-bit row accesses
-  a.box_cols = bc;
-  a.eps = 1e-12f;
-  a.col_shift = ((ky / 2) % 4 == 0) ? 0 : (ky / 2) % 4 - 4;
-  cp.dense = dense != nullptr;
-  if (a.box_rows > 256 || a.box_cols > 256) return set_err(c, THZ_EINVAL, "PSF too large for one TMA box");
-  const int tile_floats = (a.box_rows * a.box_cols + 31) & ~31;
-  std::vector<float> w;
-  if (!cp.dense) {
-    cp.smem = (size_t)(tile_floats + a.box_rows * kMidStride + a.kxp + a.kyp) * sizeof(float) + 256;
-    cp.wstride = a.kxp + a.kyp;
-    w.assign(2 * cp.wstride, 0.f);
-    // orientation 0 = first conv of the iteration (u with psf), 1 = second (r with the mirrored psf).
-    // direct branch: correlation with the given kernel; FFT branch: convolution = correlation with the flip.
-    for (int o = 0; o < 2; ++o) {
-      const bool flip = (o == 0) ? (direct == 0) : (direct != 0);
-      for (int i = 0; i < kx; ++i) w[o * cp.wstride + i] = psf_x[flip ? kx - 1 - i : i];
-      for (int j = 0; j < ky; ++j) w[o * cp.wstride + a.kxp + j] = psf_y[flip ? ky - 1 - j : j];
-    }
-  } else {
-    cp.smem = (size_t)(tile_floats + kx * a.kyp) * sizeof(float) + 256;
-    cp.wstride = kx * a.kyp;
-    w.assign(2 * cp.wstride, 0.f);
-    for (int o = 0; o < 2; ++o) {
-      const bool flip = (o == 0) ? (direct == 0) : (direct != 0);
-      for (int i = 0; i < kx; ++i)
-        for (int j = 0; j < ky; ++j)
-          w[o * cp.wstride + i * a.kyp + j] = dense[(flip ? kx - 1 - i : i) * ky + (flip ? ky - 1 - j : j)];
-    }
-  }
-  if (cp.smem > 227 * 1024) return set_err(c, THZ_EINVAL, "PSF too large for the shared-memory tile");
-  const size_t w_tile = w.size();
-  if (!cp.dense) {
-    StreamArgs& sa = cp.sa;
-    sa.Hp = Hp; sa.Wp = Wp; sa.pitch = pitch;
-    sa.WU = round_up(kx - 1, 8);
-    sa.KW = round_up(ky - 1, 8);
-    const int padx = sa.WU - (kx - 1), pady = sa.KW - (ky - 1);
-    sa.gy_off = kx / 2 + padx;
-    sa.gx_off = ky / 2 + pady;
-    sa.Rg = 2 * kCR + sa.WU;
-    sa.RS = sa.Rg + 4;
-    if (((sa.RS / 4) & 1) == 0) sa.RS += 4;
-    sa.col_shift = (sa.gx_off % 4 == 0) ? 0 : (sa.gx_off % 4) - 4;
-    sa.eps = a.eps;
-    auto box_cols = [&](int sw) {
-      int v = round_up(sw + sa.KW, 4);
-      if (((v / 4) & 1) == 0) v += 4;
-      return v;
-    };
-    auto smem_of = [&](int sw) {
-      return (size_t)(2 * kCR * box_cols(sw) + sw * sa.RS + sa.WU + 8 + sa.KW + 8) * sizeof(float) + 256;
-    };
-    // two 64-column CTAs per SM when both fit (each CTA also pays 1 KB of driver-reserved shared memory)
-    cp.sw = (2 * (smem_of(64) + 1024) <= 228 * 1024) ? 64 : 128;
-    sa.bc = box_cols(cp.sw);
-    cp.ssmem = smem_of(cp.sw);
-    cp.streaming = cp.ssmem <= 227 * 1024 && sa.bc <= 256;
-    if (cp.streaming) {
-      // segments: as many per strip as fill the resident CTA slots once, each a whole number of chunks
-      const int strips = (Wp - sa.col_shift + cp.sw - 1) / cp.sw;
-      const int slots = c->sm_count * (cp.sw == 64 ? 2 : 1);
-      int segs = std::max(1, slots / strips);
-      segs = std::min(segs, (Hp + kCR - 1) / kCR);
-      const int per_seg = (Hp + segs - 1) / segs;
-      const int chunks = (per_seg + sa.WU + kCR - 1) / kCR;
-      sa.seg_rows = chunks * kCR - sa.WU;
-      segs = (Hp + sa.seg_rows - 1) / sa.seg_rows;
-      cp.sgrid = dim3(strips, segs);
-      cp.swstride = sa.WU + 8 + sa.KW + 8;
-      w.resize(w_tile + 2 * cp.swstride, 0.f);
-      for (int o = 0; o < 2; ++o) {
-        const bool flip = (o == 0) ? (direct == 0) : (direct != 0);
-        float* wx = w.data() + w_tile + o * cp.swstride;
-        float* wy = wx + sa.WU + 8;
-        for (int i = 0; i < kx; ++i) wx[padx + i] = psf_x[flip ? kx - 1 - i : i];
-        for (int j = 0; j < ky; ++j) wy[pady + j] = psf_y[flip ? ky - 1 - j : j];
-      }
-    }
-  }
-  void* dp = nullptr;
-  int rc = ws_get(c, WS_RL_TAPS, w.size() * sizeof(float), &dp);
+// ---- the two cube-touching halves of the host-pointer chain (thz_chain_host, thz_group_chain_host) ----
+// in : H2D chunks -> fused trace pass -> band energies; the filtered cube stays in WS_HOST_CUBE, the intensity in
+//      WS_HOST_IMG, the energies in WS_ENERGY [n_bands][P].  Without bands the filtered chunks go straight back.
+int chain_pass_in(thz_ctx* c, const float* cube, int64_t P, int n, const thz_band_plan* bands, int n_bands, float* out,
+                  float** d_energy_out, float** d_gain_out) {
+  if (c->plan.n != n) return set_err(c, THZ_ESTATE, "thz_plan_trace(n, ...) must be called first");
+  if (!cube || !out) return set_err(c, THZ_EINVAL, "null pointer");
+  if (n_bands < 0 || n_bands > THZ_MAX_BANDS || (n_bands > 0 && !bands)) return set_err(c, THZ_EINVAL, "bad bands");
+  void *pc = nullptr, *pi = nullptr, *pe = nullptr, *pg = nullptr;
+  int rc = ws_get(c, WS_HOST_CUBE, (size_t)P * n * sizeof(float), &pc);
+  if (rc == THZ_OK) rc = ws_get(c, WS_HOST_IMG, (size_t)P * sizeof(float), &pi);
+  if (rc == THZ_OK && n_bands) rc = ws_get(c, WS_ENERGY, (size_t)n_bands * P * sizeof(float), &pe);
+  if (rc == THZ_OK && n_bands) rc = ws_get(c, WS_GAIN, (size_t)n_bands * P * sizeof(float), &pg);
   if (rc != THZ_OK) return rc;
-  cp.d_w = (float*)dp;
-  cp.d_ws = cp.d_w + w_tile;
-  THZ_CUDA(c, cudaStreamSynchronize(s));   // the previous band's kernels are done with the taps
-  THZ_CUDA(c, cudaMemcpyAsync(cp.d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-  THZ_CUDA(c, cudaStreamSynchronize(s));
-  return THZ_OK;
-}
-
-template <int MODE>
-static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUtensorMap& map, int orient,
-                       const float* d, float* out) {
-  ConvArgs a = cp.a;
-  if (cp.dense) {
-    a.wdense = cp.d_w + (size_t)orient * cp.wstride;
-  } else {
-    a.wx = cp.d_w + (size_t)orient * cp.wstride;
-    a.wy = a.wx + a.kxp;
+  float *d_cube = (float*)pc, *d_img = (float*)pi, *d_energy = (float*)pe;
+  if (d_energy_out) *d_energy_out = d_energy;
+  if (d_gain_out) *d_gain_out = (float*)pg;
+  // FIR tables are built (and cached) before the pipelined loop so that no chunk waits on the host
+  if (n_bands) {
+    FirTables ft;
+    rc = upload_fir_tables(c, c->stream, n, bands, n_bands, ft);
+    if (rc != THZ_OK) return rc;
   }
-  a.d = d;
-  a.out = out;
-  dim3 grid((a.Wp - a.col_shift + kTW - 1) / kTW, (a.Hp + kTH - 1) / kTH);
-  cudaError_t e;
-  if (cp.streaming) {
-    StreamArgs sa = cp.sa;
-    sa.wx = cp.d_ws + (size_t)orient * cp.swstride;
-    sa.wy = sa.wx + sa.WU + 8;
-    sa.d = d;
-    sa.out = out;
-    auto launch = [&](auto kernel, int threads) -> cudaError_t {
-      const void* skey = (const void*)kernel;
-      size_t& shave = c->smem_set[skey];
-      if (shave < cp.ssmem) {
-        cudaError_t e2 = cudaFuncSetAttribute(skey, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.ssmem);
-        if (e2 != cudaSuccess) return e2;
-        shave = cp.ssmem;
-      }
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = cp.sgrid;
-      cfg.blockDim = dim3(threads);
-      cfg.dynamicSmemBytes = cp.ssmem;
-      cfg.stream = s;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      return cudaLaunchKernelEx(&cfg, kernel, map, sa);
-    };
-    e = (cp.sw == 64) ? launch(k_rl_stream<MODE, 64>, 256) : launch(k_rl_stream<MODE, 128>, 512);
-    c->launches++;
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_stream launch");
-    return THZ_OK;
-  }
-  if (!cp.dense) {
-    // persistent, double-buffered form: two haloed tiles + the intermediate tile
-    const int tile_floats = (a.box_rows * a.box_cols + 31) & ~31;
-    const size_t smem = (size_t)(2 * tile_floats + a.box_rows * kMidStride + a.kxp + a.kyp) * sizeof(float) + 256;
-    if (smem <= 227 * 1024) {
-      const void* pkey = (const void*)k_rl_conv_persistent<MODE>;
-      size_t& phave = c->smem_set[pkey];
-      if (phave < smem) {
-        e = cudaFuncSetAttribute(pkey, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl persistent)");
-        phave = smem;
-      }
-      const int ntiles = (int)(grid.x * grid.y);
-      const int nb = std::min(ntiles, c->sm_count);
-      k_rl_conv_persistent<MODE><<<nb, kRlThreads, smem, s>>>(map, a, (int)grid.x, (int)grid.y);
-      c->launches++;
-      e = cudaGetLastError();
-      if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_conv_persistent launch");
-      return THZ_OK;
+  int64_t ct = (int64_t)c->host_chunk_bytes / ((int64_t)n * 4);   // 256 MiB chunks (THZ_CHAIN_CHUNK_BYTES), whole pairs
+  ct &= ~(int64_t)1;
+  if (ct < 2) ct = 2;
+  int i = 0;
+  for (int64_t p = 0; p < P && rc == THZ_OK; p += ct, ++i) {
+    const int64_t np = std::min(ct, P - p);
+    cudaStream_t s = c->hstream[i % kHostStreams];
+    float* d = d_cube + p * n;
+    THZ_CUDA(c, cudaMemcpyAsync(d, cube + p * n, (size_t)np * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = launch_trace_fused(c, s, d, d, d_img + p, np);
+    if (rc == THZ_OK && n_bands) rc = deconv_energies(c, s, d, np, n, bands, n_bands, d_energy + p, P);
+    if (rc == THZ_OK && !n_bands) {
+      THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
   }
-  const void* key = cp.dense ? (const void*)k_rl_conv<MODE, true> : (const void*)k_rl_conv<MODE, false>;
-  size_t& have = c->smem_set[key];
-  if (have < cp.smem) {
-    e = cudaFuncSetAttribute(key, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);
-    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl)");
-    have = cp.smem;
-  }
-  if (cp.dense) k_rl_conv<MODE, true><<<grid, 256, cp.smem, s>>>(map, a);
-  else k_rl_conv<MODE, false><<<grid, 256, cp.smem, s>>>(map, a);
-  c->launches++;
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_conv launch");
-  return THZ_OK;
-}
-
-static int grid_for(thz_ctx* c, int64_t total) {
-  int64_t b = (total + 255) / 256;
-  const int64_t cap = (int64_t)c->sm_count * 8;
-  return (int)std::max<int64_t>(1, std::min(b, cap));
-}
-
-int conv2d_once(thz_ctx* c, cudaStream_t s, const float* d_in, int rows, int cols, const float* psf_x, int kx,
-                const float* psf_y, int ky, const float* dense, int direct, float* d_out) {
-  if (!d_in || !d_out || rows < 1 || cols < 1) return set_err(c, THZ_EINVAL, "bad image");
-  const int pitch = round_up(cols, 4);
-  void *pa = nullptr, *pb = nullptr;
-  int rcw = ws_get(c, WS_CONV_A, (size_t)rows * pitch * sizeof(float), &pa);
-  if (rcw == THZ_OK) rcw = ws_get(c, WS_CONV_B, (size_t)rows * pitch * sizeof(float), &pb);
-  if (rcw != THZ_OK) return rcw;
-  float *d_a = (float*)pa, *d_b = (float*)pb;
-  k_copy2d<<<grid_for(c, (int64_t)rows * cols), 256, 0, s>>>(d_in, rows, cols, cols, d_a, pitch);
-  c->launches++;
-  ConvPlan cp;
-  int rc = make_conv_plan(c, s, rows, cols, pitch, psf_x, kx, psf_y, ky, dense, direct ? 1 : 0, cp);
-  CUtensorMap map;
-  if (rc == THZ_OK) rc = make_tmap(c, &map, d_a, rows, cols, pitch, cp.map_rows(), cp.map_cols());
-  // orientation 0 is "the kernel as given": correlation when direct, convolution otherwise
-  if (rc == THZ_OK) rc = launch_conv<0>(c, s, cp, map, 0, nullptr, d_b);
-  if (rc == THZ_OK) {
-    k_copy2d<<<grid_for(c, (int64_t)rows * cols), 256, 0, s>>>(d_b, rows, cols, pitch, d_out, cols);
-    c->launches++;
-  }
-  cudaStreamSynchronize(s);
-  cudaError_t e = cudaGetLastError();
-  if (rc == THZ_OK && e != cudaSuccess) return cuda_fail(c, e, "conv2d");
+  for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
   return rc;
 }
 
-int richardson_lucy(thz_ctx* c, cudaStream_t s, const float* d_image, int rows, int cols, const float* psf_x, int kx,
-                    const float* psf_y, int ky, const float* dense, int direct, int n_iter, float* d_deconv,
-                    float* d_gain, const volatile uint8_t* abort_flag, thz_progress_fn progress, void* puser,
-                    float pbase, float pspan) {
-  if (!d_image || rows < 2 || cols < 2) return set_err(c, THZ_EINVAL, "bad image");
-  const int pad_y = kx / 2, pad_x = ky / 2;   // psf.nrows()/2 pads axis 0 (deconvolution.rs:629-631)
-  if (pad_y >= rows - 1 || pad_x >= cols - 1) return set_err(c, THZ_EINVAL, "PSF larger than the image");
-  const int Hp = rows + 2 * pad_y, Wp = cols + 2 * pad_x, pitch = round_up(Wp, 4);
-  const size_t img_bytes = (size_t)Hp * pitch * sizeof(float);
-  void *pd = nullptr, *pu = nullptr, *pr = nullptr;
-  int rcw = ws_get(c, WS_RL_D, img_bytes, &pd);
-  if (rcw == THZ_OK) rcw = ws_get(c, WS_RL_U, img_bytes, &pu);
-  if (rcw == THZ_OK) rcw = ws_get(c, WS_RL_R, img_bytes, &pr);
-  if (rcw != THZ_OK) return rcw;
-  float *d_d = (float*)pd, *d_u = (float*)pu, *d_r = (float*)pr;
-  THZ_CUDA(c, cudaMemsetAsync(d_d, 0, img_bytes, s));
-  k_reflect_pad<<<grid_for(c, (int64_t)Hp * Wp), 256, 0, s>>>(d_image, rows, cols, pad_y, pad_x, d_d, pitch);
-  c->launches++;
-  THZ_CUDA(c, cudaMemcpyAsync(d_u, d_d, img_bytes, cudaMemcpyDeviceToDevice, s));
-  THZ_CUDA(c, cudaMemsetAsync(d_r, 0, img_bytes, s));
-  ConvPlan cp;
-  int rc = make_conv_plan(c, s, Hp, Wp, pitch, psf_x, kx, psf_y, ky, dense, direct ? 1 : 0, cp);
-  CUtensorMap map_u, map_r;
-  if (rc == THZ_OK) rc = make_tmap(c, &map_u, d_u, Hp, Wp, pitch, cp.map_rows(), cp.map_cols());
-  if (rc == THZ_OK) rc = make_tmap(c, &map_r, d_r, Hp, Wp, pitch, cp.map_rows(), cp.map_cols());
-  bool aborted = false;
-  for (int it = 0; rc == THZ_OK && it < n_iter; ++it) {
-    rc = launch_conv<1>(c, s, cp, map_u, 0, d_d, d_r);          // r = d / (u (*) psf + eps)
-    if (rc == THZ_OK) rc = launch_conv<2>(c, s, cp, map_r, 1, nullptr, d_u);   // u *= r (*) mirror
-    if ((it & 15) == 15 || it == n_iter - 1) {
-      if (abort_flag && *abort_flag) { aborted = true; break; }
-      if (progress || abort_flag) {
-        cudaError_t e = cudaStreamSynchronize(s);   // keep the queue short so that abort is responsive
-        if (e != cudaSuccess) { rc = cuda_fail(c, e, "richardson_lucy"); break; }
-        if (progress) progress(pbase + pspan * (float)(it + 1) / (float)n_iter, puser);
-      }
+// out: gain application chunks overlapped with their D2H copies, then the intensity image
+int chain_pass_out(thz_ctx* c, int64_t P, int n, const thz_band_plan* bands, int n_bands, float* out, float* img) {
+  float* d_cube = (float*)c->ws[WS_HOST_CUBE].first;
+  float* d_img = (float*)c->ws[WS_HOST_IMG].first;
+  float* d_gain = n_bands ? (float*)c->ws[WS_GAIN].first : nullptr;
+  if (!d_cube || !d_img || (n_bands && !d_gain)) return set_err(c, THZ_ESTATE, "chain_pass_in has not run");
+  int rc = THZ_OK;
+  if (n_bands) {
+    int64_t ct = (int64_t)c->host_chunk_bytes / ((int64_t)n * 4);
+    ct &= ~(int64_t)1;
+    if (ct < 2) ct = 2;
+    int i = 0;
+    for (int64_t p = 0; p < P && rc == THZ_OK; p += ct, ++i) {
+      const int64_t np = std::min(ct, P - p);
+      cudaStream_t s = c->hstream[i % kHostStreams];
+      float* d = d_cube + p * n;
+      rc = deconv_apply(c, s, d, d_gain + p, np, n, bands, n_bands, d, d_img + p, P, 1 + i % kHostStreams);
+      if (rc == THZ_OK)
+        THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
+    for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
+    if (rc != THZ_OK) return rc;
   }
-  if (rc == THZ_OK && !aborted) {
-    k_rl_finish<<<grid_for(c, (int64_t)rows * cols), 256, 0, s>>>(d_u, pitch, pad_y, pad_x, rows, cols, d_image,
-                                                                  d_deconv, d_gain);
-    c->launches++;
+  if (img) {
+    THZ_CUDA(c, cudaMemcpyAsync(img, d_img, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    THZ_CUDA(c, cudaStreamSynchronize(c->stream));
   }
-  cudaError_t e = cudaStreamSynchronize(s);
-  if (rc == THZ_OK && e != cudaSuccess) return cuda_fail(c, e, "richardson_lucy");
-  if (rc == THZ_OK && aborted) return THZ_ABORTED;
-  return rc;
+  return THZ_OK;
 }
 
 }  // namespace thz
@@ -2626,38 +1800,6 @@ int thz_deconv_apply_dev(thz_ctx* c, const float* d_cube, const float* d_gain, i
                          const thz_band_plan* bands, int n_bands, float* d_out, float* d_img) {
   CHECK_CTX(c);
   return deconv_apply(c, c->stream, d_cube, d_gain, P, n, bands, n_bands, d_out, d_img);
-}
-
-int thz_rl_separable_dev(thz_ctx* c, const float* d_image, int rows, int cols, const float* psf_x, int kx,
-                         const float* psf_y, int ky, int direct, int n_iter, float* d_deconvolved, float* d_gain,
-                         const volatile uint8_t* abort_flag, thz_progress_fn progress, void* progress_user,
-                         float progress_base, float progress_span) {
-  CHECK_CTX(c);
-  if (!psf_x || !psf_y) return set_err(c, THZ_EINVAL, "null PSF");
-  return richardson_lucy(c, c->stream, d_image, rows, cols, psf_x, kx, psf_y, ky, nullptr, direct, n_iter,
-                         d_deconvolved, d_gain, abort_flag, progress, progress_user, progress_base, progress_span);
-}
-
-int thz_rl_dense_dev(thz_ctx* c, const float* d_image, int rows, int cols, const float* psf, int kx, int ky, int direct,
-                     int n_iter, float* d_deconvolved, float* d_gain, const volatile uint8_t* abort_flag) {
-  CHECK_CTX(c);
-  if (!psf) return set_err(c, THZ_EINVAL, "null PSF");
-  return richardson_lucy(c, c->stream, d_image, rows, cols, nullptr, kx, nullptr, ky, psf, direct, n_iter,
-                         d_deconvolved, d_gain, abort_flag, nullptr, nullptr, 0.f, 0.f);
-}
-
-int thz_conv2d_separable_dev(thz_ctx* c, const float* d_in, int rows, int cols, const float* psf_x, int kx,
-                             const float* psf_y, int ky, int direct, float* d_out) {
-  CHECK_CTX(c);
-  if (!psf_x || !psf_y) return set_err(c, THZ_EINVAL, "null PSF");
-  return conv2d_once(c, c->stream, d_in, rows, cols, psf_x, kx, psf_y, ky, nullptr, direct, d_out);
-}
-
-int thz_conv2d_dense_dev(thz_ctx* c, const float* d_in, int rows, int cols, const float* psf, int kx, int ky,
-                         int direct, float* d_out) {
-  CHECK_CTX(c);
-  if (!psf) return set_err(c, THZ_EINVAL, "null PSF");
-  return conv2d_once(c, c->stream, d_in, rows, cols, nullptr, kx, nullptr, ky, psf, direct, d_out);
 }
 
 int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, int n, const thz_band_plan* bands,
@@ -2704,6 +1846,48 @@ int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, i
   return rc;
 }
 
+// CUDA-event pairs around the cube kernels of ANY call between begin and end (the sharded path calls the passes
+// one by one); end synchronises the context's streams and returns the sums like thz_deconv_kernel_ms.
+int thz_kernel_timing_begin(thz_ctx* c) {
+  CHECK_CTX(c);
+  resolve_kernel_events(c);
+  for (float& v : c->kernel_ms) v = 0.f;
+  c->time_kernels = true;
+  return THZ_OK;
+}
+
+int thz_kernel_timing_end(thz_ctx* c, float* ms4) {
+  CHECK_CTX(c);
+  c->time_kernels = false;
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < kHostStreams; ++i) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[i]));
+  resolve_kernel_events(c);
+  if (ms4)
+    for (int i = 0; i < 4; ++i) ms4[i] = c->kernel_ms[i];
+  return THZ_OK;
+}
+
+// The two cube-touching halves of thz_chain_host as separate calls, for hosts that run their own middle part
+// (one process per GPU: thz_slab_rl between them).  begin leaves the filtered slab, its band energies
+// [n_bands][P] and room for the gains [n_bands][P] on the device and returns the two pointers; end applies the
+// gains found there and downloads.
+int thz_chain_host_begin(thz_ctx* c, const float* cube, int rows, int cols, int n, const thz_band_plan* bands,
+                         int n_bands, float* out, float** d_energy, float** d_gain) {
+  CHECK_CTX(c);
+  const int64_t P = (int64_t)rows * cols;
+  if (P == 0) return THZ_OK;
+  return chain_pass_in(c, cube, P, n, bands, n_bands, out, d_energy, d_gain);
+}
+
+int thz_chain_host_end(thz_ctx* c, int rows, int cols, int n, const thz_band_plan* bands, int n_bands, float* out,
+                       float* img) {
+  CHECK_CTX(c);
+  const int64_t P = (int64_t)rows * cols;
+  if (P == 0) return THZ_OK;
+  if (!out) return set_err(c, THZ_EINVAL, "null pointer");
+  return chain_pass_out(c, P, n, bands, n_bands, out, img);
+}
+
 int thz_deconv_stage_ms(const thz_ctx* c, float* ms4) {
   if (!c || !ms4) return THZ_EINVAL;
   for (int i = 0; i < 4; ++i) ms4[i] = c->stage_ms[i];
@@ -2747,41 +1931,11 @@ int thz_chain_host(thz_ctx* c, const float* cube, int rows, int cols, int n, con
                    float* out, float* img, const volatile uint8_t* abort_flag, thz_progress_fn progress,
                    void* progress_user) {
   CHECK_CTX(c);
-  if (c->plan.n != n) return set_err(c, THZ_ESTATE, "thz_plan_trace(n, ...) must be called first");
   const int64_t P = (int64_t)rows * cols;
   if (P == 0) return THZ_OK;
-  if (!cube || !out) return set_err(c, THZ_EINVAL, "null pointer");
-  if (n_bands < 0 || n_bands > THZ_MAX_BANDS || (n_bands > 0 && !bands)) return set_err(c, THZ_EINVAL, "bad bands");
-  void *pc = nullptr, *pi = nullptr, *pe = nullptr, *pg = nullptr;
-  int rc = ws_get(c, WS_HOST_CUBE, (size_t)P * n * sizeof(float), &pc);
-  if (rc == THZ_OK) rc = ws_get(c, WS_HOST_IMG, (size_t)P * sizeof(float), &pi);
-  if (rc == THZ_OK && n_bands) rc = ws_get(c, WS_ENERGY, (size_t)n_bands * P * sizeof(float), &pe);
-  if (rc == THZ_OK && n_bands) rc = ws_get(c, WS_GAIN, (size_t)n_bands * P * sizeof(float), &pg);
-  if (rc != THZ_OK) return rc;
-  float *d_cube = (float*)pc, *d_img = (float*)pi, *d_energy = (float*)pe, *d_gain = (float*)pg;
   if (progress) progress(0.0f, progress_user);
-  // FIR tables are built (and cached) before the pipelined loop so that no chunk waits on the host
-  if (n_bands) {
-    FirTables ft;
-    rc = upload_fir_tables(c, c->stream, n, bands, n_bands, ft);
-    if (rc != THZ_OK) return rc;
-  }
-  int64_t ct = (int64_t)c->host_chunk_bytes / ((int64_t)n * 4);   // 256 MiB chunks (THZ_CHAIN_CHUNK_BYTES), whole pairs
-  ct &= ~(int64_t)1;
-  if (ct < 2) ct = 2;
-  int i = 0;
-  for (int64_t p = 0; p < P && rc == THZ_OK; p += ct, ++i) {
-    const int64_t np = std::min(ct, P - p);
-    cudaStream_t s = c->hstream[i % kHostStreams];
-    float* d = d_cube + p * n;
-    THZ_CUDA(c, cudaMemcpyAsync(d, cube + p * n, (size_t)np * n * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = launch_trace_fused(c, s, d, d, d_img + p, np);
-    if (rc == THZ_OK && n_bands) rc = deconv_energies(c, s, d, np, n, bands, n_bands, d_energy + p, P);
-    if (rc == THZ_OK && !n_bands) {
-      THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    }
-  }
-  for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
+  float *d_energy = nullptr, *d_gain = nullptr;
+  int rc = chain_pass_in(c, cube, P, n, bands, n_bands, out, &d_energy, &d_gain);
   if (rc != THZ_OK) return rc;
   if (n_bands) {
     long total_iter = 0, done_iter = 0;
@@ -2796,24 +1950,10 @@ int thz_chain_host(thz_ctx* c, const float* cube, int rows, int cols, int n, con
       done_iter += std::max(bands[b].n_iter, 1);
     }
     if (rc != THZ_OK) return rc;
-    i = 0;
-    for (int64_t p = 0; p < P && rc == THZ_OK; p += ct, ++i) {
-      const int64_t np = std::min(ct, P - p);
-      cudaStream_t s = c->hstream[i % kHostStreams];
-      float* d = d_cube + p * n;
-      rc = deconv_apply(c, s, d, d_gain + p, np, n, bands, n_bands, d, d_img + p, P, 1 + i % kHostStreams);
-      if (rc == THZ_OK)
-        THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    }
-    for (int k = 0; k < kHostStreams; ++k) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[k]));
-    if (rc != THZ_OK) return rc;
   }
-  if (img) {
-    THZ_CUDA(c, cudaMemcpyAsync(img, d_img, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    THZ_CUDA(c, cudaStreamSynchronize(c->stream));
-  }
-  if (progress) progress(1.0f, progress_user);
-  return THZ_OK;
+  rc = chain_pass_out(c, P, n, bands, n_bands, out, img);
+  if (rc == THZ_OK && progress) progress(1.0f, progress_user);
+  return rc;
 }
 
 }  // extern "C"

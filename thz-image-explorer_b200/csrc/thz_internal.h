@@ -34,6 +34,22 @@ struct TracePlan {
 
 constexpr int kHostStreams = 3;
 
+// thz_deconv.cu (FIR passes A and C)
+int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
+                    int B, float* d_energy, int64_t bstride = 0);
+int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d_gain, int64_t P, int n,
+                 const thz_band_plan* bands, int B, float* d_out, float* d_img, int64_t bstride = 0, int lane = 0);
+int chain_pass_in(thz_ctx* c, const float* cube, int64_t P, int n, const thz_band_plan* bands, int n_bands, float* out,
+                  float** d_energy_out, float** d_gain_out);
+int chain_pass_out(thz_ctx* c, int64_t P, int n, const thz_band_plan* bands, int n_bands, float* out, float* img);
+// thz_rl.cu
+int conv2d_once(thz_ctx* c, cudaStream_t s, const float* d_in, int rows, int cols, const float* psf_x, int kx,
+                const float* psf_y, int ky, const float* dense, int direct, float* d_out);
+int richardson_lucy(thz_ctx* c, cudaStream_t s, const float* d_image, int rows, int cols, const float* psf_x, int kx,
+                    const float* psf_y, int ky, const float* dense, int direct, int n_iter, float* d_deconv,
+                    float* d_gain, const volatile uint8_t* abort_flag, thz_progress_fn progress, void* puser,
+                    float pbase, float pspan);
+
 }  // namespace thz
 
 struct thz_ctx {

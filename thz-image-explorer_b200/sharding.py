@@ -99,3 +99,57 @@ def sharded_deconvolution(ops, slab, width: int, height: int, n_bands: int, dist
     out = ops.apply(slab, g_slab)
     lap("gain_application", t)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Row-slab Richardson-Lucy: the band images stay sharded, halo rows travel over NVLink
+# --------------------------------------------------------------------------------------
+def all_slab_bounds(width: int, world: int):
+    """row_bounds[world + 1] as thz_slab_plan takes them."""
+    return [slab_bounds(width, world, r)[0] for r in range(world)] + [width]
+
+
+def exchange_handles(handle: bytes, dist, world: int):
+    """Every rank's 64-byte arena handle (thz_slab_export), ordered by rank.  Host-side plumbing only: the handles
+    go through torch.distributed's object collective, the data they describe never does."""
+    if world == 1:
+        return [handle]
+    got = [None] * world
+    dist.all_gather_object(got, handle)
+    return got
+
+
+class SlabExchange:
+    """One rank's thz_slab plus the collective bookkeeping around it (plan -> export -> connect, with the host
+    barriers thz_slab_plan asks for).  `slab` needs .plan / .export / .connect_ipc / .rl / .status (binding.Slab)."""
+
+    def __init__(self, slab, dist, rank: int, world: int, sync):
+        self.slab, self.dist, self.rank, self.world, self.sync = slab, dist, rank, world, sync
+
+    def plan(self, width: int, height: int, bands):
+        self.sync()                       # this rank is idle ...
+        if self.world > 1:
+            self.dist.barrier()           # ... and so is everybody else: nobody pushes into an arena being zeroed
+        changed = self.slab.plan(all_slab_bounds(width, self.world), height, bands)
+        if changed == 2:
+            self.slab.connect_ipc(exchange_handles(self.slab.export(), self.dist, self.world))
+        if changed and self.world > 1:
+            self.dist.barrier()
+        return changed
+
+
+def sharded_deconvolution_slab(ops, slab, timings: dict | None = None):
+    """Deconvolution of this rank's slab with the halo-exchanged Richardson-Lucy: three slab-local calls, no
+    collective on the data path (ops.energies -> ops.slab_rl -> ops.apply).  `timings` receives the device
+    milliseconds of the phases when ops.lap() provides them."""
+    lap = getattr(ops, "lap", None)
+    e = ops.energies(slab)
+    if lap:
+        lap("energies", timings)
+    g = ops.slab_rl(e)
+    if lap:
+        lap("richardson_lucy_slab", timings)
+    out = ops.apply(slab, g)
+    if lap:
+        lap("gain_application", timings)
+    return out
