@@ -100,26 +100,55 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": float(max(pw))}
 
 
+CONFIGS = {
+    # BASELINE.json `configs`, at the stand-in shapes SURVEY.md 8d names (the real scans are LFS pointers)
+    "c1": dict(width=200, height=200, samples=2048, deconv=False, spectra=False,
+               name="BASELINE config 1 stand-in: 200x200 pixels x 2048 samples, default filter chain"),
+    "c2": dict(width=100, height=100, samples=2048, deconv=False, spectra=True,
+               name="BASELINE config 2 stand-in: 100x100 pixels x 2048 samples, spectra materialised and normalised "
+                    "by a reference pulse (amplitude ratio / phase difference maps)"),
+    "c3": dict(width=256, height=256, samples=2048, deconv=True, spectra=False,
+               name="BASELINE config 3 stand-in: 256x256 pixels x 2048 samples, default chain + deconvolution "
+                    "(psf.npz, 8 bands, n_iterations 500)"),
+    "c4": dict(width=1024, height=1024, samples=2048, deconv=False, spectra=False,
+               name="BASELINE config 4: synthetic 1024x1024 pixels x 2048 samples, full chain with both time gates"),
+    "c5": dict(width=2048, height=2048, samples=4096, deconv=True, spectra=False,
+               name="BASELINE config 5: synthetic 2048x2048 pixels x 4096 samples, full chain + deconvolution"),
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=2048)
-    ap.add_argument("--height", type=int, default=2048)
-    ap.add_argument("--samples", type=int, default=4096)
+    ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--samples", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-deconv", action="store_true", help="trace pass only (skip the PSF deconvolution)")
     ap.add_argument("--bands", type=int, default=8)
     ap.add_argument("--rl-iterations", type=int, default=500)
+    ap.add_argument("--rl", default="slab", choices=["slab", "bands"],
+                    help="several GPUs: halo-exchanged row slabs (default) or the older band-parallel split")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline slab (0 = auto)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    a.width = a.width or cfg["width"]
+    a.height = a.height or cfg["height"]
+    a.samples = a.samples or cfg["samples"]
+    if not cfg["deconv"]:
+        a.no_deconv = True
+    a.spectra = cfg["spectra"]
+    a.workload = cfg["name"]
+    return a
 
 
 def workload_name(a):
-    return f"synthetic {a.width}x{a.height} pixels x {a.samples} samples, default filter chain (BASELINE config 5)"
+    return f"synthetic {a.width}x{a.height} pixels x {a.samples} samples -- {a.workload}"
 
 
 # --------------------------------------------------------------------------------------
@@ -137,7 +166,7 @@ def cpu_reference_sample(a, rows_chain=4, rows_scan=1, rl_iters=1, with_deconv=T
     Returns a dict with the extrapolated full-cube seconds and traces/s."""
     from oracle import thz_oracle as orc     # timed CPU baseline (cpu_baseline / --impl reference only)
     from oracle import c_twin
-    cores = len(os.sched_getaffinity(0))
+    cores = min(16, len(os.sched_getaffinity(0)))   # fixed worker count: more scipy workers get slower on the 32-core boxes
     W, H, N = a.width, a.height, a.samples
     P_total = W * H
     rng = np.random.default_rng(1)
@@ -244,6 +273,29 @@ def bind_to_gpu_numa(index):
     return 0
 
 
+def rl_flops(bands, W, H):
+    """FLOPs of the separable Richardson-Lucy as timed: per iteration two 2-D filterings of the reflect-padded image,
+    each a column pass (ky taps) and a row pass (kx taps), one multiply-add per tap and pixel, plus the division
+    and the product of the update (4 FLOP per pixel)."""
+    tot = 0.0
+    for b in bands:
+        hp, wp = W + 2 * (b.kx // 2), H + 2 * (b.ky // 2)
+        tot += b.n_iter * (4.0 * (b.kx + b.ky) + 4.0) * hp * wp
+    return tot
+
+
+def latest_traffic():
+    """ncu DRAM bytes per launch of the cube kernels, newest committed capture (profiles/r*_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        return json.load(open(files[-1])), os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 def run_ours(a):
     import torch
     m = importlib.import_module(PKG)
@@ -251,31 +303,32 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     numa_cpus = bind_to_gpu_numa(local) if world > 1 else 0
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     else:
         dist = None
-        torch.cuda.set_device(local)
 
     W, H, N = a.width, a.height, a.samples
-    # row-slab partition over axis 0 (x), uneven last slab allowed
-    row0, row1 = m.sharding.slab_bounds(W, world, rank)
+    row0, row1 = m.sharding.slab_bounds(W, world, rank)   # row slabs over axis 0 (x), uneven last slab allowed
     rows = row1 - row0
     P = rows * H
     P_total = W * H
 
     ctx = m.Context(local)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     t_axis = (np.float32(1000.0) + np.float32(0.05) * np.arange(N, dtype=np.float32)).astype(np.float32)
     m_pre, band, m_post = m.host.chain_multipliers(t_axis)
     ctx.plan_trace(N, m_pre, band, m_post)
+    F = N // 2 + 1
 
     cube_bytes = P * N * 4
     d_in = ctx.alloc(max(cube_bytes, 16))
     d_out = ctx.alloc(max(cube_bytes, 16))
-    d_img = ctx.alloc(max(P * 4, 16))
+    p_max = ((W + world - 1) // world) * H                            # same size on every rank (uneven slabs)
+    img_t = torch.zeros(max(p_max, 4), dtype=torch.float32, device=dev)   # intensity map of the slab, gathered in the step
     ctx.generate_cube(d_in, rows, H, N, row0=row0, total_width=W)
     ctx.sync()
 
@@ -284,7 +337,6 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # deconvolution plan: BASELINE config 5 = 8 FIR bands, shipped psf.npz, dx = dy = 0.5 mm
     bands = None
     if not a.no_deconv:
         psf = m.host.PSF.load(os.path.join(ROOT, "tests", "golden", "psf.npz"))
@@ -294,22 +346,46 @@ def run_ours(a):
             raise SystemExit(f"deconvolution plan refused: {why}")
     n_rl_iter = sum(b.n_iter for b in bands) if bands is not None else 0
     B = len(bands) if bands is not None else 0
+
+    # config 2: spectra materialised (fft, amplitudes, phases) + maps normalised by the reference pulse
+    spec = None
+    if a.spectra:
+        spec = {k: torch.empty((P, F) if k != "fft" else (P, 2 * F), dtype=torch.float32, device=dev)
+                for k in ("fft", "amp", "phase")}
+
+    # several GPUs: the band images stay sharded; Richardson-Lucy exchanges halo rows over NVLink (thz_slab_*)
+    slab = slabx = None
+    rl_mode = "single GPU"
+    e_t = g_t = None
+    if bands is not None and world > 1:
+        e_t = torch.empty((B, P), dtype=torch.float32, device=dev)
+        g_t = torch.empty((B, P), dtype=torch.float32, device=dev)
+        rl_mode = "band-parallel (gather, LPT, all-reduce)"
+        if a.rl == "slab":
+            slab = m.Slab(ctx, rank, world)
+            slabx = m.sharding.SlabExchange(slab, dist, rank, world, sync=ctx.sync)
+            try:
+                slabx.plan(W, H, bands)
+                rl_mode = "row slabs, halo rows pushed over NVLink by the filtering kernels"
+            except m.ThzError as ex:      # slabs thinner than three PSF half-heights: every rank takes this branch
+                slab.close()
+                slab = slabx = None
+                rl_mode += f" [slab form refused: {ex}]"
+
     class GpuOps:
-        """libthzgpu stage calls on torch device tensors (raw pointers through the C ABI)."""
+        """band-parallel fall-back: libthzgpu stage calls on torch device tensors"""
 
         def __init__(self):
-            self.dev = torch.device("cuda", local)
             self.taps = [(np.ascontiguousarray(b.psf_x_np()), np.ascontiguousarray(b.psf_y_np())) for b in bands]
 
         def energies(self, slab_ptr):
-            e = torch.empty((B, P), dtype=torch.float32, device=self.dev)
-            ctx.deconv_energies_dev(slab_ptr, P, N, bands, e.data_ptr())
+            ctx.deconv_energies_dev(slab_ptr, P, N, bands, e_t.data_ptr())
             ctx.sync()
-            return e
+            return e_t
 
         def rl_gain(self, b, image):
             image = image.contiguous()
-            g = torch.empty(W * H, dtype=torch.float32, device=self.dev)
+            g = torch.empty(W * H, dtype=torch.float32, device=dev)
             torch.cuda.synchronize()
             px, py = self.taps[b]
             ctx._check(m.lib.thz_rl_separable_dev(ctx.handle, image.data_ptr(), W, H, px.ctypes.data, px.size,
@@ -320,27 +396,51 @@ def run_ours(a):
 
         def apply(self, slab_ptr, g_slab):
             torch.cuda.synchronize()
-            ctx.deconv_apply_dev(slab_ptr, g_slab.data_ptr(), P, N, bands, slab_ptr, d_img.ptr)
+            ctx.deconv_apply_dev(slab_ptr, g_slab.data_ptr(), P, N, bands, slab_ptr, img_t.data_ptr())
             ctx.sync()
 
-    ops = GpuOps() if (bands is not None and world > 1) else None
-
-    phase_s = {}
-    # measured per-kernel cost is ~16 us fixed + ~0.16 us per tap of the two 1-D passes (2048 x 2048 image)
+    ops = GpuOps() if (bands is not None and world > 1 and slab is None) else None
     band_costs = [b.n_iter * (100 + b.kx + b.ky) for b in bands] if bands is not None else None
+    phase_s = {}
+    img_full = torch.empty((world, img_t.numel()), dtype=torch.float32, device=dev) if world > 1 else None
+    marks = []   # (name, event) of the current step, device-timed phases of this rank
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        marks.append((name, e))
 
     def step():
-        ctx.trace_fused_dev(d_in.ptr, d_out.ptr, d_img.ptr, P)
-        if bands is None:
+        marks.clear()
+        mark("start")
+        if spec is not None:
+            ctx.trace_forward_dev(d_in.ptr, d_out.ptr, spec["fft"].data_ptr(), spec["amp"].data_ptr(),
+                                  spec["phase"].data_ptr(), P)
+            mark("trace_forward_spectra")
             return
-        if world == 1:
-            ctx._check(m.lib.thz_deconvolution_dev(ctx.handle, d_out.ptr, rows, H, N, bands, B, d_out.ptr,
-                                                   d_img.ptr, None, None, None))
-        else:
-            m.sharding.sharded_deconvolution(ops, d_out.ptr, W, H, B, dist, world, rank, timings=phase_s,
-                                             band_costs=band_costs)
+        ctx.trace_fused_dev(d_in.ptr, d_out.ptr, img_t.data_ptr(), P)
+        mark("trace_fused")
+        if bands is not None:
+            if world == 1:
+                ctx._check(m.lib.thz_deconvolution_dev(ctx.handle, d_out.ptr, rows, H, N, bands, B, d_out.ptr,
+                                                       img_t.data_ptr(), None, None, None))
+                mark("deconvolution")
+            elif slab is not None:
+                ctx.deconv_energies_dev(d_out.ptr, P, N, bands, e_t.data_ptr())
+                mark("band_energies")
+                slab.rl(e_t.data_ptr(), P, g_t.data_ptr())
+                mark("richardson_lucy_slab")
+                ctx.deconv_apply_dev(d_out.ptr, g_t.data_ptr(), P, N, bands, d_out.ptr, img_t.data_ptr())
+                mark("gain_application")
+            else:
+                m.sharding.sharded_deconvolution(ops, d_out.ptr, W, H, B, dist, world, rank, timings=phase_s,
+                                                 band_costs=band_costs)
+        if world > 1:
+            # the displayed map: gather of the slabs' intensity rows (NCCL over NVLink, 4 bytes per pixel)
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(img_full, img_t)
+            mark("gather_map")
 
-    launches0 = None
     for _ in range(a.warmup):
         step()
     ctx.sync()
@@ -358,11 +458,15 @@ def run_ours(a):
         ev[i + 1].record(stream)
     ctx.sync()
     barrier()
+    if slab is not None:
+        slab.status()
     launches = ctx.launches - launches0
-    phases_ms = {k: 1e3 * v / a.steps for k, v in phase_s.items()} if world > 1 else None
-    per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
     total_ms = ev[0].elapsed_time(ev[a.steps])
     clocks = sampler.stop() if rank == 0 else None
+    # device-timed phases of the last step on this rank
+    phases_ms = {marks[i + 1][0]: marks[i][1].elapsed_time(marks[i + 1][1]) for i in range(len(marks) - 1)}
+    if phase_s:
+        phases_ms.update({k + "_wall": 1e3 * v / a.steps for k, v in phase_s.items()})
     if dist is not None:
         tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -370,20 +474,40 @@ def run_ours(a):
     ms_per_step = total_ms / a.steps
     value = P_total / (ms_per_step / 1e3)
 
-    # stage breakdown of the last step (CUDA events inside the library) + fused trace kernel timed alone
+    # ---- per-kernel breakdown of one extra step (event pairs inside the library), this rank ----
     peak, peak_src = measured_peaks()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
-    e0.record(stream)
-    for _ in range(reps):
-        ctx.trace_fused_dev(d_in.ptr, d_out.ptr, d_img.ptr, P)
-    e1.record(stream)
-    ctx.sync()
-    trace_ms = e0.elapsed_time(e1) / reps
-    stages = {"trace_fused": {"ms": trace_ms, "kernel": f"k_trace_fused<{N}>", "algorithmic_bytes": (8 * N + 4) * P}}
-    if bands is not None and world == 1:
-        st = ctx.deconv_stage_ms()
-        km = ctx.deconv_kernel_ms()
+    stages = {}
+    if spec is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record(stream)
+        for _ in range(reps):
+            ctx.trace_fused_dev(d_in.ptr, d_out.ptr, img_t.data_ptr(), P)
+        e1.record(stream)
+        ctx.sync()
+        stages["trace_fused"] = {"ms": e0.elapsed_time(e1) / reps, "kernel": f"k_trace_fused<{N}>",
+                                 "algorithmic_bytes": (8 * N + 4) * P}
+    else:
+        stages["trace_forward_spectra"] = {"ms": phases_ms["trace_forward_spectra"], "kernel": f"k_trace_forward<{N}>",
+                                           "algorithmic_bytes": (8 * N + 16 * F) * P}
+    rl_ms = None
+    if bands is not None:
+        if world == 1:
+            st = ctx.deconv_stage_ms()
+            km = ctx.deconv_kernel_ms()
+            rl_ms = st["rl_ms"]
+            stages["stage_totals_ms"] = {"energies": st["energies_ms"], "richardson_lucy": st["rl_ms"],
+                                         "gain_application": st["apply_ms"]}
+        else:
+            barrier()
+            ctx._check(m.lib.thz_kernel_timing_begin(ctx.handle))
+            step()
+            ms4 = np.zeros(4, np.float32)
+            ctx._check(m.lib.thz_kernel_timing_end(ctx.handle, ms4.ctypes.data))
+            barrier()
+            km = {"energy_spectra_ms": float(ms4[0]), "energy_edges_ms": float(ms4[1]),
+                  "apply_edges_ms": float(ms4[2]), "apply_main_ms": float(ms4[3])}
+            rl_ms = phases_ms.get("richardson_lucy_slab", phases_ms.get("richardson_lucy_own_bands_wall"))
         # per-kernel algorithmic bytes (SURVEY 8d / DESIGN.md): the spectra pass reads the cube and writes B
         # energies per trace; the edge passes touch 2 x 249 samples per trace; the main gain pass reads and
         # writes the cube, reads B gains and 2 x 249 corrections and writes the intensity
@@ -395,38 +519,47 @@ def run_ours(a):
                                         "algorithmic_bytes": (4 * 498 + 4 * B + 4 * 498) * P}
         stages["deconv_apply"] = {"ms": km["apply_main_ms"], "kernel": f"k_fir_apply_circ<{N}>",
                                   "algorithmic_bytes": (8 * N + 4 * B + 4 * 498 + 4) * P}
-        stages["richardson_lucy"] = {"ms": st["rl_ms"], "kernel": "k_rl_stream<1|2>",
-                                     "iterations": st["rl_iterations"],
-                                     "iters_per_s": st["rl_iterations"] / (st["rl_ms"] / 1e3) if st["rl_ms"] > 0 else None}
-        stages["stage_totals_ms"] = {"energies": st["energies_ms"], "richardson_lucy": st["rl_ms"],
-                                     "gain_application": st["apply_ms"]}
     for v in stages.values():
         if "algorithmic_bytes" in v and v["ms"] > 0:
             v["gbs"] = v["algorithmic_bytes"] / (v["ms"] / 1e3) / 1e9
             v["frac_of_hbm_peak"] = v["gbs"] / peak
+    # FP32 issue-rate microbenchmark in the same run, and the Richardson-Lucy FLOP fraction against it
+    fp32 = {"ffma_tflops": 2 * ctx.fp32_rate(0) / 1e12, "ffma2_packed_tflops": 2 * ctx.fp32_rate(1) / 1e12,
+            "fadd_tops": ctx.fp32_rate(2) / 1e12, "fadd2_packed_tops": ctx.fp32_rate(3) / 1e12,
+            "fmul_tops": ctx.fp32_rate(4) / 1e12, "fmul2_packed_tops": ctx.fp32_rate(5) / 1e12,
+            "how": "thz_fp32_rate: 16 independent chains per thread, 8 x 256 threads per SM, register operands"}
+    if bands is not None and rl_ms:
+        fl = rl_flops(bands, W, H) / world          # this rank's share
+        tf = fl / (rl_ms / 1e3) / 1e12
+        stages["richardson_lucy"] = {
+            "ms": rl_ms, "kernel": "k_rl_stream<1|2>", "iterations": n_rl_iter,
+            "iters_per_s": n_rl_iter / (rl_ms / 1e3), "algorithm": "separable (row + column pass per filtering), f32",
+            "tflops": tf, "flop_frac": tf / fp32["ffma_tflops"] if fp32["ffma_tflops"] > 0 else None,
+            "flop_frac_of": "measured scalar FFMA rate of this GPU (fp32_peak.ffma_tflops); tensor cores not applicable",
+            "mode": rl_mode}
     dom = max((k for k in stages if "gbs" in stages[k]), key=lambda k: stages[k]["ms"])
-    # DRAM traffic of the same kernel from the committed ncu capture (profiles/r01_traffic.json, C5 on 1 GPU)
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
-        if world == 1 and (W, H, N, B if bands is not None else 8) == (2048, 2048, 4096, 8):
-            traffic = sum(v["traffic_bytes_per_launch"] for k, v in tj.items()
-                          if k.split("<")[0] == stages[dom]["kernel"].split("<")[0]) or None
-    except Exception:
-        traffic = None
+    traffic, traffic_src = None, None
+    tj, tname = latest_traffic()
+    if tj is not None and (W, H, N) == tuple(tj.get("cube", (0, 0, 0))):
+        ent = tj["kernels"].get(stages[dom]["kernel"].split("<")[0])
+        if ent:
+            # captured at one GPU on the full cube; bytes scale with the traces of this rank
+            traffic = ent["traffic_bytes_per_launch"] * P / float(P_total)
+            traffic_src = tname
     roofline = {"bound": "hbm", "kernel": stages[dom]["kernel"], "stage": dom, "achieved": stages[dom]["gbs"],
                 "peak": peak, "unit": "GB/s", "frac": stages[dom]["gbs"] / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"],
-                "kernel_ms": stages[dom]["ms"]}
+                "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"], "kernel_ms": stages[dom]["ms"],
+                "rank": 0}
     # whole-step roofline: 20N + 8B + 4 bytes per trace for the three cube passes
-    chain_bytes = ((20 * N + 8 * B + 4) if bands is not None else (8 * N + 4)) * P
+    per_trace = (8 * N + 16 * F) if spec is not None else ((20 * N + 8 * B + 4) if bands is not None else (8 * N + 4))
+    chain_bytes = per_trace * P_total
     chain = {"algorithmic_bytes_per_step": chain_bytes, "gbs": chain_bytes / (ms_per_step / 1e3) / 1e9,
-             "frac_of_hbm_peak": chain_bytes / (ms_per_step / 1e3) / 1e9 / peak}
+             "frac_of_hbm_peak": chain_bytes / (ms_per_step / 1e3) / 1e9 / (peak * world)}
 
-    # end to end through the host-pointer C ABI: pinned host cube -> H2D -> chain -> D2H (filtered cube + img)
     e2e = None
-    if not a.no_e2e:
-        e2e = run_e2e(a, m, ctx, d_in, d_out, P, rows, N, world, dist, barrier, P_total, bands, step)
+    if not a.no_e2e and spec is None:
+        e2e = run_e2e(a, m, ctx, d_in, d_out, P, rows, N, world, dist, barrier, P_total, bands, slab)
 
     cpu = None
     if rank == 0 and not a.no_cpu:
@@ -440,28 +573,35 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "partition": f"row slabs over x, {world} rank(s)",
+            "config": {"workload": workload_name(a), "name": a.config,
+                       "partition": f"row slabs over x, {world} rank(s)", "richardson_lucy": rl_mode,
                        "host_affinity": (f"rank pinned to the {numa_cpus} cores local to its GPU (NVML)"
                                          if numa_cpus else "default"),
-                       "l2": "inputs larger than L2 (cube >> 126 MB), no flush needed",
+                       "l2": ("inputs larger than L2 (cube >> 126 MB), no flush needed" if cube_bytes > (256 << 20)
+                              else "cube smaller than 2 x L2: numbers include L2 hits, parity case rather than a "
+                                   "bandwidth measurement"),
                        "stages": ["trace pass (fused)"] + (["deconvolution: band energies, Richardson-Lucy "
                                                            f"({n_rl_iter} iterations over {len(bands)} bands), "
                                                            "gain application"] if bands is not None else [])},
             "stage_breakdown": stages, "rank0_phases_ms": phases_ms, "chain_roofline": chain,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "fp32_peak": fp32, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
         }
         print(json.dumps(line))
-    d_in.free(); d_out.free(); d_img.free()
+    if slab is not None:
+        barrier()
+        slab.close()
+    d_in.free(); d_out.free()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
-def run_e2e(a, m, ctx, d_in, d_out, P, rows, N, world, dist, barrier, P_total, bands, step_dev):
+def run_e2e(a, m, ctx, d_in, d_out, P, rows, N, world, dist, barrier, P_total, bands, slab):
     """The same step through the host-pointer C ABI: pinned host cube in, filtered (and deconvolved)
-    cube + intensity map out, copies inside the timed region.  One GPU: thz_chain_host (copies
-    overlap the cube passes).  Several GPUs: each rank uploads its slab, runs the sharded device
-    step and downloads it (no overlap yet)."""
+    cube + intensity map out, copies inside the timed region.  One GPU: thz_chain_host.  Several GPUs: every rank
+    runs thz_chain_host_begin (H2D chunks under the trace / energy passes), the halo-exchanged Richardson-Lucy,
+    and thz_chain_host_end (gain application under the D2H chunks) on its slab."""
     import ctypes as C
     H = a.height
     try:
@@ -471,28 +611,33 @@ def run_e2e(a, m, ctx, d_in, d_out, P, rows, N, world, dist, barrier, P_total, b
     nbytes = P * N * 4
     if nbytes * world > 0.6 * avail:
         return {"value": None, "unit": UNIT, "note": f"host RAM too small for a {nbytes * world >> 30} GiB pinned cube"}
+    if world > 1 and bands is not None and slab is None:
+        return {"value": None, "unit": UNIT, "note": "band-parallel fall-back has no overlapped host path"}
     hp, hi = C.c_void_p(), C.c_void_p()
-    if m.lib.thz_host_alloc(nbytes, C.byref(hp)) != 0 or m.lib.thz_host_alloc(P * 4, C.byref(hi)) != 0:
+    if m.lib.thz_host_alloc(nbytes, C.byref(hp)) != 0 or m.lib.thz_host_alloc(max(P * 4, 16), C.byref(hi)) != 0:
         return None
+    B = len(bands) if bands is not None else 0
     try:
         ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_in.ptr, nbytes))
         reps = 2
-        if world == 1:
-            # thz_chain_host keeps its own device-resident cube: release the bench's output buffer first;
-            # d_in stays as the pristine copy from which the (in-place) host buffer is restored, untimed
-            d_out.free()
+        # the host-pointer calls keep their own device-resident cube: release the bench's output buffer first;
+        # d_in stays as the pristine copy from which the (in-place) host buffer is restored, untimed
+        d_out.free()
 
         def once():
             if world == 1:
-                ctx._check(m.lib.thz_chain_host(ctx.handle, hp.value, rows, H, N, bands,
-                                                len(bands) if bands is not None else 0, hp.value, hi.value,
+                ctx._check(m.lib.thz_chain_host(ctx.handle, hp.value, rows, H, N, bands, B, hp.value, hi.value,
                                                 None, None, None))
             else:
-                ctx._check(m.lib.thz_copy_h2d(ctx.handle, d_in.ptr, hp.value, nbytes))
-                step_dev()
-                ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_out.ptr, nbytes))
+                de, dg = C.c_void_p(), C.c_void_p()
+                ctx._check(m.lib.thz_chain_host_begin(ctx.handle, hp.value, rows, H, N, bands, B, hp.value,
+                                                      C.byref(de), C.byref(dg)))
+                if B:
+                    slab.rl(de.value, P, dg.value)
+                    slab.status()
+                ctx._check(m.lib.thz_chain_host_end(ctx.handle, rows, H, N, bands, B, hp.value, hi.value))
 
-        once()   # warm-up (allocates the device-resident cube / staging ring)
+        once()   # warm-up (allocates the device-resident cube)
         dt = 0.0
         for _ in range(reps):
             ctx._check(m.lib.thz_copy_d2h(ctx.handle, hp.value, d_in.ptr, nbytes))   # restore the input, untimed
@@ -509,11 +654,10 @@ def run_e2e(a, m, ctx, d_in, d_out, P, rows, N, world, dist, barrier, P_total, b
             dt = float(tt.item())
         return {"value": P_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(nbytes * world),
                 "d2h_bytes_per_step": int((nbytes + P * 4) * world), "seconds_per_step": dt,
-                "note": ("thz_chain_host: pinned host cube -> H2D chunks overlapped with the fused trace pass and the "
-                         "band-energy pass -> Richardson-Lucy -> gain application overlapped with D2H chunks"
-                         if world == 1 else
-                         "per rank: H2D of the slab, sharded device step, D2H of the slab (not overlapped); "
-                         "wall clock, max over ranks")}
+                "note": ("pinned host cube -> H2D chunks overlapped with the fused trace pass and the band-energy pass "
+                         "-> Richardson-Lucy -> gain application overlapped with D2H chunks"
+                         + ("" if world == 1 else "; per rank on its row slab (thz_chain_host_begin / thz_slab_rl / "
+                            "thz_chain_host_end), wall clock, max over ranks"))}
     finally:
         m.lib.thz_host_free(hp.value)
         m.lib.thz_host_free(hi.value)
