@@ -198,6 +198,37 @@ int thz_voxel_opacity_dev(thz_ctx* ctx, const float* d_cube, int n, int64_t P, f
 int thz_spectral_means(thz_ctx* ctx, const float* d_fft, const float* d_amp, const float* d_phase,
                        int64_t P, float* avg_fft, float* avg_amp, float* avg_phase);
 
+/* ------------------------------------------- reference-normalised spectral maps (config 2) */
+/* BASELINE config 2: a scan normalised by a reference pulse (`OpenRef`, src/data_thread.rs:372-588).  The
+ * reference program forms A_s / A_r and phi_s - phi_r only inside `calculate_optical_properties` for one pixel or a
+ * ROI mean (src/math_tools.rs:665-701, src/data_thread.rs:1489-1559); here the same two operands are produced for
+ * every pixel as an epilogue of the forward kernel -- there is no full-map equivalent upstream.
+ * thz_plan_reference uploads the reference spectrum (f = n/2 + 1 values each, e.g. from thz_reference_pulse; NULL
+ * clears it); thz_trace_forward_normalised_dev is thz_trace_forward_dev whose amplitude output is
+ * |s| / max(A_r, 1e-12) and whose phase output is unwrap(arg s) - phi_r; thz_spectral_slice_dev cuts the map of one
+ * frequency bin out of a [P][f] array. */
+int thz_plan_reference(thz_ctx* ctx, const float* ref_amp, const float* ref_phase, int f);
+int thz_trace_forward_normalised_dev(thz_ctx* ctx, const float* d_in, float* d_windowed, float* d_fft, float* d_ratio,
+                                     float* d_dphase, int64_t P);
+int thz_spectral_slice_dev(thz_ctx* ctx, const float* d_array /* [P][f] */, int f, int bin, float* d_map /* [P] */,
+                           int64_t P);
+
+/* --------------------------------------------- GUI hand-off from device-resident cubes -------- */
+/* What `data_thread` copies out for the plots after a chain run (src/data_thread.rs:1337-1431), without host copies
+ * of the cubes and without spectral cubes: the selected pixel's raw trace (slot 0), its filtered trace (last slot)
+ * and its spectrum as slot fft + 1 holds it (windowed r2c; fft and amplitudes times the band-pass, phases
+ * untouched) -- one forward transform of one trace with the current plan.  Host outputs, any may be NULL. */
+int thz_pixel_handoff_dev(thz_ctx* ctx, const float* d_raw, const float* d_filtered, int64_t P, int64_t pixel,
+                          float* raw /* [n] */, float* filtered /* [n] */, float* fft /* [2 f] */, float* amp /* [f] */,
+                          float* phase /* [f] */);
+/* `avg_signal`: mean over all pixels of a device cube [P][n] (src/data_thread.rs:1423-1431; f64 combination of
+ * per-block f32 partial sums instead of the reference's sequential f32 sums). */
+int thz_mean_trace_dev(thz_ctx* ctx, const float* d_cube, int n, int64_t P, float* avg /* [n] */);
+/* The pixel means `ifft` takes (src/math_tools.rs:421-440) from the raw device cube: spectra are formed one chunk
+ * of traces at a time and reduced, the [P][f] cubes never exist.  Any output may be NULL. */
+int thz_mean_spectra_dev(thz_ctx* ctx, const float* d_raw, int64_t P, float* avg_fft /* [2 f] */,
+                         float* avg_amp /* [f] */, float* avg_phase /* [f] */);
+
 /* ---------------------------------------------------------------- deconvolution -------- */
 /* PSF model as loaded from psf.npz (`load_psf`, src/io.rs:190-267; src/filters/psf.rs:7-22,
  * 202-207): natural cubic splines per segment a + b dx + c dx^2 + d dx^3 and the hybrid fit

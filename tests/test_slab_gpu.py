@@ -127,3 +127,62 @@ def test_two_gpus_slab_rl_over_nvlink(bands8):
     with m.Group([0, 1]) as grp:
         g = grp.rl(e, bands8)
     assert np.array_equal(g, g_ref)
+
+
+def test_two_gpus_one_process_per_gpu_ipc():
+    """One process per GPU (torchrun, as bench.py runs): arenas exchanged as cudaIpc handles, halo rows over NVLink."""
+    _need_gpus(2)
+    import os
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "tools", "mgpu_slab_check.py")], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0
+
+
+def test_two_gpus_group_chain_equals_single_gpu(psf_npz_path):
+    """thz_group_chain_host on two devices (one calling thread) == thz_chain_host on one."""
+    _need_gpus(2)
+    from helpers import default_multipliers, synthetic_cube
+    m = pkg()
+    w, h, n = 320, 64, 512
+    cube = synthetic_cube(w, h, n, seed=2, noise=0.02)
+    t, m_pre, band, m_post = default_multipliers(n)
+    psf = m.host.PSF.load(psf_npz_path)
+    bands, why = m.host.Deconvolution(n_filters=5, n_iterations=30).plan(t, (w, h), 0.5, 0.5, psf)
+    assert why is None
+    with m.Context(0) as c0:
+        c0.plan_trace(n, m_pre, band, m_post)
+        ref_out, ref_img, rc = c0.chain(cube, bands)
+    with m.Group([0, 1]) as grp:
+        out, img, rc = grp.chain(cube, m_pre, band, m_post, bands)
+    assert rc == 0
+    assert np.array_equal(out, ref_out) and np.array_equal(img, ref_img)
+
+
+def test_group_on_one_device_emulates_the_slabs(ctx, psf_npz_path):
+    """The same group call with three ranks on ONE device (serial emulation): available on a one-GPU box."""
+    from helpers import default_multipliers, synthetic_cube
+    m = pkg()
+    w, h, n = 240, 48, 512
+    cube = synthetic_cube(w, h, n, seed=4, noise=0.02)
+    t, m_pre, band, m_post = default_multipliers(n)
+    psf = m.host.PSF.load(psf_npz_path)
+    bands, why = m.host.Deconvolution(n_filters=5, n_iterations=20).plan(t, (w, h), 0.5, 0.5, psf)
+    assert why is None
+    ctx.plan_trace(n, m_pre, band, m_post)
+    ref_out, ref_img, rc = ctx.chain(cube, bands)
+    with m.Group([0, 0, 0]) as grp:
+        assert grp.row_bounds(w) == [0, 80, 160, 240]
+        out, img, rc = grp.chain(cube, m_pre, band, m_post, bands)
+        out2, img2, rc2 = grp.chain(cube, m_pre, band, m_post, bands)     # plan cached, counters carry over
+    assert rc == 0 and rc2 == 0
+    assert np.array_equal(out, ref_out) and np.array_equal(img, ref_img)
+    assert np.array_equal(out2, ref_out)

@@ -188,6 +188,12 @@ def load_library():
         "thz_slab_rl": (i32, [vp, fp, i64, fp, fp]),
         "thz_slab_rl_serial": (i32, [C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp)]),
         "thz_slab_status": (i32, [vp]),
+        "thz_plan_reference": (i32, [vp, fp, fp, i32]),
+        "thz_trace_forward_normalised_dev": (i32, [vp, fp, fp, fp, fp, fp, i64]),
+        "thz_spectral_slice_dev": (i32, [vp, fp, i32, i32, fp, i64]),
+        "thz_pixel_handoff_dev": (i32, [vp, fp, fp, i64, i64, fp, fp, fp, fp, fp]),
+        "thz_mean_trace_dev": (i32, [vp, fp, i32, i64, fp]),
+        "thz_mean_spectra_dev": (i32, [vp, fp, i64, fp, fp, fp]),
         "thz_kernel_timing_begin": (i32, [vp]),
         "thz_kernel_timing_end": (i32, [vp, fp]),
         "thz_chain_host_begin": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, C.POINTER(vp), C.POINTER(vp)]),
@@ -544,6 +550,51 @@ class Context:
                                               float(sigma), int(radius), int(max_instances), d_o.ptr,
                                               C.cast(C.byref(thr), C.c_void_p)))
         return d_o.download(cube.shape), float(thr.value)
+
+    # ------------------------------------------------------------------ config 2 / GUI hand-off
+    def plan_reference(self, ref_amp, ref_phase):
+        if ref_amp is None:
+            self._check(lib.thz_plan_reference(self.handle, None, None, 0))
+            return
+        a, p = _f32c(ref_amp), _f32c(ref_phase)
+        self._check(lib.thz_plan_reference(self.handle, a.ctypes.data, p.ctypes.data, a.size))
+
+    def trace_forward_normalised(self, data):
+        """-> (ratio [.., F], dphase [.., F]) : |s| / max(A_r, 1e-12) and unwrap(arg s) - phi_r per pixel."""
+        data = _f32c(data)
+        n = data.shape[-1]
+        P = data.size // n
+        F = n // 2 + 1
+        d_in = self.to_device(data)
+        d_a, d_p = self.alloc(P * F * 4), self.alloc(P * F * 4)
+        self._check(lib.thz_trace_forward_normalised_dev(self.handle, d_in.ptr, None, None, d_a.ptr, d_p.ptr, P))
+        shp = data.shape[:-1] + (F,)
+        return d_a.download(shp), d_p.download(shp)
+
+    def spectral_slice(self, d_array, F, bin_idx, P):
+        d_m = self.alloc(P * 4)
+        self._check(lib.thz_spectral_slice_dev(self.handle, d_array, int(F), int(bin_idx), d_m.ptr, int(P)))
+        return d_m.download((P,))
+
+    def pixel_handoff(self, d_raw, d_filtered, P, pixel):
+        n = self.n
+        F = n // 2 + 1
+        raw, fil = np.empty(n, np.float32), np.empty(n, np.float32)
+        fft, amp, ph = np.empty(2 * F, np.float32), np.empty(F, np.float32), np.empty(F, np.float32)
+        self._check(lib.thz_pixel_handoff_dev(self.handle, d_raw, d_filtered, int(P), int(pixel), raw.ctypes.data,
+                                              fil.ctypes.data, fft.ctypes.data, amp.ctypes.data, ph.ctypes.data))
+        return {"raw": raw, "filtered": fil, "fft": fft.view(np.complex64), "amp": amp, "phase": ph}
+
+    def mean_trace(self, d_cube, n, P):
+        avg = np.empty(n, np.float32)
+        self._check(lib.thz_mean_trace_dev(self.handle, d_cube, int(n), int(P), avg.ctypes.data))
+        return avg
+
+    def mean_spectra(self, d_raw, P):
+        F = self.n // 2 + 1
+        f, a, p = np.empty(2 * F, np.float32), np.empty(F, np.float32), np.empty(F, np.float32)
+        self._check(lib.thz_mean_spectra_dev(self.handle, d_raw, int(P), f.ctypes.data, a.ctypes.data, p.ctypes.data))
+        return f.view(np.complex64), a, p
 
     def fp32_rate(self, mode=0):
         """thz_fp32_rate: lane operations per second of FFMA (0), packed FFMA2 (1), FADD (2), FADD2 (3), FMUL (4), FMUL2 (5)."""

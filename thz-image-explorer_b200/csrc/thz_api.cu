@@ -28,6 +28,17 @@ int cuda_fail(thz_ctx* c, cudaError_t e, const char* what) {
   return set_err(c, e == cudaErrorMemoryAllocation ? THZ_ENOMEM : THZ_ECUDA, m);
 }
 
+cudaError_t ensure_dynamic_smem(thz_ctx* c, const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> have;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = have[{c->device, kernel}];
+  if (cur >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+
 int get_tables(thz_ctx* c, int n, const FftTables** out) {
   auto it = c->tables.find(n);
   if (it != c->tables.end()) {
@@ -177,6 +188,8 @@ void thz_ctx_destroy(thz_ctx* c) {
   if (c->plan.d_chirp) cudaFree(c->plan.d_chirp);
   if (c->plan.d_bhat) cudaFree(c->plan.d_bhat);
   if (c->plan.d_hn) cudaFree(c->plan.d_hn);
+  if (c->plan.d_ref_amp) cudaFree(c->plan.d_ref_amp);
+  if (c->plan.d_ref_phase) cudaFree(c->plan.d_ref_phase);
   if (c->d_scratch) cudaFree(c->d_scratch);
   for (auto& kv : c->ws)
     if (kv.second.first) cudaFree(kv.second.first);
@@ -386,6 +399,138 @@ int thz_spectral_means(thz_ctx* c, const float* d_fft, const float* d_amp, const
       j.out[col] = (float)(acc / (double)P);
     }
   }
+  return THZ_OK;
+}
+
+// ---------------------------------------------------------------- reference-normalised spectra (config 2)
+int thz_plan_reference(thz_ctx* c, const float* ref_amp, const float* ref_phase, int f) {
+  CHECK_CTX(c);
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < kHostStreams; ++i) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[i]));
+  TracePlan& p = c->plan;
+  if (!ref_amp || !ref_phase) {   // clear
+    if (p.d_ref_amp) cudaFree(p.d_ref_amp);
+    if (p.d_ref_phase) cudaFree(p.d_ref_phase);
+    p.d_ref_amp = p.d_ref_phase = nullptr;
+    p.ref_f = 0;
+    return THZ_OK;
+  }
+  if (f < 1) return set_err(c, THZ_EINVAL, "bad reference length");
+  int rc = upload_vec(c, &p.d_ref_amp, ref_amp, (size_t)f);
+  if (rc == THZ_OK) rc = upload_vec(c, &p.d_ref_phase, ref_phase, (size_t)f);
+  if (rc != THZ_OK) return rc;
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  p.ref_f = f;
+  return THZ_OK;
+}
+
+int thz_trace_forward_normalised_dev(thz_ctx* c, const float* d_in, float* d_windowed, float* d_fft, float* d_ratio,
+                                     float* d_dphase, int64_t P) {
+  CHECK_CTX(c);
+  return launch_trace_forward(c, c->stream, d_in, d_windowed, (float2*)d_fft, d_ratio, d_dphase, P, true);
+}
+
+int thz_spectral_slice_dev(thz_ctx* c, const float* d_array, int f, int bin, float* d_map, int64_t P) {
+  CHECK_CTX(c);
+  if (!d_array || !d_map || f < 1 || bin < 0 || bin >= f || P < 0) return set_err(c, THZ_EINVAL, "bad argument");
+  return launch_spectral_slice(c, c->stream, d_array, f, bin, d_map, P);
+}
+
+// ---------------------------------------------------------------- GUI hand-off from device-resident cubes
+int thz_pixel_handoff_dev(thz_ctx* c, const float* d_raw, const float* d_filtered, int64_t P, int64_t pixel,
+                          float* raw, float* filtered, float* fft, float* amp, float* phase) {
+  CHECK_CTX(c);
+  if (c->plan.n == 0) return set_err(c, THZ_ESTATE, "thz_plan_trace has not been called");
+  if (pixel < 0 || pixel >= P) return set_err(c, THZ_EINVAL, "selected pixel out of bounds");   // data_thread.rs:1344-1356
+  const int n = c->plan.n, F = n / 2 + 1;
+  if (raw) {
+    if (!d_raw) return set_err(c, THZ_EINVAL, "null raw cube");
+    THZ_CUDA(c, cudaMemcpyAsync(raw, d_raw + pixel * n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (filtered) {
+    if (!d_filtered) return set_err(c, THZ_EINVAL, "null filtered cube");
+    THZ_CUDA(c, cudaMemcpyAsync(filtered, d_filtered + pixel * n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost,
+                                c->stream));
+  }
+  if (fft || amp || phase) {
+    if (!d_raw) return set_err(c, THZ_EINVAL, "null raw cube");
+    // the spectrum the reference plots is the one of slot fft + 1 (data_thread.rs:1364-1379): the windowed trace's
+    // r2c with fft and amplitudes scaled by the band-pass (band_pass_fd.rs:155-159), phases untouched.  One
+    // forward transform of one trace with the chain's own plan.
+    void* ws = nullptr;
+    int rc = ws_get(c, WS_HANDOFF, (size_t)(4 * F) * sizeof(float), &ws);
+    if (rc != THZ_OK) return rc;
+    float* d_f = (float*)ws;
+    float* d_a = d_f + 2 * F;
+    float* d_p = d_a + F;
+    rc = launch_trace_forward(c, c->stream, d_raw + pixel * n, nullptr, (float2*)d_f, d_a, d_p, 1);
+    if (rc == THZ_OK && c->plan.has_band) rc = launch_band_apply(c, c->stream, (float2*)d_f, d_a, 1);
+    if (rc != THZ_OK) return rc;
+    if (fft) THZ_CUDA(c, cudaMemcpyAsync(fft, d_f, (size_t)2 * F * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (amp) THZ_CUDA(c, cudaMemcpyAsync(amp, d_a, (size_t)F * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (phase) THZ_CUDA(c, cudaMemcpyAsync(phase, d_p, (size_t)F * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  return THZ_OK;
+}
+
+// mean over the P traces of a [P][cols] device array -> host vector (per-block partial sums, combined in f64)
+static int column_means(thz_ctx* c, const float* d_x, int64_t P, int cols, std::vector<double>& acc) {
+  int nb = c->sm_count * 4;
+  if ((int64_t)nb > P) nb = (int)P;
+  int rc = ensure_scratch(c, (size_t)nb * cols * sizeof(float));
+  if (rc != THZ_OK) return rc;
+  std::vector<float> part((size_t)nb * cols);
+  rc = launch_column_sums(c, c->stream, d_x, P, cols, c->d_scratch, nb);
+  if (rc != THZ_OK) return rc;
+  THZ_CUDA(c, cudaMemcpyAsync(part.data(), c->d_scratch, part.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  THZ_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int b = 0; b < nb; ++b)
+    for (int col = 0; col < cols; ++col) acc[col] += (double)part[(size_t)b * cols + col];
+  return THZ_OK;
+}
+
+int thz_mean_trace_dev(thz_ctx* c, const float* d_cube, int n, int64_t P, float* avg) {
+  CHECK_CTX(c);
+  if (!d_cube || !avg || n < 1 || P < 1) return set_err(c, THZ_EINVAL, "bad argument");
+  std::vector<double> acc((size_t)n, 0.0);
+  int rc = column_means(c, d_cube, P, n, acc);
+  if (rc != THZ_OK) return rc;
+  for (int i = 0; i < n; ++i) avg[i] = (float)(acc[i] / (double)P);
+  return THZ_OK;
+}
+
+int thz_mean_spectra_dev(thz_ctx* c, const float* d_raw, int64_t P, float* avg_fft, float* avg_amp, float* avg_phase) {
+  CHECK_CTX(c);
+  if (c->plan.n == 0) return set_err(c, THZ_ESTATE, "thz_plan_trace has not been called");
+  if (!d_raw || P < 1) return set_err(c, THZ_EINVAL, "bad argument");
+  const int n = c->plan.n, F = n / 2 + 1;
+  // spectra of a chunk of traces at a time (<= 64 MiB of scratch), never the spectral cubes
+  int64_t ct = ((int64_t)64 << 20) / ((int64_t)4 * F * sizeof(float));
+  ct = std::max<int64_t>(2, ct & ~(int64_t)1);
+  ct = std::min(ct, (P + 1) & ~(int64_t)1);
+  void* ws = nullptr;
+  int rc = ws_get(c, WS_MEANS_SPEC, (size_t)ct * 4 * F * sizeof(float), &ws);
+  if (rc != THZ_OK) return rc;
+  float* d_f = (float*)ws;
+  float* d_a = d_f + (size_t)ct * 2 * F;
+  float* d_p = d_a + (size_t)ct * F;
+  std::vector<double> sf((size_t)2 * F, 0.0), sa((size_t)F, 0.0), sp((size_t)F, 0.0);
+  for (int64_t p = 0; p < P; p += ct) {
+    const int64_t np = std::min(ct, P - p);
+    rc = launch_trace_forward(c, c->stream, d_raw + p * n, nullptr, avg_fft ? (float2*)d_f : nullptr,
+                              avg_amp ? d_a : nullptr, avg_phase ? d_p : nullptr, np);
+    // the means `ifft` takes are those of the band-passed slot (math_tools.rs:421-440 on the output of band_pass_fd)
+    if (rc == THZ_OK && c->plan.has_band && (avg_fft || avg_amp))
+      rc = launch_band_apply(c, c->stream, avg_fft ? (float2*)d_f : nullptr, avg_amp ? d_a : nullptr, np);
+    if (rc == THZ_OK && avg_fft) rc = column_means(c, d_f, np, 2 * F, sf);
+    if (rc == THZ_OK && avg_amp) rc = column_means(c, d_a, np, F, sa);
+    if (rc == THZ_OK && avg_phase) rc = column_means(c, d_p, np, F, sp);
+    if (rc != THZ_OK) return rc;
+  }
+  if (avg_fft) for (int i = 0; i < 2 * F; ++i) avg_fft[i] = (float)(sf[i] / (double)P);
+  if (avg_amp) for (int i = 0; i < F; ++i) avg_amp[i] = (float)(sa[i] / (double)P);
+  if (avg_phase) for (int i = 0; i < F; ++i) avg_phase[i] = (float)(sp[i] / (double)P);
   return THZ_OK;
 }
 

@@ -30,6 +30,10 @@ struct TracePlan {
   float2* d_chirp = nullptr;    // [n]
   float2* d_bhat = nullptr;     // [blue_m]
   float* d_hn = nullptr;        // [n]
+  // reference pulse spectrum for the normalised forward outputs (thz_plan_reference)
+  float* d_ref_amp = nullptr;   // [ref_f]
+  float* d_ref_phase = nullptr; // [ref_f]
+  int ref_f = 0;
 };
 
 constexpr int kHostStreams = 3;
@@ -65,7 +69,6 @@ struct thz_ctx {
   std::string err;
   int64_t launches = 0;
   std::map<int, std::pair<void*, size_t>> ws;    // grow-only device workspace slots (freed at destroy)
-  std::map<const void*, size_t> smem_set;        // largest dynamic smem opted in per kernel
   uint64_t fir_key = 0;                          // cache key of the uploaded FIR spectra (slot WS_FIR)
   int fir_m = 0;
   float stage_ms[4] = {0, 0, 0, 0};              // last thz_deconvolution_dev: energies, RL, apply, RL iterations
@@ -90,17 +93,22 @@ int cuda_fail(thz_ctx* c, cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return ::thz::cuda_fail((ctx), e__, #call);  \
   } while (0)
 
+// Opt a kernel in to at least `bytes` of dynamic shared memory.  The attribute belongs to the (device, kernel) pair,
+// not to a context: the cache is process-wide and only ever raises the limit (a per-context cache let a second
+// context lower it under the first one's feet).
+cudaError_t ensure_dynamic_smem(thz_ctx* c, const void* kernel, size_t bytes);
 int get_tables(thz_ctx* c, int n, const FftTables** out);
 int ensure_scratch(thz_ctx* c, size_t bytes);
 // grow-only workspace: returns a device buffer of at least `bytes` for `slot`
 int ws_get(thz_ctx* c, int slot, size_t bytes, void** out);
-enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER, WS_VOX_KERNEL, WS_VOX_HIST,
+enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER, WS_VOX_KERNEL, WS_VOX_HIST, WS_HANDOFF, WS_MEANS_SPEC,
        WS_EDGE_CORR /* + lane, lanes 0 .. kHostStreams */, WS_EDGE_CORR_LAST = WS_EDGE_CORR + kHostStreams, WS_END };
 
 // thz_trace.cu
 int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P);
 int launch_trace_forward(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_win, float2* d_fft,
-                         float* d_amp, float* d_phase, int64_t P);
+                         float* d_amp, float* d_phase, int64_t P, bool normalise = false);
+int launch_spectral_slice(thz_ctx* c, cudaStream_t s, const float* d_a, int F, int bin, float* d_out, int64_t P);
 int launch_trace_inverse(thz_ctx* c, cudaStream_t s, const float2* d_fft, bool use_band, bool use_post,
                          float* d_out, float* d_img, int64_t P);
 int launch_time_multiply(thz_ctx* c, cudaStream_t s, const float* d_in, const float* d_mult, int n, float* d_out,

@@ -938,13 +938,8 @@ static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUt
     sa.d = d;
     sa.out = out;
     auto launch = [&](auto kernel, int threads) -> cudaError_t {
-      const void* skey = (const void*)kernel;
-      size_t& shave = c->smem_set[skey];
-      if (shave < cp.ssmem) {
-        cudaError_t e2 = cudaFuncSetAttribute(skey, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.ssmem);
-        if (e2 != cudaSuccess) return e2;
-        shave = cp.ssmem;
-      }
+      cudaError_t e2 = ensure_dynamic_smem(c, (const void*)kernel, cp.ssmem);
+      if (e2 != cudaSuccess) return e2;
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = cp.sgrid;
       cfg.blockDim = dim3(threads);
@@ -968,13 +963,8 @@ static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUt
     const int tile_floats = (a.box_rows * a.box_cols + 31) & ~31;
     const size_t smem = (size_t)(2 * tile_floats + a.box_rows * kMidStride + a.kxp + a.kyp) * sizeof(float) + 256;
     if (smem <= 227 * 1024) {
-      const void* pkey = (const void*)k_rl_conv_persistent<MODE>;
-      size_t& phave = c->smem_set[pkey];
-      if (phave < smem) {
-        e = cudaFuncSetAttribute(pkey, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl persistent)");
-        phave = smem;
-      }
+      e = ensure_dynamic_smem(c, (const void*)k_rl_conv_persistent<MODE>, smem);
+      if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl persistent)");
       const int ntiles = (int)(grid.x * grid.y);
       const int nb = std::min(ntiles, c->sm_count);
       k_rl_conv_persistent<MODE><<<nb, kRlThreads, smem, s>>>(map, a, (int)grid.x, (int)grid.y);
@@ -985,12 +975,8 @@ static int launch_conv(thz_ctx* c, cudaStream_t s, const ConvPlan& cp, const CUt
     }
   }
   const void* key = cp.dense ? (const void*)k_rl_conv<MODE, true> : (const void*)k_rl_conv<MODE, false>;
-  size_t& have = c->smem_set[key];
-  if (have < cp.smem) {
-    e = cudaFuncSetAttribute(key, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp.smem);
-    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl)");
-    have = cp.smem;
-  }
+  e = ensure_dynamic_smem(c, key, cp.smem);
+  if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(rl)");
   if (cp.dense) k_rl_conv<MODE, true><<<grid, 256, cp.smem, s>>>(map, a);
   else k_rl_conv<MODE, false><<<grid, 256, cp.smem, s>>>(map, a);
   c->launches++;
@@ -1261,13 +1247,8 @@ static int slab_launch_conv(thz_slab* sl, SlabBand& b, cudaStream_t s, unsigned 
   a.sig_val = sig_val;
   const CUtensorMap& map = (MODE == 1) ? b.map_u : b.map_r;
   auto launch = [&](auto kernel, int threads) -> cudaError_t {
-    const void* skey = (const void*)kernel;
-    size_t& shave = c->smem_set[skey];
-    if (shave < b.cp.ssmem) {
-      cudaError_t e2 = cudaFuncSetAttribute(skey, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.cp.ssmem);
-      if (e2 != cudaSuccess) return e2;
-      shave = b.cp.ssmem;
-    }
+    cudaError_t e2 = ensure_dynamic_smem(c, (const void*)kernel, b.cp.ssmem);
+    if (e2 != cudaSuccess) return e2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(b.strips, b.nseg);
     cfg.blockDim = dim3(threads);

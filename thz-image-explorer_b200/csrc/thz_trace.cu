@@ -50,6 +50,10 @@ struct TraceArgs {
   float* amp;
   float* phase;
   float* win;             // windowed trace out (forward) or null
+  // reference-pulse normalisation of the forward outputs (config 2): amp -> A_s / max(A_r, 1e-12),
+  // phase -> phi_s - phi_r (the operands of calculate_optical_properties, src/math_tools.rs:665-701); null = off
+  const float* ref_amp;   // [F]
+  const float* ref_phase; // [F]
   int64_t P;
 };
 
@@ -354,8 +358,14 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_forwar
           if (act1) __stcs(a.fft + (p0 + 1) * F + k, x1);
         }
         if (a.amp != nullptr) {
-          if (act0) st_stream(a.amp + p0 * F + k, sqrtf(fmaf(x0.x, x0.x, x0.y * x0.y)));
-          if (act1) st_stream(a.amp + (p0 + 1) * F + k, sqrtf(fmaf(x1.x, x1.x, x1.y * x1.y)));
+          float a0 = sqrtf(fmaf(x0.x, x0.x, x0.y * x0.y)), a1 = sqrtf(fmaf(x1.x, x1.x, x1.y * x1.y));
+          if (a.ref_amp != nullptr) {   // uniform over the grid
+            const float r = fmaxf(__ldg(a.ref_amp + k), 1e-12f);
+            a0 = a0 / r;
+            a1 = a1 / r;
+          }
+          if (act0) st_stream(a.amp + p0 * F + k, a0);
+          if (act1) st_stream(a.amp + (p0 + 1) * F + k, a1);
         }
         if (want_phase) {
           ph0[u] = atan2f(x0.y, x0.x);
@@ -421,8 +431,9 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_forwar
       for (int u = 0; u < NU; ++u) {
         const int k = t + u * T;
         if (u < NU - 1 || t == 0) {
-          if (act0) st_stream(a.phase + p0 * F + k, phs[pad_idx(k)]);
-          if (act1) st_stream(a.phase + (p0 + 1) * F + k, phs[PF + pad_idx(k)]);
+          const float rp = (a.ref_phase != nullptr) ? __ldg(a.ref_phase + k) : 0.f;
+          if (act0) st_stream(a.phase + p0 * F + k, phs[pad_idx(k)] - rp);
+          if (act1) st_stream(a.phase + (p0 + 1) * F + k, phs[PF + pad_idx(k)] - rp);
         }
       }
     }
@@ -902,12 +913,52 @@ int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_o
   THZ_DISPATCH_N(c->plan.n, do_fused, c, s, a);
 }
 
+// amp[p][k] /= max(ref_amp[k], 1e-12), phase[p][k] -= ref_phase[k] on [P][F] arrays (chirp-z plans, whose forward
+// kernel has no normalising epilogue)
+__global__ void k_reference_normalise(float* __restrict__ amp, float* __restrict__ phase, const float* __restrict__ ref_amp,
+                                      const float* __restrict__ ref_phase, int64_t total, int F) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k = (int)(i % F);
+    if (amp) amp[i] = amp[i] / fmaxf(__ldg(ref_amp + k), 1e-12f);
+    if (phase) phase[i] = phase[i] - __ldg(ref_phase + k);
+  }
+}
+
+// out[p] = a[p][bin] for a [P][F] array: one map slice of a spectral cube
+__global__ void k_spectral_slice(const float* __restrict__ a, int F, int bin, float* __restrict__ out, int64_t P) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += stride) out[p] = __ldg(a + p * F + bin);
+}
+
+int launch_spectral_slice(thz_ctx* c, cudaStream_t s, const float* d_a, int F, int bin, float* d_out, int64_t P) {
+  if (P == 0) return THZ_OK;
+  const int blocks = (int)std::min<int64_t>((P + 255) / 256, (int64_t)c->sm_count * 8);
+  k_spectral_slice<<<blocks, 256, 0, s>>>(d_a, F, bin, d_out, P);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_spectral_slice launch");
+  return THZ_OK;
+}
+
 int launch_trace_forward(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_win, float2* d_fft, float* d_amp,
-                         float* d_phase, int64_t P) {
+                         float* d_phase, int64_t P, bool normalise) {
+  if (normalise && (!c->plan.d_ref_amp || !c->plan.d_ref_phase || c->plan.ref_f != c->plan.n / 2 + 1))
+    return set_err(c, THZ_ESTATE, "thz_plan_reference has not been called for this trace length");
   if (c->plan.n != 0 && c->plan.blue_m != 0) {
     if (P == 0) return THZ_OK;
     if (!d_in) return set_err(c, THZ_EINVAL, "null cube pointer");
-    return launch_blue_forward(c, s, d_in, d_win, d_fft, d_amp, d_phase, P);
+    int rc = launch_blue_forward(c, s, d_in, d_win, d_fft, d_amp, d_phase, P);
+    if (rc == THZ_OK && normalise && (d_amp || d_phase)) {
+      const int F = c->plan.n / 2 + 1;
+      const int64_t total = P * F;
+      const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c->sm_count * 8);
+      k_reference_normalise<<<blocks, 256, 0, s>>>(d_amp, d_phase, c->plan.d_ref_amp, c->plan.d_ref_phase, total, F);
+      c->launches++;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return cuda_fail(c, e, "k_reference_normalise launch");
+    }
+    return rc;
   }
   TraceArgs a;
   int rc = base_args(c, a, P);
@@ -921,6 +972,8 @@ int launch_trace_forward(thz_ctx* c, cudaStream_t s, const float* d_in, float* d
   a.phase = d_phase;
   a.m_pre = c->plan.has_pre ? c->plan.d_m_pre : nullptr;
   a.pre_ends = c->plan.pre_ends_only ? 1 : 0;
+  a.ref_amp = normalise ? c->plan.d_ref_amp : nullptr;
+  a.ref_phase = normalise ? c->plan.d_ref_phase : nullptr;
   THZ_DISPATCH_N(c->plan.n, do_forward, c, s, a);
 }
 
