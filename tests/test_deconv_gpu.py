@@ -368,3 +368,29 @@ def test_config3_full_chain_and_deconvolution_matches_oracle(ctx, psfs):
     e_out, e_img = rel_err(out, ref.data), rel_err(img, ref.img)
     print(f"config 3: deconvolved cube rel err {e_out:.2e}, intensity map {e_img:.2e}")
     assert e_out <= TOL_MAP and e_img <= TOL_MAP
+
+
+def test_batched_rl_equals_band_after_band(psfs, monkeypatch):
+    """Iteration i of every band that still iterates goes into ONE launch per filtering (k_rl_multi, 2 max(n_iter)
+    launches instead of 2 sum(n_iter)); THZ_RL_BATCH=off iterates band after band with the single-band kernel.
+    Same arithmetic per pixel: identical bits."""
+    psf, _ = psfs
+    w, h, n = 150, 130, 256
+    cube = synthetic_cube(w, h, n, seed=41, noise=0.02)
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w))
+    cube *= (1.0 + 0.5 * ((xx // 10 + yy // 10) % 2)).astype(F32)[:, :, None]
+    bands, why = pkg().host.Deconvolution(n_filters=8, n_iterations=60).plan(time_axis(n), (w, h), 0.5, 0.5, psf)
+    assert why is None and len({b.n_iter for b in bands}) > 3
+    outs = []
+    for mode in ("on", "off"):
+        monkeypatch.setenv("THZ_RL_BATCH", mode)
+        c = pkg().Context(0)
+        try:
+            l0 = c.launches
+            out, img, rc = c.deconvolution(cube, bands)
+            assert rc == 0
+            outs.append((out, img, c.launches - l0))
+        finally:
+            c.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] < outs[1][2]          # fewer launches

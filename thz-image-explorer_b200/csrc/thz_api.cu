@@ -155,6 +155,8 @@ int thz_ctx_create(int device, thz_ctx** out) {
   c->unstaged_fir = true;
   if (const char* f = getenv("THZ_FIR_STAGING")) c->unstaged_fir = (strcmp(f, "on") != 0);
   if (const char* f = getenv("THZ_APPLY_FORM")) c->force_split_apply = (strcmp(f, "split") == 0);
+  if (const char* f = getenv("THZ_EDGE_MMA")) c->edge_mma = (strcmp(f, "on") == 0);
+  if (const char* f = getenv("THZ_RL_BATCH")) c->rl_batch = (strcmp(f, "off") != 0);
   if (const char* f = getenv("THZ_CHAIN_CHUNK_BYTES")) {
     const long long v = atoll(f);
     if (v >= 4096) c->host_chunk_bytes = (size_t)v;

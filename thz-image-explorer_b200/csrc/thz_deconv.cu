@@ -1621,7 +1621,10 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
       }
       if (rc == THZ_OK) {
         KernelTimer kt(c, s, 1);
-        rc = launch_fir<512>(c, s, k_fir_edges, a);
+        if (c->edge_mma && edges_mma_supported(n))   // Toeplitz GEMM on the tensor cores (thz_edges_mma.cu)
+          rc = launch_fir_edges_mma(c, s, d_cube, P, n, bands, B, d_energy, bstride);
+        else
+          rc = launch_fir<512>(c, s, k_fir_edges, a);
         kt.stop();
       }
     } else {
@@ -1788,6 +1791,33 @@ using namespace thz;
     if (e_ != cudaSuccess) return cuda_fail((c), e_, "cudaSetDevice"); \
   } while (0)
 
+// Richardson-Lucy of all band images on this GPU: iteration i of every band that still iterates batched into one
+// launch per filtering (richardson_lucy_bands); band after band when a PSF does not fit that kernel or when
+// THZ_RL_BATCH=off (A/B checks).
+static int rl_all_bands(thz_ctx* c, const float* d_energy, int64_t P, int rows, int cols, const thz_band_plan* bands,
+                        int n_bands, float* d_gain, const volatile uint8_t* abort_flag, thz_progress_fn progress,
+                        void* progress_user) {
+  if (abort_flag && *abort_flag) return THZ_ABORTED;
+  int rc = THZ_SKIP_NO_PSF;
+  if (c->rl_batch)
+    rc = richardson_lucy_bands(c, c->stream, d_energy, P, rows, cols, bands, n_bands, d_gain, abort_flag, progress,
+                               progress_user, nullptr);
+  if (rc != THZ_SKIP_NO_PSF) return rc;
+  long total_iter = 0, done_iter = 0;
+  for (int b = 0; b < n_bands; ++b) total_iter += std::max(bands[b].n_iter, 1);
+  rc = THZ_OK;
+  for (int b = 0; rc == THZ_OK && b < n_bands; ++b) {
+    if (abort_flag && *abort_flag) return THZ_ABORTED;
+    const float base = 0.1f + 0.8f * (float)done_iter / (float)total_iter;
+    const float span = 0.8f * (float)std::max(bands[b].n_iter, 1) / (float)total_iter;
+    rc = richardson_lucy(c, c->stream, d_energy + (size_t)b * P, rows, cols, bands[b].psf_x, bands[b].kx,
+                         bands[b].psf_y, bands[b].ky, nullptr, bands[b].direct, bands[b].n_iter, nullptr,
+                         d_gain + (size_t)b * P, abort_flag, progress, progress_user, base, span);
+    done_iter += std::max(bands[b].n_iter, 1);
+  }
+  return rc;
+}
+
 extern "C" {
 
 int thz_deconv_energies_dev(thz_ctx* c, const float* d_cube, int64_t P, int n, const thz_band_plan* bands, int n_bands,
@@ -1824,15 +1854,8 @@ int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, i
   cudaEventRecord(ev[1], c->stream);
   long total_iter = 0, done_iter = 0;
   for (int b = 0; b < n_bands; ++b) total_iter += std::max(bands[b].n_iter, 1);
-  for (int b = 0; rc == THZ_OK && b < n_bands; ++b) {
-    if (abort_flag && *abort_flag) { rc = THZ_ABORTED; break; }
-    const float base = 0.1f + 0.8f * (float)done_iter / (float)total_iter;
-    const float span = 0.8f * (float)std::max(bands[b].n_iter, 1) / (float)total_iter;
-    rc = richardson_lucy(c, c->stream, d_energy + (size_t)b * P, rows, cols, bands[b].psf_x, bands[b].kx,
-                         bands[b].psf_y, bands[b].ky, nullptr, bands[b].direct, bands[b].n_iter, nullptr,
-                         d_gain + (size_t)b * P, abort_flag, progress, progress_user, base, span);
-    done_iter += std::max(bands[b].n_iter, 1);
-  }
+  if (rc == THZ_OK) rc = rl_all_bands(c, d_energy, P, rows, cols, bands, n_bands, d_gain, abort_flag, progress, progress_user);
+  done_iter = total_iter;
   cudaEventRecord(ev[2], c->stream);
   if (rc == THZ_OK) rc = deconv_apply(c, c->stream, d_cube, d_gain, P, n, bands, n_bands, d_out, d_img);
   cudaEventRecord(ev[3], c->stream);
@@ -1938,17 +1961,7 @@ int thz_chain_host(thz_ctx* c, const float* cube, int rows, int cols, int n, con
   int rc = chain_pass_in(c, cube, P, n, bands, n_bands, out, &d_energy, &d_gain);
   if (rc != THZ_OK) return rc;
   if (n_bands) {
-    long total_iter = 0, done_iter = 0;
-    for (int b = 0; b < n_bands; ++b) total_iter += std::max(bands[b].n_iter, 1);
-    for (int b = 0; rc == THZ_OK && b < n_bands; ++b) {
-      if (abort_flag && *abort_flag) return THZ_ABORTED;
-      const float base = 0.1f + 0.8f * (float)done_iter / (float)total_iter;
-      const float span = 0.8f * (float)std::max(bands[b].n_iter, 1) / (float)total_iter;
-      rc = richardson_lucy(c, c->stream, d_energy + (size_t)b * P, rows, cols, bands[b].psf_x, bands[b].kx,
-                           bands[b].psf_y, bands[b].ky, nullptr, bands[b].direct, bands[b].n_iter, nullptr,
-                           d_gain + (size_t)b * P, abort_flag, progress, progress_user, base, span);
-      done_iter += std::max(bands[b].n_iter, 1);
-    }
+    rc = rl_all_bands(c, d_energy, P, rows, cols, bands, n_bands, d_gain, abort_flag, progress, progress_user);
     if (rc != THZ_OK) return rc;
   }
   rc = chain_pass_out(c, P, n, bands, n_bands, out, img);

@@ -53,6 +53,13 @@ int richardson_lucy(thz_ctx* c, cudaStream_t s, const float* d_image, int rows, 
                     const float* psf_y, int ky, const float* dense, int direct, int n_iter, float* d_deconv,
                     float* d_gain, const volatile uint8_t* abort_flag, thz_progress_fn progress, void* puser,
                     float pbase, float pspan);
+int richardson_lucy_bands(thz_ctx* c, cudaStream_t s, const float* d_energy, int64_t P, int rows, int cols,
+                          const thz_band_plan* bands, int B, float* d_gain, const volatile uint8_t* abort_flag,
+                          thz_progress_fn progress, void* puser, long* iterations_run);
+// thz_edges_mma.cu
+bool edges_mma_supported(int n);
+int launch_fir_edges_mma(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
+                         int B, float* d_energy, int64_t bstride);
 
 }  // namespace thz
 
@@ -77,6 +84,10 @@ struct thz_ctx {
   struct KernelEvent { int slot; cudaEvent_t e0, e1; };
   std::vector<KernelEvent> kernel_events;        // resolved after the call's final synchronisation
   bool force_split_apply = false;                // THZ_APPLY_FORM=split: zero-padded split form for pass C (A/B checks)
+  bool edge_mma = false;                         // THZ_EDGE_MMA=on: pass-A edge energies on the tensor cores (tcgen05, TF32)
+  uint64_t edge_mma_key = 0;                     // taps the cached Toeplitz tiles (slot WS_EDGE_MMA) were built from
+  int edge_mma_bands = 0;
+  bool rl_batch = true;                          // THZ_RL_BATCH=off: Richardson-Lucy band after band (A/B checks)
   bool unstaged_fir = true;                      // FIR passes read the cube directly so that L1 keeps the tables (THZ_FIR_STAGING=on: bulk-copy staging)
   size_t host_chunk_bytes = (size_t)256 << 20;   // chunk of the host-pointer pipelines (THZ_CHAIN_CHUNK_BYTES, tests shrink it)
   float* d_scratch = nullptr;                    // reductions
@@ -101,7 +112,7 @@ int get_tables(thz_ctx* c, int n, const FftTables** out);
 int ensure_scratch(thz_ctx* c, size_t bytes);
 // grow-only workspace: returns a device buffer of at least `bytes` for `slot`
 int ws_get(thz_ctx* c, int slot, size_t bytes, void** out);
-enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER, WS_VOX_KERNEL, WS_VOX_HIST, WS_HANDOFF, WS_MEANS_SPEC,
+enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER, WS_VOX_KERNEL, WS_VOX_HIST, WS_HANDOFF, WS_MEANS_SPEC, WS_RL_MULTI, WS_EDGE_MMA,
        WS_EDGE_CORR /* + lane, lanes 0 .. kHostStreams */, WS_EDGE_CORR_LAST = WS_EDGE_CORR + kHostStreams, WS_END };
 
 // thz_trace.cu
@@ -141,5 +152,8 @@ int launch_blue_forward(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_
                         float* d_phase, int64_t P);
 int launch_blue_inverse(thz_ctx* c, cudaStream_t s, const float2* d_fft, bool use_band, bool use_post, float* d_out,
                         float* d_img, int64_t P);
+int richardson_lucy_bands(thz_ctx* c, cudaStream_t s, const float* d_energy, int64_t P, int rows, int cols,
+                          const thz_band_plan* bands, int B, float* d_gain, const volatile uint8_t* abort_flag,
+                          thz_progress_fn progress, void* puser, long* iterations_run);
 
 }  // namespace thz

@@ -522,10 +522,28 @@ __device__ __forceinline__ void slab_signal(unsigned long long* cnt, unsigned lo
   }
 }
 
-template <int MODE, int SW, class SL>
-__global__ void __launch_bounds__(SW * 4, (SW == 64) ? 2 : 1) k_rl_stream(const __grid_constant__ CUtensorMap tmap,
-                                                                         const StreamArgs a, const SL sl) {
-  constexpr bool SLAB = !std::is_same<SL, NoSlab>::value;
+// what one CTA needs of the slab bookkeeping, in registers (the segment table stays where it is)
+struct SlabCore {
+  int row_off = 0, halo = 0, own = 0;
+  bool top = false, bottom = false;          // this CTA belongs to the first / last segment
+  float* up_out = nullptr;
+  float* down_out = nullptr;
+  const unsigned long long* wait_up = nullptr;
+  const unsigned long long* wait_down = nullptr;
+  unsigned long long wait_val = 0;
+  unsigned long long* cnt_up = nullptr;
+  unsigned long long* cnt_down = nullptr;
+  unsigned long long cnt_target = 0;
+  unsigned long long* sig_up = nullptr;
+  unsigned long long* sig_down = nullptr;
+  unsigned long long sig_val = 0;
+  int* err = nullptr;
+};
+
+// The strip march itself: CTA (strip bx, output rows [seg_row0, seg_row0 + rows_out)) of one filtering.
+template <int MODE, int SW, bool SLAB>
+__device__ __forceinline__ void rl_stream_body(const CUtensorMap* tmap, const StreamArgs& a, const SlabCore& sl, int bx,
+                                               int seg_row0, int rows_out) {
   constexpr int kSW = SW, kStThreads = SW * 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -536,17 +554,8 @@ __global__ void __launch_bounds__(SW * 4, (SW == 64) ? 2 : 1) k_rl_stream(const 
   float* wxs = ring + kSW * a.RS;
   float* wys = wxs + a.WU + 8;
   const int tid = threadIdx.x;
-  const int col0 = blockIdx.x * kSW + a.col_shift;
-  int seg_row0, rows_out, row_off = 0;
-  if constexpr (SLAB) {
-    seg_row0 = sl.seg_start[blockIdx.y];
-    rows_out = sl.seg_start[blockIdx.y + 1] - seg_row0;
-    row_off = sl.row_off;
-  } else {
-    seg_row0 = blockIdx.y * a.seg_rows;
-    rows_out = min(a.seg_rows, a.Hp - seg_row0);
-  }
-  if (rows_out <= 0) return;
+  const int col0 = bx * kSW + a.col_shift;
+  const int row_off = SLAB ? sl.row_off : 0;
   const int n_chunks = (rows_out + a.WU + kCR - 1) / kCR;
   const int gy0 = row_off + seg_row0 - a.gy_off, gx0 = col0 - a.gx_off;
   const uint32_t tile_bytes = (uint32_t)(tile_floats * sizeof(float));
@@ -569,14 +578,14 @@ __global__ void __launch_bounds__(SW * 4, (SW == 64) ? 2 : 1) k_rl_stream(const 
     if constexpr (SLAB) {
       // boundary segments read the neighbours' rows: wait for the version this kernel consumes (the other
       // threads block on the first chunk's mbarrier); the TMA reads below are ordered after the acquire
-      if (blockIdx.y == 0 && sl.wait_up) slab_wait(sl.wait_up, sl.wait_val, sl.err);
-      if (blockIdx.y == gridDim.y - 1 && sl.wait_down) slab_wait(sl.wait_down, sl.wait_val, sl.err);
+      if (sl.top && sl.wait_up) slab_wait(sl.wait_up, sl.wait_val, sl.err);
+      if (sl.bottom && sl.wait_down) slab_wait(sl.wait_down, sl.wait_val, sl.err);
       asm volatile("fence.proxy.async.global;" ::: "memory");
     }
     for (int j = 0; j < 2 && j < n_chunks; ++j)
       if (live(j)) {
         mbar_expect_tx(mbar0 + 8 * j, tile_bytes);
-        tma_load_2d(smem_u32(tile0 + j * tile_floats), &tmap, gx0, gy0 + kCR * j, mbar0 + 8 * j);
+        tma_load_2d(smem_u32(tile0 + j * tile_floats), tmap, gx0, gy0 + kCR * j, mbar0 + 8 * j);
       }
   }
   uint32_t ph0 = 0, ph1 = 0;   // mbarrier phase parity per buffer
@@ -623,7 +632,7 @@ __global__ void __launch_bounds__(SW * 4, (SW == 64) ? 2 : 1) k_rl_stream(const 
     __syncthreads();   // ring rows of chunk j are visible; tile[buf] is free
     if (tid == 0 && j + 2 < n_chunks && live(j + 2)) {
       mbar_expect_tx(mbar0 + 8 * buf, tile_bytes);
-      tma_load_2d(smem_u32(tile0 + buf * tile_floats), &tmap, gx0, gy0 + kCR * (j + 2), mbar0 + 8 * buf);
+      tma_load_2d(smem_u32(tile0 + buf * tile_floats), tmap, gx0, gy0 + kCR * (j + 2), mbar0 + 8 * buf);
     }
     // ---- row pass ----
     if (i0 < hi) {
@@ -656,9 +665,96 @@ __global__ void __launch_bounds__(SW * 4, (SW == 64) ? 2 : 1) k_rl_stream(const 
     }
   }
   if constexpr (SLAB) {
-    if (blockIdx.y == 0 && sl.sig_up) slab_signal(sl.cnt_up, sl.cnt_target, sl.sig_up, sl.sig_val);
-    if (blockIdx.y == gridDim.y - 1 && sl.sig_down) slab_signal(sl.cnt_down, sl.cnt_target, sl.sig_down, sl.sig_val);
+    if (sl.top && sl.sig_up) slab_signal(sl.cnt_up, sl.cnt_target, sl.sig_up, sl.sig_val);
+    if (sl.bottom && sl.sig_down) slab_signal(sl.cnt_down, sl.cnt_target, sl.sig_down, sl.sig_val);
   }
+}
+
+template <int MODE, int SW, class SL>
+__global__ void __launch_bounds__(SW * 4, (SW == 64) ? 2 : 1) k_rl_stream(const __grid_constant__ CUtensorMap tmap,
+                                                                         const StreamArgs a, const SL sl) {
+  constexpr bool SLAB = !std::is_same<SL, NoSlab>::value;
+  SlabCore core;
+  int seg_row0, rows_out;
+  if constexpr (SLAB) {
+    seg_row0 = sl.seg_start[blockIdx.y];
+    rows_out = sl.seg_start[blockIdx.y + 1] - seg_row0;
+    core.row_off = sl.row_off; core.halo = sl.halo; core.own = sl.own;
+    core.top = blockIdx.y == 0; core.bottom = blockIdx.y == gridDim.y - 1;
+    core.up_out = sl.up_out; core.down_out = sl.down_out;
+    core.wait_up = sl.wait_up; core.wait_down = sl.wait_down; core.wait_val = sl.wait_val;
+    core.cnt_up = sl.cnt_up; core.cnt_down = sl.cnt_down; core.cnt_target = sl.cnt_target;
+    core.sig_up = sl.sig_up; core.sig_down = sl.sig_down; core.sig_val = sl.sig_val;
+    core.err = sl.err;
+  } else {
+    seg_row0 = blockIdx.y * a.seg_rows;
+    rows_out = min(a.seg_rows, a.Hp - seg_row0);
+  }
+  if (rows_out <= 0) return;
+  rl_stream_body<MODE, SW, SLAB>(&tmap, a, core, blockIdx.x, seg_row0, rows_out);
+}
+
+// ---- all bands that still iterate, in ONE launch per filtering -----------------------------------------------
+// Richardson-Lucy runs once per FIR band with very different iteration counts (423, 251, 127, 46, 13, 4, 3, 1 for
+// the shipped PSF and 8 bands).  Band after band that is 2 * sum(n_iter) = 1736 dependent launches; batching
+// iteration i of every band with n_iter > i into one launch (blockIdx.z = band) leaves 2 * max(n_iter) = 846, and
+// the launches of the small slabs of a multi-GPU run fill the SMs with several bands at once.  Per-band arguments
+// (tensor maps included) live in device memory.
+struct BandLaunch {
+  CUtensorMap map_u, map_r;           // 128-byte objects, the struct is 128-byte aligned
+  StreamArgs sa;                      // geometry; wx / wy / d / out are set per filtering in the kernel
+  const float* taps[2];               // [orientation] -> wx' (WU + 8) | wy' (KW + 8)
+  float *d, *u, *r;
+  int strips, nseg, n_iter, uniform_seg_rows;   // uniform_seg_rows > 0: segments of that many rows (unsharded)
+  // slab form
+  int row_off, halo, own;
+  int seg_start[kMaxSlabSegs + 1];
+  float *up_u, *down_u, *up_r, *down_r;
+  const unsigned long long *wait_u_up, *wait_u_down, *wait_r_up, *wait_r_down;
+  unsigned long long *cnt_u_up, *cnt_u_down, *cnt_r_up, *cnt_r_down;
+  unsigned long long *sig_u_up, *sig_u_down, *sig_r_up, *sig_r_down;
+  unsigned long long u_base, r_base, cnt_u_base, cnt_r_base;   // values at the start of the run
+  int* err;
+};
+
+template <int MODE, bool SLAB>
+__global__ void __launch_bounds__(256, 2) k_rl_multi(const BandLaunch* __restrict__ bl, int it) {
+  const BandLaunch& B = bl[blockIdx.z];
+  if (it >= B.n_iter || (int)blockIdx.x >= B.strips || (int)blockIdx.y >= B.nseg) return;
+  StreamArgs a = B.sa;
+  const float* tp = B.taps[MODE == 1 ? 0 : 1];
+  a.wx = tp;
+  a.wy = tp + a.WU + 8;
+  a.d = B.d;
+  a.out = (MODE == 1) ? B.r : B.u;
+  SlabCore core;
+  int seg_row0, rows_out;
+  if constexpr (SLAB) {
+    seg_row0 = B.seg_start[blockIdx.y];
+    rows_out = B.seg_start[blockIdx.y + 1] - seg_row0;
+    core.row_off = B.row_off; core.halo = B.halo; core.own = B.own;
+    core.top = blockIdx.y == 0; core.bottom = (int)blockIdx.y == B.nseg - 1;
+    const unsigned long long i = (unsigned long long)it;
+    if constexpr (MODE == 1) {        // consumes u version u_base + it, publishes r version r_base + it
+      core.up_out = B.up_r; core.down_out = B.down_r;
+      core.wait_up = B.wait_u_up; core.wait_down = B.wait_u_down; core.wait_val = B.u_base + i;
+      core.cnt_up = B.cnt_r_up; core.cnt_down = B.cnt_r_down;
+      core.cnt_target = B.cnt_r_base + (i + 1ull) * (unsigned long long)B.strips;
+      core.sig_up = B.sig_r_up; core.sig_down = B.sig_r_down; core.sig_val = B.r_base + i;
+    } else {                          // consumes r version r_base + it, publishes u version u_base + it + 1
+      core.up_out = B.up_u; core.down_out = B.down_u;
+      core.wait_up = B.wait_r_up; core.wait_down = B.wait_r_down; core.wait_val = B.r_base + i;
+      core.cnt_up = B.cnt_u_up; core.cnt_down = B.cnt_u_down;
+      core.cnt_target = B.cnt_u_base + (i + 1ull) * (unsigned long long)B.strips;
+      core.sig_up = B.sig_u_up; core.sig_down = B.sig_u_down; core.sig_val = B.u_base + i + 1ull;
+    }
+    core.err = B.err;
+  } else {
+    seg_row0 = blockIdx.y * B.uniform_seg_rows;
+    rows_out = min(B.uniform_seg_rows, a.Hp - seg_row0);
+  }
+  if (rows_out <= 0) return;
+  rl_stream_body<MODE, 64, SLAB>((MODE == 1) ? &B.map_u : &B.map_r, a, core, blockIdx.x, seg_row0, rows_out);
 }
 
 // Start of a slab run: u_0 = d on the own rows; the boundary rows go to the neighbours' halos and the version is
@@ -1068,6 +1164,145 @@ int richardson_lucy(thz_ctx* c, cudaStream_t s, const float* d_image, int rows, 
 }
 
 
+// one filtering of every band that still iterates (k_rl_multi); `active` = bands with n_iter > it
+template <int MODE, bool SLAB>
+static int launch_multi(thz_ctx* c, cudaStream_t s, const BandLaunch* d_bl, int active, int grid_x, int grid_y,
+                        size_t smem, int it) {
+  auto kernel = k_rl_multi<MODE, SLAB>;
+  cudaError_t e = ensure_dynamic_smem(c, (const void*)kernel, smem);
+  if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(k_rl_multi)");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid_x, grid_y, active);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kernel, d_bl, it);
+  c->launches++;
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_multi launch");
+  return THZ_OK;
+}
+
+static void fill_band_launch_common(BandLaunch& L, const ConvPlan& cp, const CUtensorMap& map_u, const CUtensorMap& map_r,
+                                    float* d, float* u, float* r, int n_iter) {
+  memset(&L, 0, sizeof L);
+  L.map_u = map_u;
+  L.map_r = map_r;
+  L.sa = cp.sa;
+  L.taps[0] = cp.d_ws;
+  L.taps[1] = cp.d_ws + cp.swstride;
+  L.d = d; L.u = u; L.r = r;
+  L.strips = (int)cp.sgrid.x;
+  L.n_iter = n_iter;
+}
+
+// `richardson_lucy` + clamp + gain for ALL bands of a deconvolution on one GPU, iteration i of every band that
+// still iterates batched into one launch per filtering.  Returns THZ_SKIP_NO_PSF (never an error of its own)
+// when a band's PSF does not run on the 64-column streaming kernel: the caller then iterates band after band.
+int richardson_lucy_bands(thz_ctx* c, cudaStream_t s, const float* d_energy, int64_t P, int rows, int cols,
+                          const thz_band_plan* bands, int B, float* d_gain, const volatile uint8_t* abort_flag,
+                          thz_progress_fn progress, void* puser, long* iterations_run) {
+  if (B < 1 || B > THZ_MAX_BANDS) return set_err(c, THZ_EINVAL, "bad band count");
+  struct Geo { int pad_y, pad_x, Hp, Wp, pitch; size_t img_bytes; };
+  std::vector<Geo> g((size_t)B);
+  size_t total = 0;
+  for (int b = 0; b < B; ++b) {
+    const int kx = bands[b].kx, ky = bands[b].ky;
+    if (kx < 1 || ky < 1 || !(kx & 1) || !(ky & 1) || kx > THZ_MAX_PSF || ky > THZ_MAX_PSF) return THZ_SKIP_NO_PSF;
+    g[b].pad_y = kx / 2; g[b].pad_x = ky / 2;
+    if (g[b].pad_y >= rows - 1 || g[b].pad_x >= cols - 1) return set_err(c, THZ_EINVAL, "PSF larger than the image");
+    g[b].Hp = rows + 2 * g[b].pad_y; g[b].Wp = cols + 2 * g[b].pad_x; g[b].pitch = round_up(g[b].Wp, 4);
+    g[b].img_bytes = ((size_t)g[b].Hp * g[b].pitch * sizeof(float) + 1023) & ~(size_t)1023;
+    total += 3 * g[b].img_bytes + kConvTapFloats * sizeof(float);
+  }
+  const size_t launch_bytes = ((size_t)B * sizeof(BandLaunch) + 1023) & ~(size_t)1023;
+  void* ws = nullptr;
+  int rc = ws_get(c, WS_RL_MULTI, total + launch_bytes, &ws);
+  if (rc != THZ_OK) return rc;
+  unsigned char* base = (unsigned char*)ws;
+  BandLaunch* d_bl = reinterpret_cast<BandLaunch*>(base);
+  unsigned char* cur = base + launch_bytes;
+  std::vector<BandLaunch> h((size_t)B);
+  std::vector<int> order((size_t)B);
+  for (int b = 0; b < B; ++b) order[b] = b;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bands[x].n_iter > bands[y].n_iter; });
+  struct Buf { float *d, *u, *r; };
+  std::vector<Buf> bufs((size_t)B);
+  size_t smem = 0;
+  int grid_x = 1, grid_y = 1, max_iter = 0;
+  for (int b = 0; b < B; ++b) {
+    float* taps = reinterpret_cast<float*>(cur);
+    cur += kConvTapFloats * sizeof(float);
+    bufs[b].d = reinterpret_cast<float*>(cur); cur += g[b].img_bytes;
+    bufs[b].u = reinterpret_cast<float*>(cur); cur += g[b].img_bytes;
+    bufs[b].r = reinterpret_cast<float*>(cur); cur += g[b].img_bytes;
+  }
+  THZ_CUDA(c, cudaStreamSynchronize(s));   // nothing of a previous run still reads the taps / launch table
+  for (int z = 0; z < B; ++z) {
+    const int b = order[z];
+    ConvPlan cp;
+    float* taps = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bufs[b].d) - kConvTapFloats * sizeof(float));
+    rc = make_conv_plan(c, s, g[b].Hp, g[b].Wp, g[b].pitch, bands[b].psf_x, bands[b].kx, bands[b].psf_y, bands[b].ky,
+                        nullptr, bands[b].direct ? 1 : 0, cp, taps);
+    if (rc != THZ_OK) return rc;
+    if (!cp.streaming || cp.sw != 64) return THZ_SKIP_NO_PSF;
+    CUtensorMap map_u, map_r;
+    rc = make_tmap(c, &map_u, bufs[b].u, g[b].Hp, g[b].Wp, g[b].pitch, kCR, cp.sa.bc);
+    if (rc == THZ_OK) rc = make_tmap(c, &map_r, bufs[b].r, g[b].Hp, g[b].Wp, g[b].pitch, kCR, cp.sa.bc);
+    if (rc != THZ_OK) return rc;
+    fill_band_launch_common(h[z], cp, map_u, map_r, bufs[b].d, bufs[b].u, bufs[b].r, bands[b].n_iter);
+    h[z].nseg = (int)cp.sgrid.y;
+    h[z].uniform_seg_rows = cp.sa.seg_rows;
+    smem = std::max(smem, cp.ssmem);
+    grid_x = std::max(grid_x, h[z].strips);
+    grid_y = std::max(grid_y, h[z].nseg);
+    max_iter = std::max(max_iter, bands[b].n_iter);
+    // d = reflect-padded band image, u_0 = d, r = 0 (its pitch padding and the rows TMA never writes stay 0)
+    THZ_CUDA(c, cudaMemsetAsync(bufs[b].d, 0, g[b].img_bytes, s));
+    k_reflect_pad<<<grid_for(c, (int64_t)g[b].Hp * g[b].Wp), 256, 0, s>>>(d_energy + (size_t)b * P, rows, cols, g[b].pad_y,
+                                                                       g[b].pad_x, bufs[b].d, g[b].pitch);
+    c->launches++;
+    THZ_CUDA(c, cudaMemcpyAsync(bufs[b].u, bufs[b].d, g[b].img_bytes, cudaMemcpyDeviceToDevice, s));
+    THZ_CUDA(c, cudaMemsetAsync(bufs[b].r, 0, g[b].img_bytes, s));
+  }
+  THZ_CUDA(c, cudaMemcpyAsync(d_bl, h.data(), (size_t)B * sizeof(BandLaunch), cudaMemcpyHostToDevice, s));
+  long total_iter = 0, done_iter = 0;
+  for (int b = 0; b < B; ++b) total_iter += std::max(bands[b].n_iter, 1);
+  bool aborted = false;
+  for (int it = 0; rc == THZ_OK && it < max_iter; ++it) {
+    int active = 0;
+    while (active < B && h[active].n_iter > it) ++active;
+    rc = launch_multi<1, false>(c, s, d_bl, active, grid_x, grid_y, smem, it);          // r = d / (u (*) psf + eps)
+    if (rc == THZ_OK) rc = launch_multi<2, false>(c, s, d_bl, active, grid_x, grid_y, smem, it);   // u *= r (*) mirror
+    done_iter += active;
+    if ((it & 15) == 15 || it == max_iter - 1) {
+      if (abort_flag && *abort_flag) { aborted = true; break; }
+      if (progress || abort_flag) {
+        cudaError_t e = cudaStreamSynchronize(s);   // keep the queue short so that abort is responsive
+        if (e != cudaSuccess) { rc = cuda_fail(c, e, "richardson_lucy_bands"); break; }
+        if (progress) progress(0.1f + 0.8f * (float)done_iter / (float)total_iter, puser);
+      }
+    }
+  }
+  if (rc == THZ_OK && !aborted)
+    for (int b = 0; b < B; ++b) {
+      k_rl_finish<<<grid_for(c, (int64_t)rows * cols), 256, 0, s>>>(bufs[b].u, g[b].pitch, g[b].pad_y, g[b].pad_x, rows,
+                                                                    cols, d_energy + (size_t)b * P, nullptr,
+                                                                    d_gain + (size_t)b * P);
+      c->launches++;
+    }
+  if (iterations_run) *iterations_run = done_iter;
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (rc == THZ_OK && e != cudaSuccess) return cuda_fail(c, e, "richardson_lucy_bands");
+  if (rc == THZ_OK && aborted) return THZ_ABORTED;
+  return rc;
+}
+
 // ------------------------------------------------------------------------------------
 // Row-slab Richardson-Lucy over several GPUs: every rank iterates its own rows of the padded
 // domain; the kx/2 boundary rows travel as peer stores inside the filtering kernels (see SlabArgs).
@@ -1112,6 +1347,7 @@ struct thz_slab {
   std::vector<thz::SlabBand> bands;
   std::vector<unsigned char> key;   // geometry + PSF bytes of the current plan
   cudaStream_t stream = nullptr;    // stream the run is launched on (the context's by default)
+  void* d_launch = nullptr;         // BandLaunch table of the batched kernels
 };
 
 namespace thz {
@@ -1304,14 +1540,6 @@ static int slab_band_begin(thz_slab* sl, SlabBand& b, cudaStream_t s, const floa
   return THZ_OK;
 }
 
-static int slab_band_iterate(thz_slab* sl, SlabBand& b, cudaStream_t s, int it) {
-  // K1 consumes u version u_next + it and publishes r version r_next + it; K2 consumes that and publishes u + 1
-  int rc = slab_launch_conv<1>(sl, b, s, b.u_next + (unsigned long long)it, b.r_next + (unsigned long long)it);
-  if (rc == THZ_OK)
-    rc = slab_launch_conv<2>(sl, b, s, b.r_next + (unsigned long long)it, b.u_next + (unsigned long long)it + 1ull);
-  return rc;
-}
-
 static int slab_band_end(thz_slab* sl, SlabBand& b, cudaStream_t s, const float* d_energy_b, float* d_deconv_b,
                          float* d_gain_b) {
   thz_ctx* c = sl->ctx;
@@ -1329,8 +1557,45 @@ static int slab_band_end(thz_slab* sl, SlabBand& b, cudaStream_t s, const float*
   return THZ_OK;
 }
 
-// One run over all bands for a set of ranks that live in this process.  `serial` = the ranks share one GPU (the
-// single-GPU emulation used by the tests): every kernel goes to ONE stream in dependency order, so that no
+// launch table of a slab run: one BandLaunch per band, bands sorted by falling iteration count; the version /
+// counter bases are those at the start of the run, after the start-of-run push
+static void slab_fill_launch(thz_slab* sl, std::vector<BandLaunch>& h, std::vector<int>& order) {
+  const int B = (int)sl->bands.size();
+  order.resize((size_t)B);
+  for (int b = 0; b < B; ++b) order[b] = b;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return sl->bands[x].n_iter > sl->bands[y].n_iter; });
+  h.resize((size_t)B);
+  for (int z = 0; z < B; ++z) {
+    SlabBand& b = sl->bands[order[z]];
+    BandLaunch& L = h[z];
+    fill_band_launch_common(L, b.cp, b.map_u, b.map_r, reinterpret_cast<float*>(sl->arena + b.off_d),
+                            reinterpret_cast<float*>(sl->arena + b.off_u), reinterpret_cast<float*>(sl->arena + b.off_r),
+                            b.n_iter);
+    L.strips = b.strips;
+    L.nseg = b.nseg;
+    L.row_off = b.halo; L.halo = b.halo; L.own = b.own;
+    for (int i = 0; i <= b.nseg; ++i) L.seg_start[i] = b.seg_start[i];
+    const bool has_up = sl->up && b.halo > 0, has_down = sl->down && b.halo > 0;
+    L.up_u = slab_up_dst(sl, b, b.off_u); L.down_u = slab_down_dst(sl, b, b.off_u);
+    L.up_r = slab_up_dst(sl, b, b.off_r); L.down_r = slab_down_dst(sl, b, b.off_r);
+    L.wait_u_up = has_up ? slab_flag(sl->arena, b, F_U_FROM_UP) : nullptr;
+    L.wait_u_down = has_down ? slab_flag(sl->arena, b, F_U_FROM_DOWN) : nullptr;
+    L.wait_r_up = has_up ? slab_flag(sl->arena, b, F_R_FROM_UP) : nullptr;
+    L.wait_r_down = has_down ? slab_flag(sl->arena, b, F_R_FROM_DOWN) : nullptr;
+    L.cnt_u_up = slab_flag(sl->arena, b, F_CNT_U_UP); L.cnt_u_down = slab_flag(sl->arena, b, F_CNT_U_DOWN);
+    L.cnt_r_up = slab_flag(sl->arena, b, F_CNT_R_UP); L.cnt_r_down = slab_flag(sl->arena, b, F_CNT_R_DOWN);
+    L.sig_u_up = has_up ? slab_flag(sl->up, b, F_U_FROM_DOWN) : nullptr;
+    L.sig_u_down = has_down ? slab_flag(sl->down, b, F_U_FROM_UP) : nullptr;
+    L.sig_r_up = has_up ? slab_flag(sl->up, b, F_R_FROM_DOWN) : nullptr;
+    L.sig_r_down = has_down ? slab_flag(sl->down, b, F_R_FROM_UP) : nullptr;
+    L.u_base = b.u_next; L.r_base = b.r_next;
+    L.cnt_u_base = b.cnt_u; L.cnt_r_base = b.cnt_r;
+    L.err = reinterpret_cast<int*>(sl->arena);
+  }
+}
+
+// One run over all bands for a set of ranks that live in this process.  `nranks` > 1 = the ranks share one GPU
+// (the single-GPU emulation used by the tests): every kernel goes to ONE stream in dependency order, so that no
 // kernel ever waits for one that has not been launched ahead of it.
 int slab_run(thz_slab* const* ranks, int nranks, const float* const* d_energy, const int64_t* bstride,
              float* const* d_gain, float* const* d_deconv) {
@@ -1342,17 +1607,60 @@ int slab_run(thz_slab* const* ranks, int nranks, const float* const* d_energy, c
     if (sl->bands.size() != B) return set_err(sl->ctx, THZ_ESTATE, "ranks hold different plans");
   }
   int rc = THZ_OK;
-  for (size_t b = 0; rc == THZ_OK && b < B; ++b) {
+  // start of the run: every band's d, u_0 and the first push of boundary rows
+  for (size_t b = 0; rc == THZ_OK && b < B; ++b)
     for (int r = 0; rc == THZ_OK && r < nranks; ++r) {
       thz_slab* sl = ranks[r];
       cudaSetDevice(sl->ctx->device);
       rc = slab_band_begin(sl, sl->bands[b], sl->stream, d_energy[r] + b * (size_t)bstride[r]);
     }
-    const int n_iter = ranks[0]->bands[b].n_iter;
-    for (int it = 0; rc == THZ_OK && it < n_iter; ++it) {
-      if (nranks == 1) {
-        rc = slab_band_iterate(ranks[0], ranks[0]->bands[b], ranks[0]->stream, it);
-      } else {
+  bool batched = ranks[0]->ctx->rl_batch;
+  for (int r = 0; r < nranks; ++r)
+    for (const SlabBand& b : ranks[r]->bands) batched = batched && b.cp.sw == 64;
+  if (rc == THZ_OK && batched) {
+    int max_iter = 0;
+    std::vector<std::vector<BandLaunch>> h((size_t)nranks);
+    std::vector<int> order;
+    struct G { int gx = 1, gy = 1; size_t smem = 0; };
+    std::vector<G> g((size_t)nranks);
+    for (int r = 0; rc == THZ_OK && r < nranks; ++r) {
+      thz_slab* sl = ranks[r];
+      cudaSetDevice(sl->ctx->device);
+      slab_fill_launch(sl, h[r], order);
+      for (const BandLaunch& L : h[r]) {
+        g[r].gx = std::max(g[r].gx, L.strips);
+        g[r].gy = std::max(g[r].gy, L.nseg);
+        max_iter = std::max(max_iter, L.n_iter);
+      }
+      for (const SlabBand& b : sl->bands) g[r].smem = std::max(g[r].smem, b.cp.ssmem);
+      if (!sl->d_launch) {
+        void* p = nullptr;
+        THZ_CUDA(sl->ctx, cudaMalloc(&p, THZ_MAX_BANDS * sizeof(BandLaunch)));
+        sl->d_launch = p;
+      }
+      THZ_CUDA(sl->ctx, cudaMemcpyAsync(sl->d_launch, h[r].data(), B * sizeof(BandLaunch), cudaMemcpyHostToDevice,
+                                        sl->stream));
+    }
+    for (int it = 0; rc == THZ_OK && it < max_iter; ++it) {
+      int active = 0;
+      while (active < (int)B && h[0][active].n_iter > it) ++active;
+      for (int r = 0; rc == THZ_OK && r < nranks; ++r)
+        rc = launch_multi<1, true>(ranks[r]->ctx, ranks[r]->stream, (const BandLaunch*)ranks[r]->d_launch, active, g[r].gx,
+                                   g[r].gy, g[r].smem, it);
+      for (int r = 0; rc == THZ_OK && r < nranks; ++r)
+        rc = launch_multi<2, true>(ranks[r]->ctx, ranks[r]->stream, (const BandLaunch*)ranks[r]->d_launch, active, g[r].gx,
+                                   g[r].gy, g[r].smem, it);
+    }
+    // the counters the kernels advanced
+    for (int r = 0; r < nranks; ++r)
+      for (SlabBand& b : ranks[r]->bands) {
+        b.cnt_u += (unsigned long long)b.n_iter * (unsigned long long)b.strips;
+        b.cnt_r += (unsigned long long)b.n_iter * (unsigned long long)b.strips;
+      }
+  } else {
+    for (size_t b = 0; rc == THZ_OK && b < B; ++b) {
+      const int n_iter = ranks[0]->bands[b].n_iter;
+      for (int it = 0; rc == THZ_OK && it < n_iter; ++it) {
         for (int r = 0; rc == THZ_OK && r < nranks; ++r) {
           thz_slab* sl = ranks[r];
           SlabBand& bb = sl->bands[b];
@@ -1366,13 +1674,15 @@ int slab_run(thz_slab* const* ranks, int nranks, const float* const* d_energy, c
         }
       }
     }
+  }
+  for (size_t b = 0; rc == THZ_OK && b < B; ++b)
     for (int r = 0; rc == THZ_OK && r < nranks; ++r) {
       thz_slab* sl = ranks[r];
+      cudaSetDevice(sl->ctx->device);
       rc = slab_band_end(sl, sl->bands[b], sl->stream, d_energy[r] + b * (size_t)bstride[r],
                          d_deconv && d_deconv[r] ? d_deconv[r] + b * (size_t)bstride[r] : nullptr,
                          d_gain[r] + b * (size_t)bstride[r]);
     }
-  }
   return rc;
 }
 
@@ -1449,6 +1759,7 @@ void thz_slab_destroy(thz_slab* sl) {
   cudaStreamSynchronize(sl->stream);
   slab_disconnect(sl);
   if (sl->arena) cudaFree(sl->arena);
+  if (sl->d_launch) cudaFree(sl->d_launch);
   delete sl;
 }
 
