@@ -513,7 +513,9 @@ def run_ours(a):
         # writes the cube, reads B gains and 2 x 249 corrections and writes the intensity
         stages["deconv_energy_spectra"] = {"ms": km["energy_spectra_ms"], "kernel": f"k_fir_energy_split<{N}>",
                                            "algorithmic_bytes": (4 * N + 4 * B) * P}
-        stages["deconv_energy_edges"] = {"ms": km["energy_edges_ms"], "kernel": "k_fir_edges",
+        edge_kernel = ("k_fir_edges_mma (tcgen05 kind::tf32)" if (N >= 2048 and os.environ.get("THZ_EDGE_MMA", "on") != "off")
+                       else "k_fir_edges")
+        stages["deconv_energy_edges"] = {"ms": km["energy_edges_ms"], "kernel": edge_kernel,
                                          "algorithmic_bytes": (4 * 498 + 8 * B) * P}
         stages["deconv_apply_edges"] = {"ms": km["apply_edges_ms"], "kernel": "k_fir_edge_corr",
                                         "algorithmic_bytes": (4 * 498 + 4 * B + 4 * 498) * P}

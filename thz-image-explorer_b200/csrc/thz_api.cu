@@ -155,7 +155,7 @@ int thz_ctx_create(int device, thz_ctx** out) {
   c->unstaged_fir = true;
   if (const char* f = getenv("THZ_FIR_STAGING")) c->unstaged_fir = (strcmp(f, "on") != 0);
   if (const char* f = getenv("THZ_APPLY_FORM")) c->force_split_apply = (strcmp(f, "split") == 0);
-  if (const char* f = getenv("THZ_EDGE_MMA")) c->edge_mma = (strcmp(f, "on") == 0);
+  if (const char* f = getenv("THZ_EDGE_MMA")) c->edge_mma = (strcmp(f, "off") != 0);
   if (const char* f = getenv("THZ_RL_BATCH")) c->rl_batch = (strcmp(f, "off") != 0);
   if (const char* f = getenv("THZ_CHAIN_CHUNK_BYTES")) {
     const long long v = atoll(f);
@@ -286,6 +286,22 @@ int thz_plan_trace(thz_ctx* c, int n, const float* m_pre, const float* band, con
   if (!pow2 && !blue_supported(n))
     return set_err(c, THZ_EINVAL, "n must be a power of two in [64, 8192] or any length in [2, 4096]");
   int rc;
+  // the reference's stage functions rebuild their window per call (math_tools.rs:356-371) and so do the shims that
+  // mirror them: an identical plan is recognised here and costs nothing (no synchronisation, no upload)
+  {
+    TracePlan& q = c->plan;
+    auto same = [](const std::vector<float>& have, const float* want, size_t len) {
+      if (!want) return have.empty();
+      return have.size() == len && memcmp(have.data(), want, len * sizeof(float)) == 0;
+    };
+    if (q.n == n && q.valid && same(q.h_pre, m_pre, (size_t)n) && same(q.h_band, band, (size_t)n / 2 + 1) &&
+        same(q.h_post, m_post, (size_t)n))
+      return THZ_OK;
+    q.valid = false;
+    q.h_pre.assign(m_pre ? m_pre : nullptr, m_pre ? m_pre + n : nullptr);
+    q.h_band.assign(band ? band : nullptr, band ? band + n / 2 + 1 : nullptr);
+    q.h_post.assign(m_post ? m_post : nullptr, m_post ? m_post + n : nullptr);
+  }
   // make sure no kernel still reads the old vectors
   THZ_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < kHostStreams; ++i) THZ_CUDA(c, cudaStreamSynchronize(c->hstream[i]));
@@ -313,6 +329,7 @@ int thz_plan_trace(thz_ctx* c, int n, const float* m_pre, const float* band, con
     if (build_hq(n, band, hq) != THZ_OK) return set_err(c, THZ_EINVAL, "unsupported n");
     if ((rc = upload_vec(c, &p.d_hq, hq.data(), n)) != THZ_OK) return rc;
     THZ_CUDA(c, cudaStreamSynchronize(c->stream));   // hq is a local
+    p.valid = true;
     return THZ_OK;
   }
   // arbitrary length: chirp-z tables
@@ -327,6 +344,7 @@ int thz_plan_trace(thz_ctx* c, int n, const float* m_pre, const float* band, con
   if ((rc = upload_vec(c, &p.d_hn, hn.data(), n)) != THZ_OK) return rc;
   THZ_CUDA(c, cudaStreamSynchronize(c->stream));
   p.blue_m = m;
+  p.valid = true;
   return THZ_OK;
 }
 

@@ -23,6 +23,9 @@
 //               128-byte-swizzled K-major layout; every K block is reused by the 8 bands
 //   warps 4..7  epilogue: tcgen05.ld of the accumulator rows (one trace per thread), sum of squares per band,
 //               subtraction from the band energies
+// The matrices are triangular, but skipping their all-zero quarter (N = 128 MMAs on 16 KB half tiles, 12 of 16
+// tiles per band and edge) measured SLOWER than the dense N = 256 form (14.1 vs 11.4 ms at config 5): twice as many
+// mbarrier round trips on the single issuing thread cost more than the 25 % of tensor work they save.
 #include "thz_internal.h"
 
 #include <cuda.h>

@@ -30,6 +30,9 @@ struct TracePlan {
   float2* d_chirp = nullptr;    // [n]
   float2* d_bhat = nullptr;     // [blue_m]
   float* d_hn = nullptr;        // [n]
+  // host copies of the planned vectors: thz_plan_trace returns at once when called again with the same plan
+  bool valid = false;
+  std::vector<float> h_pre, h_band, h_post;
   // reference pulse spectrum for the normalised forward outputs (thz_plan_reference)
   float* d_ref_amp = nullptr;   // [ref_f]
   float* d_ref_phase = nullptr; // [ref_f]
@@ -84,7 +87,7 @@ struct thz_ctx {
   struct KernelEvent { int slot; cudaEvent_t e0, e1; };
   std::vector<KernelEvent> kernel_events;        // resolved after the call's final synchronisation
   bool force_split_apply = false;                // THZ_APPLY_FORM=split: zero-padded split form for pass C (A/B checks)
-  bool edge_mma = false;                         // THZ_EDGE_MMA=on: pass-A edge energies on the tensor cores (tcgen05, TF32)
+  bool edge_mma = true;                          // pass-A edge energies on the tensor cores for n >= 2048 (tcgen05, TF32); THZ_EDGE_MMA=off: transform kernel
   uint64_t edge_mma_key = 0;                     // taps the cached Toeplitz tiles (slot WS_EDGE_MMA) were built from
   int edge_mma_bands = 0;
   bool rl_batch = true;                          // THZ_RL_BATCH=off: Richardson-Lucy band after band (A/B checks)

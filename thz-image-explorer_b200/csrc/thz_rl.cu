@@ -12,8 +12,10 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <string>
 #include <initializer_list>
 #include <type_traits>
 #include <vector>
@@ -512,14 +514,22 @@ __device__ __forceinline__ void slab_wait(const unsigned long long* flag, unsign
 // last one publish the version
 __device__ __forceinline__ void slab_signal(unsigned long long* cnt, unsigned long long target,
                                             unsigned long long* sig, unsigned long long val) {
-  __threadfence_system();
+  // the CTA barrier orders every thread's peer stores before thread 0's system-scope fence, which is cumulative:
+  // one fence per CTA instead of one per thread (256 fences behind NVLink stores cost 6 us, measured)
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     if (atomicAdd(cnt, 1ull) + 1ull == target) {
       __threadfence_system();
       st_release_sys(sig, val);
     }
   }
+}
+
+// launch slot -> segment: slot 0 = first segment (top boundary), slot 1 = last segment (bottom boundary), then the
+// interior segments in order
+__device__ __forceinline__ int slab_segment_of_slot(int slot, int nseg) {
+  return slot == 0 ? 0 : (slot == 1 ? nseg - 1 : slot - 1);
 }
 
 // what one CTA needs of the slab bookkeeping, in registers (the segment table stays where it is)
@@ -538,6 +548,9 @@ struct SlabCore {
   unsigned long long* sig_down = nullptr;
   unsigned long long sig_val = 0;
   int* err = nullptr;
+  unsigned long long* dbg = nullptr;   // THZ_SLAB_TRACE: {first start, longest halo wait, last end, last boundary end,
+                                       //  strip-0 top CTA: t0 t1 t2 t3 t4 -, strip-0 first interior CTA: t0 t1 t2 t3 t4 -} (ns)
+  int dbg_slot = -1;
 };
 
 // The strip march itself: CTA (strip bx, output rows [seg_row0, seg_row0 + rows_out)) of one filtering.
@@ -578,9 +591,20 @@ __device__ __forceinline__ void rl_stream_body(const CUtensorMap* tmap, const St
     if constexpr (SLAB) {
       // boundary segments read the neighbours' rows: wait for the version this kernel consumes (the other
       // threads block on the first chunk's mbarrier); the TMA reads below are ordered after the acquire
+      const unsigned long long tw0 = sl.dbg ? global_ns() : 0ull;
       if (sl.top && sl.wait_up) slab_wait(sl.wait_up, sl.wait_val, sl.err);
       if (sl.bottom && sl.wait_down) slab_wait(sl.wait_down, sl.wait_val, sl.err);
       asm volatile("fence.proxy.async.global;" ::: "memory");
+      if (sl.dbg) {
+        const unsigned long long tw1 = global_ns();
+        atomicMin(sl.dbg, tw0);
+        if (sl.top || sl.bottom) atomicMax(sl.dbg + 1, tw1 - tw0);
+        if (bx == 0 && (sl.dbg_slot == 0 || sl.dbg_slot == 2)) {
+          unsigned long long* f = sl.dbg + (sl.dbg_slot == 0 ? 4 : 10);
+          f[0] = tw0;
+          f[1] = tw1;
+        }
+      }
     }
     for (int j = 0; j < 2 && j < n_chunks; ++j)
       if (live(j)) {
@@ -616,18 +640,28 @@ __device__ __forceinline__ void rl_stream_body(const CUtensorMap* tmap, const St
       float acc[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+      // rows past rows_out + WU feed no output of this segment (the last chunk of a short segment is mostly such rows)
+      const bool need = j * kCR + r < rows_out + a.WU;
       if (lv) {
-        const uint32_t mb = mbar0 + 8 * buf;
-        while (!mbar_try_wait(mb, buf ? ph1 : ph0)) {
+        if (need) {
+          const uint32_t mb = mbar0 + 8 * buf;
+          while (!mbar_try_wait(mb, buf ? ph1 : ph0)) {
+          }
+          LinearLoader ld{tile0 + buf * tile_floats + r * a.bc + cg * 16};
+          run_taps(acc, ld, wys, a.KW);
         }
         if (buf) ph1 ^= 1; else ph0 ^= 1;
-        LinearLoader ld{tile0 + buf * tile_floats + r * a.bc + cg * 16};
-        run_taps(acc, ld, wys, a.KW);
+        if constexpr (SLAB) {
+          if (sl.dbg && j == 0 && tid == 0 && bx == 0 && (sl.dbg_slot == 0 || sl.dbg_slot == 2))
+            sl.dbg[(sl.dbg_slot == 0 ? 4 : 10) + 2] = global_ns();     // first tile has landed, column pass done
+        }
       }
-      int pos = (j * kCR + r) % a.Rg;
-      float* dst = ring + (cg * 16) * a.RS + pos;
+      if (need) {
+        int pos = (j * kCR + r) % a.Rg;
+        float* dst = ring + (cg * 16) * a.RS + pos;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) dst[q * a.RS] = acc[q];
+        for (int q = 0; q < 16; ++q) dst[q * a.RS] = acc[q];
+      }
     }
     __syncthreads();   // ring rows of chunk j are visible; tile[buf] is free
     if (tid == 0 && j + 2 < n_chunks && live(j + 2)) {
@@ -665,8 +699,16 @@ __device__ __forceinline__ void rl_stream_body(const CUtensorMap* tmap, const St
     }
   }
   if constexpr (SLAB) {
+    if (sl.dbg && tid == 0 && bx == 0 && (sl.dbg_slot == 0 || sl.dbg_slot == 2))
+      sl.dbg[(sl.dbg_slot == 0 ? 4 : 10) + 3] = global_ns();           // all chunks done
     if (sl.top && sl.sig_up) slab_signal(sl.cnt_up, sl.cnt_target, sl.sig_up, sl.sig_val);
     if (sl.bottom && sl.sig_down) slab_signal(sl.cnt_down, sl.cnt_target, sl.sig_down, sl.sig_val);
+    if (sl.dbg && tid == 0) {
+      const unsigned long long te = global_ns();
+      atomicMax(sl.dbg + 2, te);
+      if (sl.top || sl.bottom) atomicMax(sl.dbg + 3, te);   // last boundary CTA done (signal sent)
+      if (bx == 0 && (sl.dbg_slot == 0 || sl.dbg_slot == 2)) sl.dbg[(sl.dbg_slot == 0 ? 4 : 10) + 4] = te;
+    }
   }
 }
 
@@ -677,10 +719,11 @@ __global__ void __launch_bounds__(SW * 4, (SW == 64) ? 2 : 1) k_rl_stream(const 
   SlabCore core;
   int seg_row0, rows_out;
   if constexpr (SLAB) {
-    seg_row0 = sl.seg_start[blockIdx.y];
-    rows_out = sl.seg_start[blockIdx.y + 1] - seg_row0;
+    const int seg = slab_segment_of_slot(blockIdx.y, gridDim.y);
+    seg_row0 = sl.seg_start[seg];
+    rows_out = sl.seg_start[seg + 1] - seg_row0;
     core.row_off = sl.row_off; core.halo = sl.halo; core.own = sl.own;
-    core.top = blockIdx.y == 0; core.bottom = blockIdx.y == gridDim.y - 1;
+    core.top = seg == 0; core.bottom = seg == (int)gridDim.y - 1;
     core.up_out = sl.up_out; core.down_out = sl.down_out;
     core.wait_up = sl.wait_up; core.wait_down = sl.wait_down; core.wait_val = sl.wait_val;
     core.cnt_up = sl.cnt_up; core.cnt_down = sl.cnt_down; core.cnt_target = sl.cnt_target;
@@ -709,18 +752,28 @@ struct BandLaunch {
   // slab form
   int row_off, halo, own;
   int seg_start[kMaxSlabSegs + 1];
+  int nseg_lone;                       // segmentation of the launches in which this band iterates alone
+  int seg_start_lone[kMaxSlabSegs + 1];
   float *up_u, *down_u, *up_r, *down_r;
   const unsigned long long *wait_u_up, *wait_u_down, *wait_r_up, *wait_r_down;
   unsigned long long *cnt_u_up, *cnt_u_down, *cnt_r_up, *cnt_r_down;
   unsigned long long *sig_u_up, *sig_u_down, *sig_r_up, *sig_r_down;
   unsigned long long u_base, r_base, cnt_u_base, cnt_r_base;   // values at the start of the run
   int* err;
+  unsigned long long* dbg;            // THZ_SLAB_TRACE: [2 * n_iter][4] time stamps of this band's launches, or null
 };
 
+// grid = (strips, bands, segment slots): CTAs are dispatched x first, then y, then z, so that the boundary segments
+// (slots 0 and 1) of EVERY band start before any interior segment: their rows reach the neighbours while the
+// interior is still being filtered, and the neighbours' next launch finds its halos in place
 template <int MODE, bool SLAB>
-__global__ void __launch_bounds__(256, 2) k_rl_multi(const BandLaunch* __restrict__ bl, int it) {
-  const BandLaunch& B = bl[blockIdx.z];
-  if (it >= B.n_iter || (int)blockIdx.x >= B.strips || (int)blockIdx.y >= B.nseg) return;
+__global__ void __launch_bounds__(256, 2) k_rl_multi(const BandLaunch* __restrict__ bl, int it, int lone) {
+  // one GPU: band-major (blockIdx.z = band), so that the CTAs in flight share one band's images in L2
+  const BandLaunch& B = bl[SLAB ? blockIdx.y : blockIdx.z];
+  const int slot = SLAB ? blockIdx.z : blockIdx.y;
+  const bool alt = SLAB && lone != 0;
+  const int nseg = alt ? B.nseg_lone : B.nseg;
+  if (it >= B.n_iter || (int)blockIdx.x >= B.strips || slot >= nseg) return;
   StreamArgs a = B.sa;
   const float* tp = B.taps[MODE == 1 ? 0 : 1];
   a.wx = tp;
@@ -730,10 +783,12 @@ __global__ void __launch_bounds__(256, 2) k_rl_multi(const BandLaunch* __restric
   SlabCore core;
   int seg_row0, rows_out;
   if constexpr (SLAB) {
-    seg_row0 = B.seg_start[blockIdx.y];
-    rows_out = B.seg_start[blockIdx.y + 1] - seg_row0;
+    const int seg = slab_segment_of_slot(slot, nseg);
+    const int* tab = alt ? B.seg_start_lone : B.seg_start;
+    seg_row0 = tab[seg];
+    rows_out = tab[seg + 1] - seg_row0;
     core.row_off = B.row_off; core.halo = B.halo; core.own = B.own;
-    core.top = blockIdx.y == 0; core.bottom = (int)blockIdx.y == B.nseg - 1;
+    core.top = seg == 0; core.bottom = seg == nseg - 1;
     const unsigned long long i = (unsigned long long)it;
     if constexpr (MODE == 1) {        // consumes u version u_base + it, publishes r version r_base + it
       core.up_out = B.up_r; core.down_out = B.down_r;
@@ -749,8 +804,10 @@ __global__ void __launch_bounds__(256, 2) k_rl_multi(const BandLaunch* __restric
       core.sig_up = B.sig_u_up; core.sig_down = B.sig_u_down; core.sig_val = B.u_base + i + 1ull;
     }
     core.err = B.err;
+    core.dbg = B.dbg ? B.dbg + (size_t)(2 * it + (MODE == 1 ? 0 : 1)) * 16 : nullptr;
+    core.dbg_slot = slot;
   } else {
-    seg_row0 = blockIdx.y * B.uniform_seg_rows;
+    seg_row0 = slot * B.uniform_seg_rows;
     rows_out = min(B.uniform_seg_rows, a.Hp - seg_row0);
   }
   if (rows_out <= 0) return;
@@ -1167,12 +1224,12 @@ int richardson_lucy(thz_ctx* c, cudaStream_t s, const float* d_image, int rows, 
 // one filtering of every band that still iterates (k_rl_multi); `active` = bands with n_iter > it
 template <int MODE, bool SLAB>
 static int launch_multi(thz_ctx* c, cudaStream_t s, const BandLaunch* d_bl, int active, int grid_x, int grid_y,
-                        size_t smem, int it) {
+                        size_t smem, int it, int lone = 0) {
   auto kernel = k_rl_multi<MODE, SLAB>;
   cudaError_t e = ensure_dynamic_smem(c, (const void*)kernel, smem);
   if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(k_rl_multi)");
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid_x, grid_y, active);
+  cfg.gridDim = SLAB ? dim3(grid_x, active, grid_y) : dim3(grid_x, grid_y, active);
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
@@ -1181,7 +1238,7 @@ static int launch_multi(thz_ctx* c, cudaStream_t s, const BandLaunch* d_bl, int 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kernel, d_bl, it);
+  e = cudaLaunchKernelEx(&cfg, kernel, d_bl, it, lone);
   c->launches++;
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(c, e, "k_rl_multi launch");
@@ -1326,7 +1383,9 @@ struct SlabBand {
   ConvPlan cp;
   CUtensorMap map_u, map_r;
   int nseg = 0, strips = 0;
-  int seg_start[kMaxSlabSegs + 1] = {};
+  int seg_start[kMaxSlabSegs + 1] = {};      // few long segments: launches that several bands share
+  int nseg_lone = 0;
+  int seg_start_lone[kMaxSlabSegs + 1] = {}; // many short segments: launches in which this band iterates alone
   unsigned long long u_next = 1, r_next = 1;   // next version numbers of this rank's u / r boundary rows
   unsigned long long cnt_u = 0, cnt_r = 0;     // cumulative boundary-CTA counts (both directions advance alike)
 };
@@ -1348,6 +1407,11 @@ struct thz_slab {
   std::vector<unsigned char> key;   // geometry + PSF bytes of the current plan
   cudaStream_t stream = nullptr;    // stream the run is launched on (the context's by default)
   void* d_launch = nullptr;         // BandLaunch table of the batched kernels
+  bool trace = false;               // THZ_SLAB_TRACE=<file prefix>: per-launch time stamps of the first band
+  std::string trace_path;
+  void* d_trace = nullptr;
+  size_t d_trace_bytes = 0;
+  int trace_launches = 0;
 };
 
 namespace thz {
@@ -1409,24 +1473,41 @@ static int slab_band_finish_plan(thz_slab* sl, const thz_band_plan& pb, SlabBand
   b.strips = (int)b.cp.sgrid.x;
   const int h = std::max(b.halo, 1);
   const int interior = b.own - 2 * h;
-  const int slots = c->sm_count * (b.cp.sw == 64 ? 2 : 1);
-  int target = std::min(std::max(slots / std::max(b.strips, 1), 3), kMaxSlabSegs);
-  int ni = std::max(1, target - 2);
-  int per = (interior + ni - 1) / ni;
-  int chunks = (per + sa.WU + kCR - 1) / kCR;
-  int seg_rows = std::max(1, chunks * kCR - sa.WU);
-  ni = (interior + seg_rows - 1) / seg_rows;
-  if (ni + 2 > kMaxSlabSegs) {
-    ni = kMaxSlabSegs - 2;
-    seg_rows = (interior + ni - 1) / ni;
-    ni = (interior + seg_rows - 1) / seg_rows;
+  const int per_sm = (b.cp.sw == 64 ? 2 : 1);
+  // Interior segments.  Every segment re-filters WU warm-up rows and works in 64-row chunks, so few long segments
+  // waste least; but a launch lasts as long as its busiest SM, and a CTA that has an SM to itself runs at less
+  // than half the rate of two that interleave (measured, profiles/r02_slab_trace_*.txt: 7.3 us per chunk alone,
+  // 3.25 us per chunk and CTA when two share an SM).  Hence two tables:
+  //   shared: strips x (ni + 2) <= SMs -- in launches that several bands share, the bands fill each other's SMs
+  //   lone  : the ni that minimises  m x chunks x cost(m)  for one band on the whole GPU (m = CTAs per SM)
+  auto chunks_of = [&](int rows) { return (rows + sa.WU + kCR - 1) / kCR; };
+  auto build = [&](int ni, int* seg, int& nseg) {
+    ni = std::max(1, std::min(ni, std::min(kMaxSlabSegs - 2, std::max(interior, 1))));
+    int seg_rows = std::max(1, (interior + ni - 1) / ni);
+    const int full = chunks_of(seg_rows) * kCR - sa.WU;     // whole chunks where that does not add a segment
+    if (full >= seg_rows && (interior + full - 1) / full == ni) seg_rows = full;
+    ni = std::max(1, (interior + seg_rows - 1) / seg_rows);
+    nseg = 0;
+    seg[nseg++] = 0;
+    seg[nseg++] = h;
+    for (int i = 1; i < ni; ++i) seg[nseg++] = h + i * seg_rows;
+    seg[nseg++] = b.own - h;
+    seg[nseg] = b.own;
+  };
+  build(c->sm_count / std::max(b.strips, 1) - 2, b.seg_start, b.nseg);
+  int ni_lone = 1;
+  double best = 1e30;
+  for (int cand = 1; cand <= kMaxSlabSegs - 2 && cand <= std::max(interior, 1); ++cand) {
+    const int ctas = b.strips * (cand + 2);
+    if (ctas > c->sm_count * per_sm && cand > 1) break;
+    const int m = (ctas + c->sm_count - 1) / c->sm_count;
+    const double t = (double)m * chunks_of((interior + cand - 1) / cand) * (m == 1 ? 7.3 : 3.25);
+    if (t < best - 1e-9) {
+      best = t;
+      ni_lone = cand;
+    }
   }
-  b.nseg = 0;
-  b.seg_start[b.nseg++] = 0;
-  b.seg_start[b.nseg++] = h;
-  for (int i = 1; i < ni; ++i) b.seg_start[b.nseg++] = h + i * seg_rows;
-  b.seg_start[b.nseg++] = b.own - h;
-  b.seg_start[b.nseg] = b.own;
+  build(ni_lone, b.seg_start_lone, b.nseg_lone);
   return THZ_OK;
 }
 
@@ -1435,7 +1516,7 @@ static void slab_fill_args(const thz_slab* sl, const SlabBand& b, SlabArgs& a) {
   a.row_off = b.halo;
   a.halo = b.halo;
   a.own = b.own;
-  for (int i = 0; i <= b.nseg; ++i) a.seg_start[i] = b.seg_start[i];
+  for (int i = 0; i <= b.nseg_lone; ++i) a.seg_start[i] = b.seg_start_lone[i];
   a.err = reinterpret_cast<int*>(sl->arena);
 }
 
@@ -1486,7 +1567,7 @@ static int slab_launch_conv(thz_slab* sl, SlabBand& b, cudaStream_t s, unsigned 
     cudaError_t e2 = ensure_dynamic_smem(c, (const void*)kernel, b.cp.ssmem);
     if (e2 != cudaSuccess) return e2;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(b.strips, b.nseg);
+    cfg.gridDim = dim3(b.strips, b.nseg_lone);
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = b.cp.ssmem;
     cfg.stream = s;
@@ -1575,6 +1656,8 @@ static void slab_fill_launch(thz_slab* sl, std::vector<BandLaunch>& h, std::vect
     L.nseg = b.nseg;
     L.row_off = b.halo; L.halo = b.halo; L.own = b.own;
     for (int i = 0; i <= b.nseg; ++i) L.seg_start[i] = b.seg_start[i];
+    L.nseg_lone = b.nseg_lone;
+    for (int i = 0; i <= b.nseg_lone; ++i) L.seg_start_lone[i] = b.seg_start_lone[i];
     const bool has_up = sl->up && b.halo > 0, has_down = sl->down && b.halo > 0;
     L.up_u = slab_up_dst(sl, b, b.off_u); L.down_u = slab_down_dst(sl, b, b.off_u);
     L.up_r = slab_up_dst(sl, b, b.off_r); L.down_r = slab_down_dst(sl, b, b.off_r);
@@ -1591,6 +1674,22 @@ static void slab_fill_launch(thz_slab* sl, std::vector<BandLaunch>& h, std::vect
     L.u_base = b.u_next; L.r_base = b.r_next;
     L.cnt_u_base = b.cnt_u; L.cnt_r_base = b.cnt_r;
     L.err = reinterpret_cast<int*>(sl->arena);
+    L.dbg = nullptr;
+    if (z == 0 && sl->trace) {      // time stamps of the longest-running band's launches
+      const size_t bytes = (size_t)2 * b.n_iter * 16 * sizeof(unsigned long long);
+      if (sl->d_trace_bytes < bytes) {
+        if (sl->d_trace) cudaFree(sl->d_trace);
+        sl->d_trace = nullptr;
+        if (cudaMalloc(&sl->d_trace, bytes) == cudaSuccess) sl->d_trace_bytes = bytes;
+      }
+      if (sl->d_trace) {
+        std::vector<unsigned long long> init((size_t)2 * b.n_iter * 16, 0ull);
+        for (size_t i = 0; i < init.size(); i += 16) init[i] = ~0ull;
+        cudaMemcpyAsync(sl->d_trace, init.data(), bytes, cudaMemcpyHostToDevice, sl->stream);
+        L.dbg = (unsigned long long*)sl->d_trace;
+        sl->trace_launches = 2 * b.n_iter;
+      }
+    }
   }
 }
 
@@ -1621,7 +1720,7 @@ int slab_run(thz_slab* const* ranks, int nranks, const float* const* d_energy, c
     int max_iter = 0;
     std::vector<std::vector<BandLaunch>> h((size_t)nranks);
     std::vector<int> order;
-    struct G { int gx = 1, gy = 1; size_t smem = 0; };
+    struct G { int gx = 1, gy = 1, gy_lone = 1; size_t smem = 0; };
     std::vector<G> g((size_t)nranks);
     for (int r = 0; rc == THZ_OK && r < nranks; ++r) {
       thz_slab* sl = ranks[r];
@@ -1632,6 +1731,7 @@ int slab_run(thz_slab* const* ranks, int nranks, const float* const* d_energy, c
         g[r].gy = std::max(g[r].gy, L.nseg);
         max_iter = std::max(max_iter, L.n_iter);
       }
+      g[r].gy_lone = h[r][0].nseg_lone;      // the band with the most iterations is the one that ends up alone
       for (const SlabBand& b : sl->bands) g[r].smem = std::max(g[r].smem, b.cp.ssmem);
       if (!sl->d_launch) {
         void* p = nullptr;
@@ -1644,12 +1744,13 @@ int slab_run(thz_slab* const* ranks, int nranks, const float* const* d_energy, c
     for (int it = 0; rc == THZ_OK && it < max_iter; ++it) {
       int active = 0;
       while (active < (int)B && h[0][active].n_iter > it) ++active;
+      const int lone = active == 1 ? 1 : 0;
       for (int r = 0; rc == THZ_OK && r < nranks; ++r)
         rc = launch_multi<1, true>(ranks[r]->ctx, ranks[r]->stream, (const BandLaunch*)ranks[r]->d_launch, active, g[r].gx,
-                                   g[r].gy, g[r].smem, it);
+                                   lone ? g[r].gy_lone : g[r].gy, g[r].smem, it, lone);
       for (int r = 0; rc == THZ_OK && r < nranks; ++r)
         rc = launch_multi<2, true>(ranks[r]->ctx, ranks[r]->stream, (const BandLaunch*)ranks[r]->d_launch, active, g[r].gx,
-                                   g[r].gy, g[r].smem, it);
+                                   lone ? g[r].gy_lone : g[r].gy, g[r].smem, it, lone);
     }
     // the counters the kernels advanced
     for (int r = 0; r < nranks; ++r)
@@ -1741,6 +1842,10 @@ int thz_slab_create(thz_ctx* c, int rank, int world, thz_slab** out) {
   sl->rank = rank;
   sl->world = world;
   sl->stream = c->stream;
+  if (const char* t = getenv("THZ_SLAB_TRACE")) {
+    sl->trace = true;
+    sl->trace_path = std::string(t) + ".rank" + std::to_string(rank) + ".csv";
+  }
   *out = sl;
   return THZ_OK;
 }
@@ -1760,6 +1865,7 @@ void thz_slab_destroy(thz_slab* sl) {
   slab_disconnect(sl);
   if (sl->arena) cudaFree(sl->arena);
   if (sl->d_launch) cudaFree(sl->d_launch);
+  if (sl->d_trace) cudaFree(sl->d_trace);
   delete sl;
 }
 
@@ -1919,6 +2025,21 @@ int thz_slab_status(thz_slab* sl) {
   int err = 0;
   THZ_CUDA(c, cudaMemcpy(&err, sl->arena, sizeof err, cudaMemcpyDeviceToHost));
   if (err) return set_err(c, THZ_ECUDA, "a halo wait timed out: a neighbouring rank did not deliver its boundary rows");
+  if (sl->trace && sl->d_trace && sl->trace_launches > 0) {
+    std::vector<unsigned long long> h((size_t)sl->trace_launches * 16);
+    THZ_CUDA(c, cudaMemcpy(h.data(), sl->d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(sl->trace_path.c_str(), "w")) {
+      fprintf(f, "launch,start_ns,halo_wait_ns,end_ns,boundary_end_ns,top_t0,top_t1,top_t2,top_t3,top_t4,int_t0,int_t1,int_t2,int_t3,int_t4\n");
+      for (int i = 0; i < sl->trace_launches; ++i) {
+        const unsigned long long* r = h.data() + 16 * (size_t)i;
+        fprintf(f, "%d,%llu,%llu,%llu,%llu", i, r[0] - h[0], r[1], r[2] - h[0], r[3] - h[0]);
+        for (int k = 4; k < 9; ++k) fprintf(f, ",%lld", (long long)(r[k] - r[0]));
+        for (int k = 10; k < 15; ++k) fprintf(f, ",%lld", (long long)(r[k] - r[0]));
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   return THZ_OK;
 }
 
