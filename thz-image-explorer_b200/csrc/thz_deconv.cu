@@ -828,10 +828,27 @@ __global__ void __launch_bounds__(256, 2) k_fir_edges(const FirArgs a) {
 // Z[N-k] in shared memory, which only this thread reads).  After a barrier every thread fetches its
 // upper-half registers.  Halves the table loads and the S / D arithmetic.  `sm` holds the spectrum in
 // natural order on entry; thread 0 also owns the self-mirrored Nyquist bin (register kE/2).
+// lane-distributed gains of a pair: lane b (b < 16) holds gain[b][p0], lane 16 + b holds gain[b][p0 + 1]; one
+// load per lane, issued before the forward transform so that its L2 latency is hidden, one live register.
+// Non-finite gains (dead pixel: sqrt(u / 0), quirk 10) are reported through bad0 / bad1 and replaced by 0.
+constexpr int kGainLanes = 16;
+__device__ __forceinline__ float prefetch_pair_gains(const FirArgs& a, int64_t p0, bool act0, bool act1, bool& bad0,
+                                                     bool& bad1) {
+  const int lane = threadIdx.x & 31, b = lane & (kGainLanes - 1);
+  const bool second = lane >= kGainLanes;
+  float gv = 0.f;
+  if (b < a.B && (second ? act1 : act0)) gv = __ldg(a.gain + (size_t)b * a.bstride + p0 + (second ? 1 : 0));
+  const bool nonfinite = !(fabsf(gv) <= 3.0e38f);
+  const unsigned m = __ballot_sync(0xffffffffu, nonfinite);
+  bad0 = (m & 0xFFFFu) != 0u;
+  bad1 = (m >> kGainLanes) != 0u;
+  return nonfinite ? 0.f : gv;
+}
+
 template <int N>
 __device__ __forceinline__ void mix_paired(float2 (&z)[kE], float2* sm, int t, const FirArgs& a,
                                            const float* __restrict__ htab, int64_t p0, bool act0, bool act1,
-                                           bool& bad0, bool& bad1, float gmul) {
+                                           bool& bad0, bool& bad1, float gmul, float gv) {
   constexpr int T = SGeo<N>::T;
   constexpr int LAST = Plan<N>::ns - 1;
   constexpr int RL = Plan<N>::r[LAST];
@@ -847,10 +864,16 @@ __device__ __forceinline__ void mix_paired(float2 (&z)[kE], float2* sm, int t, c
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) {
       const int b = b0 + bb;
-      float g0 = (act0 && b < a.B) ? __ldg(a.gain + (size_t)b * a.bstride + p0) : 0.f;
-      float g1 = (act1 && b < a.B) ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
-      if (!(fabsf(g0) <= 3.0e38f)) { bad0 = true; g0 = 0.f; }
-      if (!(fabsf(g1) <= 3.0e38f)) { bad1 = true; g1 = 0.f; }
+      float g0, g1;
+      if (b0 + 3 < kGainLanes) {   // uniform: this group of four comes from the prefetched lanes
+        g0 = __shfl_sync(0xffffffffu, gv, b);
+        g1 = __shfl_sync(0xffffffffu, gv, kGainLanes + b);
+      } else {
+        g0 = (act0 && b < a.B) ? __ldg(a.gain + (size_t)b * a.bstride + p0) : 0.f;
+        g1 = (act1 && b < a.B) ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
+        if (!(fabsf(g0) <= 3.0e38f)) { bad0 = true; g0 = 0.f; }
+        if (!(fabsf(g1) <= 3.0e38f)) { bad1 = true; g1 = 0.f; }
+      }
       gs[bb] = gmul * (g0 + g1);
       gd[bb] = gmul * (g0 - g1);
     }
@@ -937,6 +960,30 @@ __global__ void __launch_bounds__(256, 2) k_fir_edge_corr(const FirArgs a) {
     if (pair >= npairs) continue;                 // warps are independent (warp-scope barriers only)
     const int64_t p0 = pair * 2;
     const bool act1 = p0 + 1 < a.P;
+    // pull the NEXT pair's edge samples into L2 (2 traces x 2 edges x 8 lines of 128 bytes = one line per lane): the
+    // 16 warps of an SM cannot hide the DRAM latency of their own first loads
+    {
+      const int64_t npair = pair + (int64_t)gridDim.x * G;
+      if (npair < npairs) {
+        const int tr = t >> 4, ed = (t >> 3) & 1, ln = t & 7;
+        const int64_t np = npair * 2 + tr;
+        if (np < a.P) {
+          const float* q = a.x + np * a.n + (ed ? a.n - 256 : 0) + ln * 32;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
+      }
+    }
+    // the pair's gains of the first sixteen bands, one per lane (lane b: trace 0, lane 16 + b: trace 1), fetched
+    // before the transforms and broadcast by shuffles where the mix needs them: their L2 latency was the kernel's
+    // largest stall (long scoreboard 3.5 per issue slot in the round-2 ncu capture); one live register
+    constexpr int kPre = 16;
+    float gv = 0.f;
+    {
+      const int b = t & (kPre - 1);
+      const bool second = t >= kPre;
+      if (b < a.B && (!second || act1)) gv = __ldg(a.gain + (size_t)b * a.bstride + p0 + (second ? 1 : 0));
+      if (!(fabsf(gv) <= 3.0e38f)) gv = 0.f;   // the main kernel marks such traces NaN
+    }
     for (int edge = 0; edge < 2; ++edge) {
       const int off = edge ? a.n - kSeg : 0;
       const float* r0 = a.x + p0 * a.n + off;
@@ -963,12 +1010,7 @@ __global__ void __launch_bounds__(256, 2) k_fir_edge_corr(const FirArgs a) {
 #pragma unroll
         for (int j = 0; j < NLOW; ++j) sacc[j] = dacc[j] = make_float2(0.f, 0.f);
         float2 sny = make_float2(0.f, 0.f), dny = make_float2(0.f, 0.f);
-        for (int b = 0; b < a.B; ++b) {
-          float g0 = __ldg(a.gain + (size_t)b * a.bstride + p0);
-          float g1 = act1 ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
-          if (!(fabsf(g0) <= 3.0e38f)) g0 = 0.f;   // the main kernel marks such traces NaN
-          if (!(fabsf(g1) <= 3.0e38f)) g1 = 0.f;
-          const float gs = 0.5f * (g0 + g1), gd = 0.5f * (g0 - g1);
+        auto add_band = [&](int b, float gs, float gd) {
           const float2* hq = a.edge + ((size_t)edge * a.B + b) * M;
 #pragma unroll
           for (int j = 0; j < NLOW; ++j) {
@@ -986,6 +1028,17 @@ __global__ void __launch_bounds__(256, 2) k_fir_edge_corr(const FirArgs a) {
             dny.x = fmaf(gd, h.x, dny.x);
             dny.y = fmaf(gd, h.y, dny.y);
           }
+        };
+        for (int b = 0; b < kPre && b < a.B; ++b) {
+          const float g0 = __shfl_sync(0xffffffffu, gv, b), g1 = __shfl_sync(0xffffffffu, gv, kPre + b);
+          add_band(b, 0.5f * (g0 + g1), 0.5f * (g0 - g1));
+        }
+        for (int b = kPre; b < a.B; ++b) {
+          float g0 = __ldg(a.gain + (size_t)b * a.bstride + p0);
+          float g1 = act1 ? __ldg(a.gain + (size_t)b * a.bstride + p0 + 1) : 0.f;
+          if (!(fabsf(g0) <= 3.0e38f)) g0 = 0.f;
+          if (!(fabsf(g1) <= 3.0e38f)) g1 = 0.f;
+          add_band(b, 0.5f * (g0 + g1), 0.5f * (g0 - g1));
         }
         // S a + D conj(b)
         auto mixc = [](float2 S, float2 D, float2 za, float2 zb) {
@@ -1061,13 +1114,14 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_
       }
       load_pair_direct<N>(z, a.x, p0, t, act0, act1, nz0, nz1);
     }
+    const float gv = prefetch_pair_gains(a, p0, act0, act1, bad0, bad1);
     fft_forward<N>(z, t, sm, a.tw);
     __syncthreads();
 #pragma unroll
     for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];   // mirrors of lower-half bins are upper-half registers
     __syncthreads();
     // he holds H / (2N): the N-point inverse needs H / N
-    mix_paired<N>(z, sm, t, a, a.he, p0, act0, act1, bad0, bad1, 1.0f);
+    mix_paired<N>(z, sm, t, a, a.he, p0, act0, act1, bad0, bad1, 1.0f, gv);
     // wrap-around corrections of this thread's outputs, in flight across the inverse transform
     const float2* cp = a.corr + (size_t)pair * 2 * kCorrStride;
     float2 cr[kE];

@@ -20,7 +20,9 @@ with open(out, "w") as f:
     for r in rows[2:]:
         f.write(f"## {r[ki]}\n")
         for h, u, v in zip(hdr, units, r):
-            if h in keys or (h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")):
+            tensor = h.endswith("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed") or \
+                h == "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"
+            if h in keys or tensor or (h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")):
                 try:
                     if h.startswith("smsp__average_warps") and float(v.replace(",", "")) < 0.02:
                         continue
