@@ -247,8 +247,9 @@ def test_gain_application_matches_oracle(ctx, psfs, n, w, h):
 
 
 def test_gain_application_forms_agree(psfs, monkeypatch):
-    """The circular form of pass C (default), the zero-padded split form (THZ_APPLY_FORM=split) and the
-    bulk-copy-staged variants (THZ_FIR_STAGING=on) are three routes to the same linear convolution."""
+    """The circular form of pass C (default), the zero-padded split form (THZ_APPLY_FORM=split), the
+    bulk-copy-staged variants (THZ_FIR_STAGING=on) and the transform form of the pass-A edges (THZ_EDGE_MMA=off)
+    are routes to the same result."""
     psf, _ = psfs
     w, h, n = 6, 5, 2048
     cube = synthetic_cube(w, h, n, seed=77, noise=0.05)
@@ -259,8 +260,8 @@ def test_gain_application_forms_agree(psfs, monkeypatch):
     P = w * h
     gains = (0.25 + 2.0 * rng.random((len(bands), P))).astype(F32)
     outs, energies = [], []
-    for env in ({}, {"THZ_APPLY_FORM": "split"}, {"THZ_FIR_STAGING": "on"}):
-        for k in ("THZ_APPLY_FORM", "THZ_FIR_STAGING"):
+    for env in ({}, {"THZ_APPLY_FORM": "split"}, {"THZ_FIR_STAGING": "on"}, {"THZ_EDGE_MMA": "off"}):
+        for k in ("THZ_APPLY_FORM", "THZ_FIR_STAGING", "THZ_EDGE_MMA"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
