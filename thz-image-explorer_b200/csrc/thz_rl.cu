@@ -1472,42 +1472,63 @@ static int slab_band_finish_plan(thz_slab* sl, const thz_band_plan& pb, SlabBand
   const StreamArgs& sa = b.cp.sa;
   b.strips = (int)b.cp.sgrid.x;
   const int h = std::max(b.halo, 1);
-  const int interior = b.own - 2 * h;
   const int per_sm = (b.cp.sw == 64 ? 2 : 1);
-  // Interior segments.  Every segment re-filters WU warm-up rows and works in 64-row chunks, so few long segments
-  // waste least; but a launch lasts as long as its busiest SM, and a CTA that has an SM to itself runs at less
-  // than half the rate of two that interleave (measured, profiles/r02_slab_trace_*.txt: 7.3 us per chunk alone,
-  // 3.25 us per chunk and CTA when two share an SM).  Hence two tables:
-  //   shared: strips x (ni + 2) <= SMs -- in launches that several bands share, the bands fill each other's SMs
-  //   lone  : the ni that minimises  m x chunks x cost(m)  for one band on the whole GPU (m = CTAs per SM)
+  // Segments.  A CTA works in 64-row chunks and re-filters WU warm-up rows, so a segment of 64 c - WU rows uses its
+  // c chunks fully.  The boundary segments must hold the halo rows (they read the neighbours' rows and produce the
+  // rows the neighbours need) but may be longer: a 23-row boundary costs two chunks either way, an 80-row one does
+  // 57 interior rows in the same time.  Plans: every segment c chunks long, the boundaries included; c is chosen
+  // per table from measured costs (profiles/r02_slab_trace_*.txt: ~6 us per chunk when a CTA has its SM to itself,
+  // 3.25 us per chunk and CTA when two interleave; a launch lasts as long as its busiest SM):
+  //   lone  : min over c of  m x c x cost(m),  m = CTAs per SM -- launches in which this band iterates alone
+  //   shared: CTAs <= SMs with the fewest chunk units -- launches several bands share fill each other's SMs
   auto chunks_of = [&](int rows) { return (rows + sa.WU + kCR - 1) / kCR; };
-  auto build = [&](int ni, int* seg, int& nseg) {
-    ni = std::max(1, std::min(ni, std::min(kMaxSlabSegs - 2, std::max(interior, 1))));
-    int seg_rows = std::max(1, (interior + ni - 1) / ni);
-    const int full = chunks_of(seg_rows) * kCR - sa.WU;     // whole chunks where that does not add a segment
-    if (full >= seg_rows && (interior + full - 1) / full == ni) seg_rows = full;
-    ni = std::max(1, (interior + seg_rows - 1) / seg_rows);
+  struct Cand { int b_rows, seg_rows, ni, ctas, c; double t; };
+  const int sms = c->sm_count;
+  auto make = [&](int nch) -> Cand {
+    const int c = nch;
+    Cand k{};
+    k.c = c;
+    k.b_rows = c * kCR - sa.WU;
+    if (k.b_rows < h || 2 * k.b_rows > b.own) {   // too short for the halo / too long for the slab: tight boundaries
+      k.b_rows = h;
+      k.c = std::max(c, chunks_of(h));
+    }
+    const int interior = b.own - 2 * k.b_rows;
+    k.seg_rows = std::max(1, c * kCR - sa.WU);
+    k.ni = interior > 0 ? (interior + k.seg_rows - 1) / k.seg_rows : 0;
+    if (k.ni > 0) k.seg_rows = (interior + k.ni - 1) / k.ni;   // equal parts
+    k.ctas = b.strips * (k.ni + 2);
+    const int m = (k.ctas + sms - 1) / sms;
+    k.t = (double)m * k.c * (m == 1 ? 6.0 : 3.25);
+    return k;
+  };
+  Cand lone{}, shared{};
+  lone.t = 1e30;
+  double shared_units = 1e30;
+  bool have_shared = false;
+  for (int cc = 1; cc <= 40; ++cc) {
+    const Cand k = make(cc);
+    if (k.ni + 2 > kMaxSlabSegs) continue;
+    if (k.ctas <= sms * per_sm && k.t < lone.t - 1e-9) lone = k;
+    if (k.ctas <= sms && (double)k.ctas * k.c < shared_units - 1e-9) {
+      shared_units = (double)k.ctas * k.c;
+      shared = k;
+      have_shared = true;
+    }
+    if (2 * (cc * kCR - sa.WU) > b.own && cc > chunks_of(h)) break;
+  }
+  if (lone.t >= 1e30) lone = make(std::max(1, chunks_of(b.own / 2)));   // cannot happen for sane sizes
+  if (!have_shared) shared = lone;
+  auto build = [&](const Cand& k, int* seg, int& nseg) {
     nseg = 0;
     seg[nseg++] = 0;
-    seg[nseg++] = h;
-    for (int i = 1; i < ni; ++i) seg[nseg++] = h + i * seg_rows;
-    seg[nseg++] = b.own - h;
+    seg[nseg++] = k.b_rows;
+    for (int i = 1; i < k.ni; ++i) seg[nseg++] = k.b_rows + i * k.seg_rows;
+    if (k.ni > 0) seg[nseg++] = b.own - k.b_rows;
     seg[nseg] = b.own;
   };
-  build(c->sm_count / std::max(b.strips, 1) - 2, b.seg_start, b.nseg);
-  int ni_lone = 1;
-  double best = 1e30;
-  for (int cand = 1; cand <= kMaxSlabSegs - 2 && cand <= std::max(interior, 1); ++cand) {
-    const int ctas = b.strips * (cand + 2);
-    if (ctas > c->sm_count * per_sm && cand > 1) break;
-    const int m = (ctas + c->sm_count - 1) / c->sm_count;
-    const double t = (double)m * chunks_of((interior + cand - 1) / cand) * (m == 1 ? 7.3 : 3.25);
-    if (t < best - 1e-9) {
-      best = t;
-      ni_lone = cand;
-    }
-  }
-  build(ni_lone, b.seg_start_lone, b.nseg_lone);
+  build(shared, b.seg_start, b.nseg);
+  build(lone, b.seg_start_lone, b.nseg_lone);
   return THZ_OK;
 }
 
