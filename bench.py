@@ -418,19 +418,20 @@ def run_ours(a):
                                   spec["phase"].data_ptr(), P)
             mark("trace_forward_spectra")
             return
-        ctx.trace_fused_dev(d_in.ptr, d_out.ptr, img_t.data_ptr(), P)
-        mark("trace_fused")
+        if bands is None or ops is not None:
+            ctx.trace_fused_dev(d_in.ptr, d_out.ptr, img_t.data_ptr(), P)
+            mark("trace_fused")
         if bands is not None:
             if world == 1:
-                ctx._check(m.lib.thz_deconvolution_dev(ctx.handle, d_out.ptr, rows, H, N, bands, B, d_out.ptr,
-                                                       img_t.data_ptr(), None, None, None))
-                mark("deconvolution")
+                # trace pass fused with the band energies -> Richardson-Lucy -> gain application (thz_chain_dev)
+                ctx.chain_dev(d_in.ptr, rows, H, N, bands, d_out.ptr, img_t.data_ptr())
+                mark("chain_and_deconvolution")
             elif slab is not None:
-                ctx.deconv_energies_dev(d_out.ptr, P, N, bands, e_t.data_ptr())
-                mark("band_energies")
+                ctx.chain_begin_dev(d_in.ptr, d_out.ptr, img_t.data_ptr(), P, N, bands, e_t.data_ptr())
+                mark("trace_and_band_energies")
                 slab.rl(e_t.data_ptr(), P, g_t.data_ptr())
                 mark("richardson_lucy_slab")
-                ctx.deconv_apply_dev(d_out.ptr, g_t.data_ptr(), P, N, bands, d_out.ptr, img_t.data_ptr())
+                ctx.chain_end_dev(d_out.ptr, g_t.data_ptr(), P, N, bands, d_out.ptr, img_t.data_ptr())
                 mark("gain_application")
             else:
                 m.sharding.sharded_deconvolution(ops, d_out.ptr, W, H, B, dist, world, rank, timings=phase_s,
@@ -477,7 +478,9 @@ def run_ours(a):
     # ---- per-kernel breakdown of one extra step (event pairs inside the library), this rank ----
     peak, peak_src = measured_peaks()
     stages = {}
-    if spec is None:
+    fused_chain = (bands is not None and ops is None and N >= 512 and (N & (N - 1)) == 0
+                   and os.environ.get("THZ_CHAIN_FUSE", "on") != "off")
+    if spec is None and not fused_chain:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3
         e0.record(stream)
@@ -487,16 +490,16 @@ def run_ours(a):
         ctx.sync()
         stages["trace_fused"] = {"ms": e0.elapsed_time(e1) / reps, "kernel": f"k_trace_fused<{N}>",
                                  "algorithmic_bytes": (8 * N + 4) * P}
-    else:
+    elif spec is not None:
         stages["trace_forward_spectra"] = {"ms": phases_ms["trace_forward_spectra"], "kernel": f"k_trace_forward<{N}>",
                                            "algorithmic_bytes": (8 * N + 16 * F) * P}
     rl_ms = None
     if bands is not None:
         if world == 1:
             st = ctx.deconv_stage_ms()
-            km = ctx.deconv_kernel_ms()
+            km = ctx.chain_kernel_ms()
             rl_ms = st["rl_ms"]
-            stages["stage_totals_ms"] = {"energies": st["energies_ms"], "richardson_lucy": st["rl_ms"],
+            stages["stage_totals_ms"] = {"trace_pass_and_band_energies": st["energies_ms"], "richardson_lucy": st["rl_ms"],
                                          "gain_application": st["apply_ms"]}
         else:
             barrier()
@@ -511,15 +514,24 @@ def run_ours(a):
         # per-kernel algorithmic bytes (SURVEY 8d / DESIGN.md): the spectra pass reads the cube and writes B
         # energies per trace; the edge passes touch 2 x 249 samples per trace; the main gain pass reads and
         # writes the cube, reads B gains and 2 x 249 corrections and writes the intensity
-        stages["deconv_energy_spectra"] = {"ms": km["energy_spectra_ms"], "kernel": f"k_fir_energy_split<{N}>",
-                                           "algorithmic_bytes": (4 * N + 4 * B) * P}
+        if fused_chain:
+            # one kernel: reads the raw cube, writes the filtered cube, the intensity and B energies per trace
+            post_mode = "0" if m_post is None or np.all(m_post == 1) else (
+                "1" if np.all(np.delete(m_post, np.r_[0:4, N - 4:N]) == 1) else "2")
+            stages["trace_energy_fused"] = {"ms": km["energy_spectra_ms"], "kernel": f"k_chain_energy_fused<{N},{post_mode}>",
+                                            "algorithmic_bytes": (8 * N + 4 + 4 * B) * P}
+        else:
+            stages["deconv_energy_spectra"] = {"ms": km["energy_spectra_ms"], "kernel": f"k_fir_energy_split<{N}>",
+                                               "algorithmic_bytes": (4 * N + 4 * B) * P}
         edge_kernel = ("k_fir_edges_mma (tcgen05 kind::tf32)" if (N >= 2048 and os.environ.get("THZ_EDGE_MMA", "on") != "off")
                        else "k_fir_edges")
         stages["deconv_energy_edges"] = {"ms": km["energy_edges_ms"], "kernel": edge_kernel,
                                          "algorithmic_bytes": (4 * 498 + 8 * B) * P}
         stages["deconv_apply_edges"] = {"ms": km["apply_edges_ms"], "kernel": "k_fir_edge_corr",
                                         "algorithmic_bytes": (4 * 498 + 4 * B + 4 * 498) * P}
-        stages["deconv_apply"] = {"ms": km["apply_main_ms"], "kernel": f"k_fir_apply_circ<{N}>",
+        spectral = fused_chain and os.environ.get("THZ_CHAIN_SPECTRAL", "on") != "off" and P % 2 == 0
+        stages["deconv_apply"] = {"ms": km["apply_main_ms"],
+                                  "kernel": f"k_fir_apply_circ<{N}>" + (" (spectral hand-off: no forward transform)" if spectral else ""),
                                   "algorithmic_bytes": (8 * N + 4 * B + 4 * 498 + 4) * P}
     for v in stages.values():
         if "algorithmic_bytes" in v and v["ms"] > 0:
@@ -557,7 +569,9 @@ def run_ours(a):
     per_trace = (8 * N + 16 * F) if spec is not None else ((20 * N + 8 * B + 4) if bands is not None else (8 * N + 4))
     chain_bytes = per_trace * P_total
     chain = {"algorithmic_bytes_per_step": chain_bytes, "gbs": chain_bytes / (ms_per_step / 1e3) / 1e9,
-             "frac_of_hbm_peak": chain_bytes / (ms_per_step / 1e3) / 1e9 / (peak * world)}
+             "frac_of_hbm_peak": chain_bytes / (ms_per_step / 1e3) / 1e9 / (peak * world),
+             "note": "bytes of the three cube passes of SURVEY 8d (20N + 8B + 4 per trace)" +
+                     ("; the fused trace + energy kernel moves 16N + 8B + 8 per trace" if fused_chain else "")}
 
     e2e = None
     if not a.no_e2e and spec is None:
@@ -582,9 +596,11 @@ def run_ours(a):
                        "l2": ("inputs larger than L2 (cube >> 126 MB), no flush needed" if cube_bytes > (256 << 20)
                               else "cube smaller than 2 x L2: numbers include L2 hits, parity case rather than a "
                                    "bandwidth measurement"),
-                       "stages": ["trace pass (fused)"] + (["deconvolution: band energies, Richardson-Lucy "
-                                                           f"({n_rl_iter} iterations over {len(bands)} bands), "
-                                                           "gain application"] if bands is not None else [])},
+                       "stages": (["trace pass fused with the band-energy pass of the deconvolution"] if fused_chain
+                                  else ["trace pass (fused)"]) +
+                                 ([("deconvolution: " if fused_chain else "deconvolution: band energies, ") +
+                                   f"Richardson-Lucy ({n_rl_iter} iterations over {len(bands)} bands), "
+                                   "gain application"] if bands is not None else [])},
             "stage_breakdown": stages, "rank0_phases_ms": phases_ms, "chain_roofline": chain,
             "roofline": roofline, "fp32_peak": fp32, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,

@@ -352,6 +352,33 @@ int thz_chain_host(thz_ctx* ctx, const float* cube, int rows, int cols, int n, c
                    int n_bands, float* out, float* img, const volatile uint8_t* abort_flag,
                    thz_progress_fn progress, void* progress_user);
 
+/* The same chain on a device-resident cube (no copies): slots 2..7 of the chain fused with the band-energy
+ * pass of `Deconvolution::filter` in ONE kernel (the filtered pair is still on chip when its FIR band energies are
+ * formed, src/data_thread.rs:1090-1190 followed by src/filters/deconvolution.rs:963-966), then Richardson-Lucy
+ * and the gain application.  thz_plan_trace(n, ...) must have been called; d_out may alias d_in; d_img is [rows*cols].
+ * thz_deconv_stage_ms then reports {trace pass + band energies, Richardson-Lucy, gain application, iterations}. */
+int thz_chain_dev(thz_ctx* ctx, const float* d_in, int rows, int cols, int n, const thz_band_plan* bands,
+                  int n_bands, float* d_out, float* d_img, const volatile uint8_t* abort_flag,
+                  thz_progress_fn progress, void* progress_user);
+/* First part of thz_chain_dev alone (what a rank of a multi-GPU run calls before thz_slab_rl): d_out = filtered
+ * traces, d_img = their intensities, d_energy [n_bands][P] = band energies of the filtered traces.  Power-of-two
+ * n >= 512 run the fused kernel; other lengths (and THZ_CHAIN_FUSE=off) run thz_trace_fused_dev followed by
+ * thz_deconv_energies_dev.  Results of the two forms agree to f32 rounding. */
+int thz_chain_energies_dev(thz_ctx* ctx, const float* d_in, float* d_out, float* d_img, int64_t P, int n,
+                           const thz_band_plan* bands, int n_bands, float* d_energy);
+/* thz_chain_dev in two calls for a host that runs Richardson-Lucy itself in between (one rank of a multi-GPU run:
+ * thz_slab_rl on d_energy -> d_gain).  d_work [P][n] carries the hand-off between the two halves in a private
+ * layout (the spectra of the filtered trace pairs when the plan allows it -- pass C then needs no forward
+ * transform -- otherwise the filtered traces) and must not be touched in between; d_out may alias d_work. */
+int thz_chain_begin_dev(thz_ctx* ctx, const float* d_in, float* d_work, float* d_img, int64_t P, int n,
+                        const thz_band_plan* bands, int n_bands, float* d_energy);
+int thz_chain_end_dev(thz_ctx* ctx, const float* d_work, const float* d_gain, int64_t P, int n,
+                      const thz_band_plan* bands, int n_bands, float* d_out, float* d_img);
+/* Per-kernel CUDA-event sums of the last timed call (thz_chain_dev, thz_deconvolution_dev, or the calls between
+ * thz_kernel_timing_begin/_end): ms5 = {band-energy spectra pass or the fused trace + energy kernel, band-energy
+ * edge pass, gain-application edge corrections, gain-application main pass, trace pass when it ran on its own}. */
+int thz_chain_kernel_ms(const thz_ctx* ctx, float* ms5);
+
 /* thz_chain_host in two calls, for a host that runs the middle part itself (one process per GPU with
  * thz_slab_rl in between): begin = H2D chunks, fused trace pass, band energies (returns the device pointers of the
  * energies [n_bands][rows*cols] and of the gain buffer of the same shape); end = gain application, D2H chunks,

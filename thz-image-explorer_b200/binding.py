@@ -147,6 +147,11 @@ def load_library():
         "thz_deconv_stage_ms": (i32, [vp, fp]),
         "thz_deconv_kernel_ms": (i32, [vp, fp]),
         "thz_chain_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
+        "thz_chain_dev": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
+        "thz_chain_energies_dev": (i32, [vp, fp, fp, fp, i64, i32, C.POINTER(BandPlanC), i32, fp]),
+        "thz_chain_kernel_ms": (i32, [vp, fp]),
+        "thz_chain_begin_dev": (i32, [vp, fp, fp, fp, i64, i32, C.POINTER(BandPlanC), i32, fp]),
+        "thz_chain_end_dev": (i32, [vp, fp, fp, i64, i32, C.POINTER(BandPlanC), i32, fp, fp]),
         "thz_deconvolution_host": (i32, [vp, fp, i32, i32, i32, C.POINTER(BandPlanC), i32, fp, fp, vp, vp, vp]),
         "thz_scale_blocks_dev": (i32, [vp, fp, i32, i32, i32, i32, fp]),
         "thz_scale_blocks_host": (i32, [vp, fp, i32, i32, i32, i32, fp]),
@@ -429,6 +434,30 @@ class Context:
     # ------------------------------------------------------------------ deconvolution
     def deconv_energies_dev(self, d_cube, P, n, bands, d_energy):
         self._check(lib.thz_deconv_energies_dev(self.handle, d_cube, int(P), int(n), bands, len(bands), d_energy))
+
+    def chain_energies_dev(self, d_in, d_out, d_img, P, n, bands, d_energy):
+        """thz_chain_energies_dev: trace pass fused with the band-energy pass."""
+        self._check(lib.thz_chain_energies_dev(self.handle, d_in, d_out, d_img, int(P), int(n), bands, len(bands),
+                                               d_energy))
+
+    def chain_begin_dev(self, d_in, d_work, d_img, P, n, bands, d_energy):
+        """thz_chain_begin_dev: trace pass + band energies, hand-off for thz_chain_end_dev left in d_work."""
+        self._check(lib.thz_chain_begin_dev(self.handle, d_in, d_work, d_img, int(P), int(n), bands, len(bands),
+                                            d_energy))
+
+    def chain_end_dev(self, d_work, d_gain, P, n, bands, d_out, d_img):
+        self._check(lib.thz_chain_end_dev(self.handle, d_work, d_gain, int(P), int(n), bands, len(bands), d_out, d_img))
+
+    def chain_dev(self, d_in, rows, cols, n, bands, d_out, d_img):
+        """thz_chain_dev: default chain + deconvolution on a device-resident cube."""
+        self._check(lib.thz_chain_dev(self.handle, d_in, int(rows), int(cols), int(n), bands, len(bands), d_out, d_img,
+                                      None, None, None))
+
+    def chain_kernel_ms(self):
+        ms = np.zeros(5, np.float32)
+        self._check(lib.thz_chain_kernel_ms(self.handle, ms.ctypes.data))
+        return {"energy_spectra_ms": float(ms[0]), "energy_edges_ms": float(ms[1]), "apply_edges_ms": float(ms[2]),
+                "apply_main_ms": float(ms[3]), "trace_ms": float(ms[4])}
 
     def deconv_apply_dev(self, d_cube, d_gain, P, n, bands, d_out, d_img):
         self._check(lib.thz_deconv_apply_dev(self.handle, d_cube, d_gain, int(P), int(n), bands, len(bands), d_out,

@@ -157,6 +157,9 @@ int thz_ctx_create(int device, thz_ctx** out) {
   if (const char* f = getenv("THZ_APPLY_FORM")) c->force_split_apply = (strcmp(f, "split") == 0);
   if (const char* f = getenv("THZ_EDGE_MMA")) c->edge_mma = (strcmp(f, "off") != 0);
   if (const char* f = getenv("THZ_RL_BATCH")) c->rl_batch = (strcmp(f, "off") != 0);
+  if (const char* f = getenv("THZ_CHAIN_FUSE")) c->chain_fuse = (strcmp(f, "off") != 0);
+  if (const char* f = getenv("THZ_CHAIN_SPECTRAL")) c->chain_spectral = (strcmp(f, "off") != 0);
+  if (const char* f = getenv("THZ_CHAIN_EVEN")) c->chain_even_transform = (strcmp(f, "transform") == 0);
   if (const char* f = getenv("THZ_CHAIN_CHUNK_BYTES")) {
     const long long v = atoll(f);
     if (v >= 4096) c->host_chunk_bytes = (size_t)v;
@@ -317,6 +320,11 @@ int thz_plan_trace(thz_ctx* c, int n, const float* m_pre, const float* band, con
   };
   p.pre_ends_only = ends_only(m_pre);
   p.post_ends_only = ends_only(m_post);
+  p.post_mode = 0;
+  if (m_post) {
+    for (int i = 0; i < n; ++i)
+      if (m_post[i] != 1.0f) p.post_mode = std::max(p.post_mode, (i < 4 || i >= n - 4) ? 1 : 2);
+  }
   p.has_band = band != nullptr;
   if (m_pre && (rc = upload_vec(c, &p.d_m_pre, m_pre, n)) != THZ_OK) return rc;
   if (m_post && (rc = upload_vec(c, &p.d_m_post, m_post, n)) != THZ_OK) return rc;

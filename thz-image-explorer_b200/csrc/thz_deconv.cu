@@ -24,8 +24,7 @@
 // other powers as products (measured: -2.5 % on the spectra pass, -5 % on the edge pass; the trace pass, whose
 // tables fit anyway, is 2 % faster with the full table and keeps it)
 #define THZ_TW_POWERS 1
-#include "thz_fft.cuh"
-#include "thz_internal.h"
+#include "thz_trace_dev.cuh"
 
 #include <math.h>
 #include <algorithm>
@@ -71,6 +70,9 @@ struct FirArgs {
   const float* wo4;      // [Bp/4][N/2][4]
   const float* he4;      // [Bp/4][N/2][4]  H_b[2j] / M, lower-half registers
   const float* hny4;     // [Bp]       H_b[N] / M (Nyquist of the N-point spectrum)
+  // spectral hand-off between the fused trace + energy kernel and pass C (see k_chain_energy_fused)
+  float* edges;          // [P][512]: samples [0, 256) and [N - 256, N) of every filtered trace
+  const float2* xspec;   // [P / 2][N]: FFT_N of the filtered pair in Plan<N> register order (pass C input)
 };
 
 template <int M>
@@ -437,6 +439,114 @@ __device__ __forceinline__ void parseval_terms(const float2 (&z)[kE], const floa
   }
 }
 
+// Band energies of one pair from the Parseval terms of the two sub-spectra: e[band][trace] = sum over the
+// lower-half registers of we q_even + wo q_odd (+ the Nyquist bin), reduced over the group and written to
+// energy[band][p0 .. p0+1].  `red` is group-private shared memory nobody else reads any more.
+template <int N>
+__device__ __forceinline__ void band_energy_reduce(const FirArgs& a, const float (&q1e)[kE / 2], const float (&q2e)[kE / 2],
+                                                   const float (&q1o)[kE / 2], const float (&q2o)[kE / 2], float ny1,
+                                                   float ny2, int t, float* red, int64_t p0, bool act0, bool act1,
+                                                   bool z0, bool z1) {
+  constexpr int T = SGeo<N>::T;
+  constexpr int LAST = Plan<N>::ns - 1;
+  constexpr int RL = Plan<N>::r[LAST];
+  constexpr int UL = kE / RL;
+  constexpr int NLOW = kE / 2;
+  constexpr int W = (T < 32) ? T : 32;
+  constexpr int NW = (T + 31) / 32;
+  // eight bands per round: e[2*bb + trace]; the 16 partial sums of a warp are reduced by a halving tree
+  // (16 shuffles instead of 80), then across the warps through shared memory
+  for (int b0 = 0; b0 < a.B; b0 += 8) {
+    float e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NLOW; ++j) {
+      const int u = j % UL, m = j / UL;
+      const int idx = m * (N / RL) + t + u * T;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (b0 + 4 * h < a.Bp) {
+          const size_t o = ((size_t)((b0 >> 2) + h) * (N / 2) + idx) * 4;
+          const float4 w_e = __ldg(reinterpret_cast<const float4*>(a.we4 + o));
+          const float4 w_o = __ldg(reinterpret_cast<const float4*>(a.wo4 + o));
+          const float we_[4] = {w_e.x, w_e.y, w_e.z, w_e.w}, wo_[4] = {w_o.x, w_o.y, w_o.z, w_o.w};
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            const int k = 2 * (4 * h + bb);
+            e[k] = fmaf(we_[bb], q1e[j], e[k]);
+            e[k + 1] = fmaf(we_[bb], q2e[j], e[k + 1]);
+            e[k] = fmaf(wo_[bb], q1o[j], e[k]);
+            e[k + 1] = fmaf(wo_[bb], q2o[j], e[k + 1]);
+          }
+        }
+      }
+    }
+    if (t == 0) {
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) {
+        if (b0 + bb < a.B) {
+          const float w = __ldg(a.wnyq + b0 + bb);
+          e[2 * bb] = fmaf(w, ny1, e[2 * bb]);
+          e[2 * bb + 1] = fmaf(w, ny2, e[2 * bb + 1]);
+        }
+      }
+    }
+    if constexpr (W == 32) {
+      // after the step with lane offset `off` a lane keeps the upper half of its values when its `off` bit is
+      // set: lane l ends with the warp total of value l >> 1
+      const int lane = t & 31;
+#pragma unroll
+      for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+          const float send = up ? e[k] : e[k + half];
+          const float keep = up ? e[k + half] : e[k];
+          e[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      e[0] += __shfl_xor_sync(0xffffffffu, e[0], 1);
+      if constexpr (T > 32) {
+        if ((lane & 1) == 0) red[(t >> 5) * 16 + (lane >> 1)] = e[0];
+        __syncthreads();
+        if (t < 16) {   // thread t sums value t = (band t/2, trace t%2) over the warps
+          float acc = 0.f;
+          for (int w = 0; w < NW; ++w) acc += red[w * 16 + t];
+          const int bnd = b0 + (t >> 1);
+          const bool second = (t & 1) != 0;
+          if (bnd < a.B && (second ? act1 : act0))
+            a.energy[(size_t)bnd * a.bstride + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : acc;
+        }
+        __syncthreads();
+      } else {
+        // one warp per pair: lane l holds value l >> 1
+        const int v = lane >> 1, bnd = b0 + (v >> 1);
+        const bool second = (v & 1) != 0;
+        if ((lane & 1) == 0 && bnd < a.B && (second ? act1 : act0))
+          a.energy[(size_t)bnd * a.bstride + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : e[0];
+      }
+    } else {
+      // groups narrower than a warp (N < 512): plain butterfly inside the group
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) e[k] += __shfl_xor_sync(0xffffffffu, e[k], o);
+      }
+      if (t == 0) {
+#pragma unroll
+        for (int bb = 0; bb < 8; ++bb) {
+          const int bnd = b0 + bb;
+          if (bnd < a.B) {
+            if (act0) a.energy[(size_t)bnd * a.bstride + p0] = z0 ? 0.f : e[2 * bb];
+            if (act1) a.energy[(size_t)bnd * a.bstride + p0 + 1] = z1 ? 0.f : e[2 * bb + 1];
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int N, bool STAGED>
 __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy_split(const FirArgs a) {
   using GEO = SGeo<N>;
@@ -453,8 +563,6 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
   constexpr int RL = Plan<N>::r[LAST];
   constexpr int UL = kE / RL;
   constexpr int NLOW = kE / 2;
-  constexpr int W = (T < 32) ? T : 32;
-  constexpr int NW = (T + 31) / 32;
   unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
   float* red = reinterpret_cast<float*>(sm);
   int parity = 0;
@@ -501,97 +609,202 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
     __syncthreads();
     parseval_terms<N, true>(zo, sm, t, q1o, q2o);
     __syncthreads();   // partner reads done: the buffer becomes reduction scratch
-    // eight bands per round: e[2*bb + trace]; the 16 partial sums of a warp are reduced by a halving tree
-    // (16 shuffles instead of 80), then across the warps through shared memory
-    for (int b0 = 0; b0 < a.B; b0 += 8) {
-      float e[16];
+    band_energy_reduce<N>(a, q1e, q2e, q1o, q2o, ny1, ny2, t, red, p0, act0, act1, z0, z1);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Trace pass + pass A in ONE kernel: window -> FFT -> band-pass -> inverse FFT -> gate -> store +
+// intensity, and, while the filtered pair is still on chip, the Parseval band energies of the full linear FIR
+// convolution (the edge kernel subtracts the cut-off samples afterwards, as after k_fir_energy_split).
+//
+// Odd bins of the M = 2N spectrum: the gated pair y is in registers after the store -> modulate -> one forward
+// transform.  Even bins are FFT_N(y).  POST selects how they are obtained:
+//   0  no gate after the inverse: FFT_N(y) = N Z' with Z' = (band / N) X, the filtered spectrum this kernel held
+//      before the inverse transform (kept in a thread-private shared-memory stash) -- no transform at all;
+//   1  the gate differs from 1 only in the first / last four samples (the default gate: a 0.1 ps edge at 0.05 ps
+//      steps): y = y0 - c with c supported on those eight samples, so FFT_N(y)[k] = N Z'[k] - sum_n c_n w_N^(k n).
+//      A thread's 16 bins are k0(u) + m N/RL (m = digit of the last radix-RL stage), hence
+//      w_N^(k n) = w_N^(k0 n) exp(-2 pi i m n / RL): the correction of its RL bins is ONE RL-point DFT of the eight
+//      twiddled samples -- a few hundred flops instead of a 4096-point transform;
+//   2  general gate: the stash holds y instead and the even bins cost a second forward transform.
+// Modes 0 / 1 differ from transforming the stored trace by f32 rounding only (tests/test_chain_fused_gpu.py).
+//
+// SPEC (spectral hand-off, whole-chain calls): the kernel writes FFT_N of the gated pair -- which it holds anyway
+// -- INSTEAD of the filtered traces, same bytes, same place; pass C (k_fir_apply_circ<.., SPEC>) then starts from
+// the spectrum and saves its forward transform.  The 2 x 256 edge samples per trace that k_fir_edges(_mma) and
+// k_fir_edge_corr read go to a side buffer of 512-float rows (those kernels see it as a cube of 512-sample traces,
+// of which they only touch the first and last 249 / 256 samples).  Trace counts must be even (whole pairs).
+// ------------------------------------------------------------------------------------
+template <int N> struct FGeo {
+  static constexpr size_t stash_off = (Geo<N>::smem_bytes + 15) & ~(size_t)15;
+  static constexpr size_t smem_bytes = stash_off + (size_t)Geo<N>::G * (N + 8) * sizeof(float2);
+};
+
+template <int N, int POST, bool SPEC>
+__global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_chain_energy_fused(const TraceArgs a, const FirArgs f) {
+  using GEO = Geo<N>;
+  constexpr int T = GEO::T, G = GEO::G;
+  static_assert(T >= 8, "head and tail gate samples must belong to different threads");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(N));
+  const int g = threadIdx.x / T, t = threadIdx.x % T;
+  float2* sm = smem + (size_t)g * padded_len(N);
+  float2* stash = reinterpret_cast<float2*>(smem_raw + FGeo<N>::stash_off) + (size_t)g * N + t;   // [i * T]: thread-private
+  float2* cs = reinterpret_cast<float2*>(smem_raw + FGeo<N>::stash_off) + (size_t)G * N + g * 8;  // gate corrections of the group
+  const int64_t npairs = (a.P + 1) >> 1;
+  const int64_t nitems = (npairs + G - 1) / G;
+  constexpr int LAST = Plan<N>::ns - 1;
+  constexpr int RL = Plan<N>::r[LAST];
+  constexpr int UL = kE / RL;
+  constexpr int NLOW = kE / 2;
+  unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
+  float* red = reinterpret_cast<float*>(sm);
+  int parity = 0;
+
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
+    const int64_t p0 = (item * G + g) * 2;
+    const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
+    const int64_t next = item + gridDim.x;
+    if (next < nitems) {
+      int64_t cnt = a.P - next * G * 2;
+      if (cnt > 2 * G) cnt = 2 * G;
+      prefetch_l2_slab(a.in + next * G * 2 * N, cnt * N);
+    }
+    float2 v[kE];
+    bool nz0, nz1, z0, z1;
+    load_pair<N>(v, a, t, act0, act1, p0, nz0, nz1);
+    nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
+    {
+      float hq[kE];
+      auto fetch_hq = [&]() {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) e[k] = 0.f;
+        for (int i = 0; i < kE; ++i) {
+          const int u = i % UL, m = i / UL;
+          hq[i] = __ldg(a.hq + m * (N / RL) + t + u * T);
+        }
+      };
+      fft_forward_hook<N>(v, t, sm, a.tw, fetch_hq);
 #pragma unroll
-      for (int j = 0; j < NLOW; ++j) {
-        const int u = j % UL, m = j / UL;
-        const int idx = m * (N / RL) + t + u * T;
+      for (int i = 0; i < kE; ++i) {
+        v[i].x *= hq[i];
+        v[i].y *= hq[i];
+      }
+    }
+    if constexpr (POST != 2) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (b0 + 4 * h < a.Bp) {
-            const size_t o = ((size_t)((b0 >> 2) + h) * (N / 2) + idx) * 4;
-            const float4 w_e = __ldg(reinterpret_cast<const float4*>(a.we4 + o));
-            const float4 w_o = __ldg(reinterpret_cast<const float4*>(a.wo4 + o));
-            const float we_[4] = {w_e.x, w_e.y, w_e.z, w_e.w}, wo_[4] = {w_o.x, w_o.y, w_o.z, w_o.w};
+      for (int i = 0; i < kE; ++i) stash[i * T] = v[i];
+    }
+    fft_inverse<N>(v, t, sm, a.tw);
+    nz_resolve<T>(g, parity, nzbuf, z0, z1);
+    float2 y0h = v[0], y0t = v[kE - 1];   // samples t and N - T + t before the gate
+    store_pair<N, !SPEC>(v, a, t, g, act0, act1, p0, a.m_post != nullptr, scr, z0, z1);
+    if constexpr (SPEC) {
+      // the filtered traces themselves are not written: pass C starts from their spectrum (stored below) and the
+      // edge kernels from the first / last 256 samples, kept as rows of 512 floats
+      float* e0 = f.edges + p0 * 512;
+      float* e1 = e0 + 512;
+      constexpr int NE = (T >= 256) ? 1 : 256 / T;   // registers that hold head (tail) samples
 #pragma unroll
-            for (int bb = 0; bb < 4; ++bb) {
-              const int k = 2 * (4 * h + bb);
-              e[k] = fmaf(we_[bb], q1e[j], e[k]);
-              e[k + 1] = fmaf(we_[bb], q2e[j], e[k + 1]);
-              e[k] = fmaf(wo_[bb], q1o[j], e[k]);
-              e[k + 1] = fmaf(wo_[bb], q2o[j], e[k + 1]);
-            }
-          }
+      for (int i = 0; i < NE; ++i) {
+        const int n = t + i * T;
+        if (T <= 256 || n < 256) {
+          if (act0) e0[n] = v[i].x;
+          if (act1) e1[n] = v[i].y;
         }
       }
-      if (t == 0) {
 #pragma unroll
-        for (int bb = 0; bb < 8; ++bb) {
-          if (b0 + bb < a.B) {
-            const float w = __ldg(a.wnyq + b0 + bb);
-            e[2 * bb] = fmaf(w, ny1, e[2 * bb]);
-            e[2 * bb + 1] = fmaf(w, ny2, e[2 * bb + 1]);
-          }
-        }
-      }
-      if constexpr (W == 32) {
-        // after the step with lane offset `off` a lane keeps the upper half of its values when its `off` bit is
-        // set: lane l ends with the warp total of value l >> 1
-        const int lane = t & 31;
-#pragma unroll
-        for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-          const bool up = (lane & off) != 0;
-#pragma unroll
-          for (int k = 0; k < half; ++k) {
-            const float send = up ? e[k] : e[k + half];
-            const float keep = up ? e[k + half] : e[k];
-            e[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
-        }
-        e[0] += __shfl_xor_sync(0xffffffffu, e[0], 1);
-        if constexpr (T > 32) {
-          if ((lane & 1) == 0) red[(t >> 5) * 16 + (lane >> 1)] = e[0];
-          __syncthreads();
-          if (t < 16) {   // thread t sums value t = (band t/2, trace t%2) over the warps
-            float acc = 0.f;
-            for (int w = 0; w < NW; ++w) acc += red[w * 16 + t];
-            const int bnd = b0 + (t >> 1);
-            const bool second = (t & 1) != 0;
-            if (bnd < a.B && (second ? act1 : act0))
-              a.energy[(size_t)bnd * a.bstride + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : acc;
-          }
-          __syncthreads();
-        } else {
-          // one warp per pair: lane l holds value l >> 1
-          const int v = lane >> 1, bnd = b0 + (v >> 1);
-          const bool second = (v & 1) != 0;
-          if ((lane & 1) == 0 && bnd < a.B && (second ? act1 : act0))
-            a.energy[(size_t)bnd * a.bstride + p0 + (second ? 1 : 0)] = (second ? z1 : z0) ? 0.f : e[0];
-        }
-      } else {
-        // groups narrower than a warp (N < 512): plain butterfly inside the group
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-#pragma unroll
-          for (int o = W / 2; o > 0; o >>= 1) e[k] += __shfl_xor_sync(0xffffffffu, e[k], o);
-        }
-        if (t == 0) {
-#pragma unroll
-          for (int bb = 0; bb < 8; ++bb) {
-            const int bnd = b0 + bb;
-            if (bnd < a.B) {
-              if (act0) a.energy[(size_t)bnd * a.bstride + p0] = z0 ? 0.f : e[2 * bb];
-              if (act1) a.energy[(size_t)bnd * a.bstride + p0 + 1] = z1 ? 0.f : e[2 * bb + 1];
-            }
-          }
+      for (int i = kE - NE; i < kE; ++i) {
+        const int n = t + i * T - (N - 512);           // 256 + (sample - (N - 256))
+        if (T <= 256 || n >= 256) {
+          if (act0) e0[n] = v[i].x;
+          if (act1) e1[n] = v[i].y;
         }
       }
     }
+    if constexpr (POST == 1) {
+      // c_n = y0[n] - y[n] for n = 0..3 (cs[n]) and n = N - j, j = 1..4 (cs[3 + j]); read after the barriers of the
+      // transform below, overwritten only after the barriers of the next item
+      if (t < 4) cs[t] = csub(y0h, v[0]);
+      if (t >= T - 4) cs[3 + (T - t)] = csub(y0t, v[kE - 1]);
+    } else {
+      (void)y0h;
+      (void)y0t;
+    }
+    if constexpr (POST == 2) {
+#pragma unroll
+      for (int i = 0; i < kE; ++i) stash[i * T] = v[i];
+    }
+    // ---- odd bins: FFT_N(y w_M^n) ----
+    float q1o[NLOW], q2o[NLOW];
+    modulate<N>(v, f.mod, t);
+    fft_forward<N>(v, t, sm, a.tw);
+    __syncthreads();
+#pragma unroll
+    for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = v[i];   // mirrors of lower-half bins are upper-half registers
+    __syncthreads();
+    parseval_terms<N, true>(v, sm, t, q1o, q2o);
+    // ---- even bins: FFT_N(y) ----
+    float2 z[kE];
+#pragma unroll
+    for (int i = 0; i < kE; ++i) z[i] = stash[i * T];
+    if constexpr (POST == 2) {
+      fft_forward<N>(z, t, sm, a.tw);   // its first barrier orders the partner reads above before the exchange
+    } else {
+#pragma unroll
+      for (int i = 0; i < kE; ++i) {
+        z[i].x *= (float)N;
+        z[i].y *= (float)N;
+      }
+      if constexpr (POST == 1) {
+        float2 c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = cs[j];
+#pragma unroll
+        for (int u = 0; u < UL; ++u) {
+          const int k0 = pos_to_bin<N>(stage_elem<N, LAST>(t, u));   // bin of digit m = 0; < N / RL
+          const float2 w1 = __ldg(f.mod + 2 * k0);                   // exp(-2 pi i k0 / N)
+          const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+          float2 d[RL];
+#pragma unroll
+          for (int m = 0; m < RL; ++m) d[m] = make_float2(0.f, 0.f);
+          d[0] = c[0];
+          d[1 % RL] = cadd(d[1 % RL], cmul(c[1], w1));
+          d[2 % RL] = cadd(d[2 % RL], cmul(c[2], w2));
+          d[3 % RL] = cadd(d[3 % RL], cmul(c[3], w3));
+          d[(RL - 1) % RL] = cadd(d[(RL - 1) % RL], cmul_conj(c[4], w1));           // n = N - 1: w_N^(-k0)
+          d[(2 * RL - 2) % RL] = cadd(d[(2 * RL - 2) % RL], cmul_conj(c[5], w2));
+          d[(3 * RL - 3) % RL] = cadd(d[(3 * RL - 3) % RL], cmul_conj(c[6], w3));
+          d[(4 * RL - 4) % RL] = cadd(d[(4 * RL - 4) % RL], cmul_conj(c[7], w4));
+          dftR<RL, false>(d);
+#pragma unroll
+          for (int m = 0; m < RL; ++m) z[u + UL * m] = csub(z[u + UL * m], d[m]);
+        }
+      }
+    }
+    if constexpr (SPEC) {
+      // FFT_N of the gated pair in register order: what pass C would otherwise recompute from the stored traces
+      float2* so = reinterpret_cast<float2*>(a.out) + (p0 >> 1) * N + t;
+      if (act0) {
+#pragma unroll
+        for (int i = 0; i < kE; ++i) __stcs(so + i * T, z[i]);
+      }
+    }
+    __syncthreads();   // the odd-bin partner reads (and the last exchange of the POST == 2 transform) are done
+#pragma unroll
+    for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
+    __syncthreads();
+    float q1e[NLOW], q2e[NLOW];
+    parseval_terms<N, false>(z, sm, t, q1e, q2e);
+    float ny1 = 0.f, ny2 = 0.f;   // bin M/2 = even index N/2: register (u = 0, digit RL/2) of thread 0
+    if (t == 0) {
+      const float2 zz = z[UL * (RL / 2)];
+      ny1 = zz.x * zz.x;
+      ny2 = zz.y * zz.y;
+    }
+    __syncthreads();   // partner reads done: the buffer becomes reduction scratch
+    band_energy_reduce<N>(f, q1e, q2e, q1o, q2o, ny1, ny2, t, red, p0, act0, act1, z0, z1);
   }
 }
 
@@ -1080,7 +1293,7 @@ __global__ void __launch_bounds__(256, 2) k_fir_edge_corr(const FirArgs a) {
   }
 }
 
-template <int N, bool STAGED>
+template <int N, bool STAGED, bool SPEC = false>
 __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_circ(const FirArgs a) {
   using GEO = SGeo<N>;
   constexpr int T = GEO::T, G = GEO::G;
@@ -1102,7 +1315,19 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_
     const bool act0 = p0 < a.P, act1 = p0 + 1 < a.P;
     bool nz0, nz1, bad0 = false, bad1 = false;
     float2 z[kE];
-    if constexpr (STAGED) {
+    if constexpr (SPEC) {
+      // spectral hand-off: the fused trace + energy kernel left FFT_N of the pair here, in register order
+      const int64_t next = item + gridDim.x;
+      if (next < nitems) {
+        int64_t cnt = a.P - next * G * 2;
+        if (cnt > 2 * G) cnt = 2 * G;
+        prefetch_l2_slab(reinterpret_cast<const float*>(a.xspec) + next * G * 2 * N, cnt * N);
+      }
+      const float2* sp = a.xspec + pair * N + t;
+      nz0 = nz1 = false;
+#pragma unroll
+      for (int i = 0; i < kE; ++i) z[i] = act0 ? __ldcs(sp + i * T) : make_float2(0.f, 0.f);
+    } else if constexpr (STAGED) {
       const float* slab = pipe.acquire(item);
       load_pair_n<N>(z, slab, t, g, act0, act1, nz0, nz1);
     } else {
@@ -1115,8 +1340,8 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_apply_
       load_pair_direct<N>(z, a.x, p0, t, act0, act1, nz0, nz1);
     }
     const float gv = prefetch_pair_gains(a, p0, act0, act1, bad0, bad1);
-    fft_forward<N>(z, t, sm, a.tw);
-    __syncthreads();
+    if constexpr (!SPEC) fft_forward<N>(z, t, sm, a.tw);
+    __syncthreads();   // SPEC: the previous item's exchanges are done with the buffer
 #pragma unroll
     for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];   // mirrors of lower-half bins are upper-half registers
     __syncthreads();
@@ -1573,6 +1798,7 @@ template <int N> static int do_apply_split(thz_ctx* c, cudaStream_t s, const Fir
   return launch_fir<N>(c, s, k_fir_apply_split<N>, a, SGeo<N>::smem_bytes);
 }
 template <int N> static int do_apply_circ(thz_ctx* c, cudaStream_t s, const FirArgs& a) {
+  if (a.xspec != nullptr) return launch_fir<N>(c, s, k_fir_apply_circ<N, false, true>, a, SGeo<N>::base_bytes, 40);
   if (c->unstaged_fir) return launch_fir<N>(c, s, k_fir_apply_circ<N, false>, a, SGeo<N>::base_bytes, 40);
   return launch_fir<N>(c, s, k_fir_apply_circ<N, true>, a, SGeo<N>::smem_bytes);
 }
@@ -1688,12 +1914,136 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
   return rc;
 }
 
+// ---- trace pass + band energies in one cube pass (k_chain_energy_fused) ----
+template <int N, int POST, bool SPEC>
+static int launch_chain_fused(thz_ctx* c, cudaStream_t s, const TraceArgs& ta, const FirArgs& fa) {
+  using GEO = Geo<N>;
+  auto kernel = k_chain_energy_fused<N, POST, SPEC>;
+  const size_t smem = FGeo<N>::smem_bytes;
+  const void* key = (const void*)kernel;
+  auto it = c->occ.find(key);
+  if (it == c->occ.end()) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(smem)");
+    // shared memory for kMinBlocks CTAs (exchange buffer + stash, 1 KB reserved per CTA), the rest stays L1 for the tables
+    int pct = (int)((GEO::kMinBlocks * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+    if (pct > 100) pct = 100;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaFuncSetAttribute(carveout)");
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, GEO::NT, smem);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (nb < 1) return set_err(c, THZ_ECUDA, "fused chain kernel does not fit on an SM");
+    it = c->occ.emplace(key, nb).first;
+  }
+  const int64_t npairs = (ta.P + 1) / 2;
+  const int64_t nitems = (npairs + GEO::G - 1) / GEO::G;
+  if (nitems <= 0) return THZ_OK;
+  int64_t grid = (int64_t)c->sm_count * it->second;
+  if (grid > nitems) grid = nitems;
+  kernel<<<(unsigned)grid, GEO::NT, smem, s>>>(ta, fa);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(c, e, "fused chain kernel launch");
+  return THZ_OK;
+}
+template <int N> static int do_chain_fused(thz_ctx* c, cudaStream_t s, const TraceArgs& ta, const FirArgs& fa, int post) {
+  if constexpr (N < 512) {
+    return THZ_EINVAL;
+  } else {
+    if (fa.edges != nullptr) {
+      if (post == 0) return launch_chain_fused<N, 0, true>(c, s, ta, fa);
+      if (post == 1) return launch_chain_fused<N, 1, true>(c, s, ta, fa);
+      return launch_chain_fused<N, 2, true>(c, s, ta, fa);
+    }
+    if (post == 0) return launch_chain_fused<N, 0, false>(c, s, ta, fa);
+    if (post == 1) return launch_chain_fused<N, 1, false>(c, s, ta, fa);
+    return launch_chain_fused<N, 2, false>(c, s, ta, fa);
+  }
+}
+static int dispatch_chain_fused(thz_ctx* c, cudaStream_t s, int n, const TraceArgs& ta, const FirArgs& fa, int post) {
+  THZ_DISPATCH_M(n, do_chain_fused, c, s, ta, fa, post);
+}
+
+// Slots 2..7 of the chain on d_in -> d_out (+ intensity) and the band energies of the filtered traces.  One fused
+// kernel + the edge kernel when the plan is a power-of-two length >= 512 with the split FIR form (every BASELINE
+// shape); the trace pass followed by deconv_energies otherwise, or with THZ_CHAIN_FUSE=off (A/B checks).
+// c->chain_even: how the fused kernel obtains the even bins -- 0 = from the filtered spectrum when the gate allows
+// it (default), 1 = always by a forward transform of the stored trace (THZ_CHAIN_EVEN=transform, A/B checks).
+bool chain_spectral_ok(const thz_ctx* c, int n, int64_t P) {
+  return c->chain_fuse && c->chain_spectral && !c->force_split_apply && c->plan.blue_m == 0 && c->plan.n == n &&
+         n >= 512 && supported_n(n) && (P % 2) == 0;
+}
+
+int chain_energies(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P, int n,
+                   const thz_band_plan* bands, int B, float* d_energy, int64_t bstride, float* d_edges) {
+  if (bstride == 0) bstride = P;
+  if (d_edges && !chain_spectral_ok(c, n, P)) return set_err(c, THZ_ESTATE, "spectral hand-off not available for this plan");
+  if (c->plan.n != n) return set_err(c, THZ_ESTATE, "thz_plan_trace(n, ...) must be called first");
+  if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
+  if (P == 0) return THZ_OK;
+  if (!d_in || !d_out || !d_energy) return set_err(c, THZ_EINVAL, "null pointer");
+  bool fuse = c->chain_fuse && c->plan.blue_m == 0 && n >= 512 && supported_n(n);
+  FirTables ft;
+  int rc = THZ_OK;
+  if (fuse) {
+    rc = upload_fir_tables(c, s, n, bands, B, ft);
+    if (rc != THZ_OK) return rc;
+    fuse = ft.split && ft.m >= n + THZ_FIR_TAPS - 1;
+  }
+  if (!fuse) {
+    if (d_edges) return set_err(c, THZ_ESTATE, "spectral hand-off needs the fused kernel");
+    KernelTimer kt(c, s, 4);
+    rc = launch_trace_fused(c, s, d_in, d_out, d_img, P);
+    kt.stop();
+    if (rc == THZ_OK) rc = deconv_energies(c, s, d_out, P, n, bands, B, d_energy, bstride);
+    return rc;
+  }
+  TraceArgs ta;
+  rc = trace_fused_args(c, ta, d_in, d_out, d_img, P);
+  if (rc != THZ_OK) return rc;
+  const FftTables *tbn = nullptr, *tb512 = nullptr;
+  rc = get_tables(c, n, &tbn);
+  if (rc == THZ_OK) rc = get_tables(c, 512, &tb512);
+  if (rc != THZ_OK) return rc;
+  FirArgs a{};
+  a.x = d_out; a.n = n; a.P = P; a.hq = ft.d_hq; a.B = B; a.energy = d_energy; a.bstride = bstride;
+  a.wq = ft.d_wq; a.wnyq = ft.d_wnyq; a.edge = ft.d_edge; a.tw512 = tb512->d_tw;
+  FirArgs as = a;
+  as.tw = tbn->d_tw;
+  as.he = ft.d_he; as.ho = ft.d_ho; as.we = ft.d_we; as.wo = ft.d_wo; as.mod = ft.d_mod;
+  as.Bp = ft.Bp; as.we4 = ft.d_we4; as.wo4 = ft.d_wo4;
+  as.edges = d_edges;
+  if (d_edges) {   // the edge kernels read the side buffer as a cube of 512-sample rows
+    a.x = d_edges;
+    a.n = 512;
+  }
+  const int post = c->chain_even_transform ? 2 : c->plan.post_mode;
+  {
+    KernelTimer kt(c, s, 0);
+    rc = dispatch_chain_fused(c, s, n, ta, as, post);
+    kt.stop();
+  }
+  if (rc == THZ_OK) {
+    KernelTimer kt(c, s, 1);
+    if (c->edge_mma && edges_mma_supported(n))
+      rc = d_edges ? launch_fir_edges_mma(c, s, d_edges, P, 512, bands, B, d_energy, bstride, true)
+                   : launch_fir_edges_mma(c, s, d_out, P, n, bands, B, d_energy, bstride);
+    else
+      rc = launch_fir<512>(c, s, k_fir_edges, a);
+    kt.stop();
+  }
+  return rc;
+}
+
 // `lane` selects the wrap-around correction workspace: calls that are in flight on different streams at the same
 // time (the chunk pipeline of thz_chain_host) must not share one (k_fir_edge_corr of chunk i+1 would overwrite
 // what k_fir_apply_circ of chunk i still reads).  Lane 0 = the context's compute stream, 1 + k = hstream[k].
 int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d_gain, int64_t P, int n,
-                 const thz_band_plan* bands, int B, float* d_out, float* d_img, int64_t bstride, int lane) {
+                 const thz_band_plan* bands, int B, float* d_out, float* d_img, int64_t bstride, int lane,
+                 const float* d_edges) {
   if (bstride == 0) bstride = P;
+  if (d_edges && !chain_spectral_ok(c, n, P)) return set_err(c, THZ_ESTATE, "spectral hand-off not available for this plan");
   if (B < 1 || B > THZ_MAX_BANDS || !bands) return set_err(c, THZ_EINVAL, "bad band count");
   if (P == 0) return THZ_OK;
   if (!d_cube || !d_gain || !d_out || n < 2) return set_err(c, THZ_EINVAL, "null pointer");
@@ -1737,10 +2087,16 @@ int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d
           ac.img = d_img ? d_img + p_lo : nullptr;
           ac.corr = (float2*)pc;
           {
+            FirArgs ae = ac;
+            if (d_edges) {   // spectral hand-off: edge samples from the side buffer (rows of 512 floats)
+              ae.x = d_edges + p_lo * 512;
+              ae.n = 512;
+            }
             KernelTimer kt(c, s, 2);
-            rc = launch_fir<512>(c, s, k_fir_edge_corr, ac);
+            rc = launch_fir<512>(c, s, k_fir_edge_corr, ae);
             kt.stop();
           }
+          if (d_edges) ac.xspec = reinterpret_cast<const float2*>(d_cube) + (p_lo / 2) * n;
           if (rc == THZ_OK) {
             KernelTimer kt(c, s, 3);
             rc = dispatch_apply_circ(c, s, n, ac);
@@ -1780,10 +2136,19 @@ int chain_pass_in(thz_ctx* c, const float* cube, int64_t P, int n, const thz_ban
   if (d_energy_out) *d_energy_out = d_energy;
   if (d_gain_out) *d_gain_out = (float*)pg;
   // FIR tables are built (and cached) before the pipelined loop so that no chunk waits on the host
+  float* d_edges = nullptr;
+  c->host_chain_spectral = false;
   if (n_bands) {
     FirTables ft;
     rc = upload_fir_tables(c, c->stream, n, bands, n_bands, ft);
     if (rc != THZ_OK) return rc;
+    if (chain_spectral_ok(c, n, P)) {   // the resident cube holds spectra between the two halves (see k_chain_energy_fused)
+      void* pr = nullptr;
+      rc = ws_get(c, WS_EDGE_ROWS, (size_t)P * 512 * sizeof(float), &pr);
+      if (rc != THZ_OK) return rc;
+      d_edges = (float*)pr;
+      c->host_chain_spectral = true;
+    }
   }
   int64_t ct = (int64_t)c->host_chunk_bytes / ((int64_t)n * 4);   // 256 MiB chunks (THZ_CHAIN_CHUNK_BYTES), whole pairs
   ct &= ~(int64_t)1;
@@ -1794,8 +2159,9 @@ int chain_pass_in(thz_ctx* c, const float* cube, int64_t P, int n, const thz_ban
     cudaStream_t s = c->hstream[i % kHostStreams];
     float* d = d_cube + p * n;
     THZ_CUDA(c, cudaMemcpyAsync(d, cube + p * n, (size_t)np * n * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = launch_trace_fused(c, s, d, d, d_img + p, np);
-    if (rc == THZ_OK && n_bands) rc = deconv_energies(c, s, d, np, n, bands, n_bands, d_energy + p, P);
+    if (n_bands) rc = chain_energies(c, s, d, d, d_img + p, np, n, bands, n_bands, d_energy + p, P,
+                                     d_edges ? d_edges + p * 512 : nullptr);
+    else rc = launch_trace_fused(c, s, d, d, d_img + p, np);
     if (rc == THZ_OK && !n_bands) {
       THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
@@ -1810,6 +2176,7 @@ int chain_pass_out(thz_ctx* c, int64_t P, int n, const thz_band_plan* bands, int
   float* d_img = (float*)c->ws[WS_HOST_IMG].first;
   float* d_gain = n_bands ? (float*)c->ws[WS_GAIN].first : nullptr;
   if (!d_cube || !d_img || (n_bands && !d_gain)) return set_err(c, THZ_ESTATE, "chain_pass_in has not run");
+  const float* d_edges = (n_bands && c->host_chain_spectral) ? (const float*)c->ws[WS_EDGE_ROWS].first : nullptr;
   int rc = THZ_OK;
   if (n_bands) {
     int64_t ct = (int64_t)c->host_chunk_bytes / ((int64_t)n * 4);
@@ -1820,7 +2187,8 @@ int chain_pass_out(thz_ctx* c, int64_t P, int n, const thz_band_plan* bands, int
       const int64_t np = std::min(ct, P - p);
       cudaStream_t s = c->hstream[i % kHostStreams];
       float* d = d_cube + p * n;
-      rc = deconv_apply(c, s, d, d_gain + p, np, n, bands, n_bands, d, d_img + p, P, 1 + i % kHostStreams);
+      rc = deconv_apply(c, s, d, d_gain + p, np, n, bands, n_bands, d, d_img + p, P, 1 + i % kHostStreams,
+                        d_edges ? d_edges + p * 512 : nullptr);
       if (rc == THZ_OK)
         THZ_CUDA(c, cudaMemcpyAsync(out + p * n, d, (size_t)np * n * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
@@ -1921,6 +2289,93 @@ int thz_deconvolution_dev(thz_ctx* c, const float* d_cube, int rows, int cols, i
   for (auto& e : ev) cudaEventDestroy(e);
   if (rc == THZ_OK && progress) progress(1.0f, progress_user);
   return rc;
+}
+
+int thz_chain_energies_dev(thz_ctx* c, const float* d_in, float* d_out, float* d_img, int64_t P, int n,
+                           const thz_band_plan* bands, int n_bands, float* d_energy) {
+  CHECK_CTX(c);
+  return chain_energies(c, c->stream, d_in, d_out, d_img, P, n, bands, n_bands, d_energy);
+}
+
+// The whole default chain + deconvolution on a device-resident cube (the device-pointer twin of thz_chain_host):
+// trace pass fused with the band energies -> Richardson-Lucy -> gain application.  d_out may alias d_in.
+int thz_chain_dev(thz_ctx* c, const float* d_in, int rows, int cols, int n, const thz_band_plan* bands, int n_bands,
+                  float* d_out, float* d_img, const volatile uint8_t* abort_flag, thz_progress_fn progress,
+                  void* progress_user) {
+  CHECK_CTX(c);
+  if (!bands || n_bands < 1 || n_bands > THZ_MAX_BANDS) return set_err(c, THZ_EINVAL, "bad band count");
+  const int64_t P = (int64_t)rows * cols;
+  if (P == 0) return THZ_OK;
+  if (!d_img) return set_err(c, THZ_EINVAL, "null intensity pointer");
+  if (progress) progress(0.0f, progress_user);
+  void *pe = nullptr, *pg = nullptr;
+  int rcw = ws_get(c, WS_ENERGY, (size_t)n_bands * P * sizeof(float), &pe);
+  if (rcw == THZ_OK) rcw = ws_get(c, WS_GAIN, (size_t)n_bands * P * sizeof(float), &pg);
+  if (rcw != THZ_OK) return rcw;
+  float *d_energy = (float*)pe, *d_gain = (float*)pg;
+  float* d_edges = nullptr;
+  if (chain_spectral_ok(c, n, P)) {
+    void* pr = nullptr;
+    rcw = ws_get(c, WS_EDGE_ROWS, (size_t)P * 512 * sizeof(float), &pr);
+    if (rcw != THZ_OK) return rcw;
+    d_edges = (float*)pr;
+  }
+  cudaEvent_t ev[4];
+  for (auto& e : ev) cudaEventCreate(&e);
+  resolve_kernel_events(c);
+  for (float& v : c->kernel_ms) v = 0.f;
+  c->time_kernels = true;
+  cudaEventRecord(ev[0], c->stream);
+  int rc = chain_energies(c, c->stream, d_in, d_out, d_img, P, n, bands, n_bands, d_energy, 0, d_edges);
+  cudaEventRecord(ev[1], c->stream);
+  long total_iter = 0;
+  for (int b = 0; b < n_bands; ++b) total_iter += std::max(bands[b].n_iter, 1);
+  if (rc == THZ_OK) rc = rl_all_bands(c, d_energy, P, rows, cols, bands, n_bands, d_gain, abort_flag, progress, progress_user);
+  cudaEventRecord(ev[2], c->stream);
+  if (rc == THZ_OK) rc = deconv_apply(c, c->stream, d_out, d_gain, P, n, bands, n_bands, d_out, d_img, 0, 0, d_edges);
+  cudaEventRecord(ev[3], c->stream);
+  c->time_kernels = false;
+  cudaStreamSynchronize(c->stream);
+  resolve_kernel_events(c);
+  for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&c->stage_ms[i], ev[i], ev[i + 1]);
+  c->stage_ms[3] = (float)total_iter;
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (rc == THZ_OK && progress) progress(1.0f, progress_user);
+  return rc;
+}
+
+// thz_chain_dev in two calls for a host that runs Richardson-Lucy itself between them (one rank of a multi-GPU run:
+// thz_slab_rl).  d_work [P][n] holds the hand-off between the halves in a private layout (the spectra of the
+// filtered pairs when the plan allows the spectral hand-off, the filtered traces otherwise) and must not be
+// touched in between; d_out of the second half may alias it.
+int thz_chain_begin_dev(thz_ctx* c, const float* d_in, float* d_work, float* d_img, int64_t P, int n,
+                        const thz_band_plan* bands, int n_bands, float* d_energy) {
+  CHECK_CTX(c);
+  float* d_edges = nullptr;
+  c->host_chain_spectral = false;
+  if (P > 0 && chain_spectral_ok(c, n, P)) {
+    void* pr = nullptr;
+    int rc = ws_get(c, WS_EDGE_ROWS, (size_t)P * 512 * sizeof(float), &pr);
+    if (rc != THZ_OK) return rc;
+    d_edges = (float*)pr;
+    c->host_chain_spectral = true;
+  }
+  return chain_energies(c, c->stream, d_in, d_work, d_img, P, n, bands, n_bands, d_energy, 0, d_edges);
+}
+
+int thz_chain_end_dev(thz_ctx* c, const float* d_work, const float* d_gain, int64_t P, int n, const thz_band_plan* bands,
+                      int n_bands, float* d_out, float* d_img) {
+  CHECK_CTX(c);
+  const float* d_edges = c->host_chain_spectral ? (const float*)c->ws[WS_EDGE_ROWS].first : nullptr;
+  return deconv_apply(c, c->stream, d_work, d_gain, P, n, bands, n_bands, d_out, d_img, 0, 0, d_edges);
+}
+
+// per-kernel sums of the last timed call, five slots: [0] band-energy spectra kernel (or the fused trace + energy
+// kernel), [1] energy edges, [2] gain-application edges, [3] gain application, [4] trace pass when it ran on its own
+int thz_chain_kernel_ms(const thz_ctx* c, float* ms5) {
+  if (!c || !ms5) return THZ_EINVAL;
+  for (int i = 0; i < 5; ++i) ms5[i] = c->kernel_ms[i];
+  return THZ_OK;
 }
 
 // CUDA-event pairs around the cube kernels of ANY call between begin and end (the sharded path calls the passes

@@ -336,9 +336,12 @@ static void build_edge_matrices(const thz_band_plan* bands, int B, std::vector<f
 bool edges_mma_supported(int n) { return n >= 2048 && (n % 4) == 0; }
 
 // Subtracts the head / tail energies from d_energy for all bands (chunks of <= 8 bands per launch).
+// edge_rows: d_cube is the side buffer of the spectral hand-off, rows of 512 floats = first / last 256 samples of
+// every trace (n = 512: the kernel only reads columns [0, 256) and [n - 256, n))
 int launch_fir_edges_mma(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
-                         int B, float* d_energy, int64_t bstride) {
-  if (!edges_mma_supported(n)) return set_err(c, THZ_EINVAL, "tensor-core edge pass needs n >= 2048");
+                         int B, float* d_energy, int64_t bstride, bool edge_rows) {
+  if (edge_rows ? n != 512 : !edges_mma_supported(n))
+    return set_err(c, THZ_EINVAL, "tensor-core edge pass needs n >= 2048");
   // matrices are cached per context, keyed by the taps
   uint64_t key = 0xcbf29ce484222325ull;
   for (int b = 0; b < B; ++b)

@@ -25,6 +25,10 @@ struct TracePlan {
   bool has_pre = false, has_post = false, has_band = false;
   // the multiplier is exactly 1 on [n/16, n - n/16): only the first and the last register of a thread need it
   bool pre_ends_only = false, post_ends_only = false;
+  // the gate after the inverse transform: 0 = none or all ones, 1 = differs from 1 only in the first / last four
+  // samples (the default gate), 2 = general.  The fused trace + band-energy kernel derives the spectrum of the
+  // gated trace from the filtered spectrum it already holds in modes 0 and 1 (thz_deconv.cu)
+  int post_mode = 0;
   // traces whose length is not a power of two go through the chirp-z kernels (thz_bluestein.cu)
   int blue_m = 0;               // power-of-two transform size (>= 2n - 1), 0 = power-of-two plan
   float2* d_chirp = nullptr;    // [n]
@@ -45,7 +49,13 @@ constexpr int kHostStreams = 3;
 int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
                     int B, float* d_energy, int64_t bstride = 0);
 int deconv_apply(thz_ctx* c, cudaStream_t s, const float* d_cube, const float* d_gain, int64_t P, int n,
-                 const thz_band_plan* bands, int B, float* d_out, float* d_img, int64_t bstride = 0, int lane = 0);
+                 const thz_band_plan* bands, int B, float* d_out, float* d_img, int64_t bstride = 0, int lane = 0,
+                 const float* d_edges = nullptr);
+// d_edges != null selects the spectral hand-off: d_out receives the spectra of the filtered pairs (private layout),
+// d_edges [P][512] their edge samples; deconv_apply must then be given the same d_edges
+int chain_energies(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P, int n,
+                   const thz_band_plan* bands, int B, float* d_energy, int64_t bstride = 0, float* d_edges = nullptr);
+bool chain_spectral_ok(const thz_ctx* c, int n, int64_t P);
 int chain_pass_in(thz_ctx* c, const float* cube, int64_t P, int n, const thz_band_plan* bands, int n_bands, float* out,
                   float** d_energy_out, float** d_gain_out);
 int chain_pass_out(thz_ctx* c, int64_t P, int n, const thz_band_plan* bands, int n_bands, float* out, float* img);
@@ -62,7 +72,7 @@ int richardson_lucy_bands(thz_ctx* c, cudaStream_t s, const float* d_energy, int
 // thz_edges_mma.cu
 bool edges_mma_supported(int n);
 int launch_fir_edges_mma(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, int n, const thz_band_plan* bands,
-                         int B, float* d_energy, int64_t bstride);
+                         int B, float* d_energy, int64_t bstride, bool edge_rows = false);
 
 }  // namespace thz
 
@@ -82,7 +92,7 @@ struct thz_ctx {
   uint64_t fir_key = 0;                          // cache key of the uploaded FIR spectra (slot WS_FIR)
   int fir_m = 0;
   float stage_ms[4] = {0, 0, 0, 0};              // last thz_deconvolution_dev: energies, RL, apply, RL iterations
-  float kernel_ms[4] = {0, 0, 0, 0};             // same call, per kernel: energy spectra, energy edges, apply edges, apply main
+  float kernel_ms[5] = {0, 0, 0, 0, 0};          // same call, per kernel: energy spectra (or the fused trace + energy kernel), energy edges, apply edges, apply main, trace pass (when not fused)
   bool time_kernels = false;                     // set while thz_deconvolution_dev runs: event pairs around the cube kernels
   struct KernelEvent { int slot; cudaEvent_t e0, e1; };
   std::vector<KernelEvent> kernel_events;        // resolved after the call's final synchronisation
@@ -90,6 +100,10 @@ struct thz_ctx {
   bool edge_mma = true;                          // pass-A edge energies on the tensor cores for n >= 2048 (tcgen05, TF32); THZ_EDGE_MMA=off: transform kernel
   uint64_t edge_mma_key = 0;                     // taps the cached Toeplitz tiles (slot WS_EDGE_MMA) were built from
   int edge_mma_bands = 0;
+  bool chain_fuse = true;                        // trace pass and band energies in one kernel (k_chain_energy_fused); THZ_CHAIN_FUSE=off: two passes
+  bool chain_spectral = true;                    // whole-chain calls hand the spectra of the filtered pairs to pass C instead of the traces (THZ_CHAIN_SPECTRAL=off: traces)
+  bool host_chain_spectral = false;              // mode chain_pass_in / thz_chain_begin_dev used, for the matching second half
+  bool chain_even_transform = false;             // THZ_CHAIN_EVEN=transform: the fused kernel always transforms the stored trace for the even bins (A/B checks)
   bool rl_batch = true;                          // THZ_RL_BATCH=off: Richardson-Lucy band after band (A/B checks)
   bool unstaged_fir = true;                      // FIR passes read the cube directly so that L1 keeps the tables (THZ_FIR_STAGING=on: bulk-copy staging)
   size_t host_chunk_bytes = (size_t)256 << 20;   // chunk of the host-pointer pipelines (THZ_CHAIN_CHUNK_BYTES, tests shrink it)
@@ -115,7 +129,7 @@ int get_tables(thz_ctx* c, int n, const FftTables** out);
 int ensure_scratch(thz_ctx* c, size_t bytes);
 // grow-only workspace: returns a device buffer of at least `bytes` for `slot`
 int ws_get(thz_ctx* c, int slot, size_t bytes, void** out);
-enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER, WS_VOX_KERNEL, WS_VOX_HIST, WS_HANDOFF, WS_MEANS_SPEC, WS_RL_MULTI, WS_EDGE_MMA,
+enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER, WS_VOX_KERNEL, WS_VOX_HIST, WS_HANDOFF, WS_MEANS_SPEC, WS_RL_MULTI, WS_EDGE_MMA, WS_EDGE_ROWS,
        WS_EDGE_CORR /* + lane, lanes 0 .. kHostStreams */, WS_EDGE_CORR_LAST = WS_EDGE_CORR + kHostStreams, WS_END };
 
 // thz_trace.cu
