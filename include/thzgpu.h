@@ -114,8 +114,9 @@ int thz_band_pass_multiplier(const float* freq, int f, double low, double high, 
  *                src/math_tools.rs:102-198, 356-371)
  *   band[n/2+1]: frequency band-pass taper (src/filters/band_pass_fd.rs:155-212)
  *   m_post[n] : time gate after the inverse FFT (src/filters/band_pass_td_after_fft.rs)
- * n: a power of two in [64, 8192] (radix-16 shared-memory kernels) or any length in [2, 4096] (chirp-z
- * kernels on the same core, thz_bluestein.cu) -- real scans and tilt-extended axes are not powers of two. */
+ * n: a power of two in [64, 8192] (radix-16 shared-memory kernels) or any other length in [2, 8192] (chirp-z
+ * kernels on the same core, thz_bluestein.cu; above 4096 the 16384-point chirp convolution runs as two
+ * 8192-point sub-spectra) -- real scans and tilt-extended axes are not powers of two. */
 int thz_plan_trace(thz_ctx* ctx, int n, const float* m_pre, const float* band, const float* m_post);
 
 /* ------------------------------------------------------- trace pass, device pointers --- */

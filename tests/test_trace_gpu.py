@@ -283,9 +283,10 @@ def test_roi_polygon_average(ctx):
     assert np.abs(orc.average_polygon_roi(data, [(3, 2), (20, 4), (25, 18), (8, 21)], 1)).max() > 0
 
 
-@pytest.mark.parametrize("n", [100, 750, 1000, 2001, 3000, 4095])
+@pytest.mark.parametrize("n", [100, 750, 1000, 2001, 3000, 4095, 4097, 5000, 6001, 8191])
 def test_arbitrary_length_traces(ctx, n):
-    """Trace lengths that are not a power of two (real scans; realfft accepts any N): chirp-z kernels.
+    """Trace lengths that are not a power of two (real scans; realfft accepts any N): chirp-z kernels;
+    n > 4096 takes the 16384-point convolution as two 8192-point sub-spectra.
     Forward, fused chain and inverse against the oracle (scipy's pocketfft handles any N)."""
     w, h = 3, 5
     cube = synthetic_cube(w, h, n, seed=n)
@@ -366,7 +367,7 @@ def test_row_slab_sharding_is_bit_identical(ctx):
 def test_error_paths(ctx):
     m = pkg()
     L = m.lib
-    assert L.thz_plan_trace(ctx.handle, 5000, None, None, None) == -1           # > 4096 and not a power of two
+    assert L.thz_plan_trace(ctx.handle, 9000, None, None, None) == -1           # > 8192
     assert b"power of two" in L.thz_last_error(ctx.handle)
     assert L.thz_plan_trace(ctx.handle, 1, None, None, None) == -1
     ctx.plan_trace(1024)

@@ -78,7 +78,7 @@ static std::vector<float> frequency_of(const std::vector<float>& time) {
 }
 
 // power of two in [64, 8192] (fast kernels) or any length up to 4096 (chirp-z kernels)
-static bool gpu_size_ok(size_t n) { return (n >= 64 && n <= 8192 && (n & (n - 1)) == 0) || (n >= 2 && n <= 4096); }
+static bool gpu_size_ok(size_t n) { return n >= 2 && n <= 8192; }
 
 // a time-domain stage that multiplies every trace by one vector
 static int multiply_stage(thz_ctx* ctx, const ScannedImageFilterData& in, const std::vector<float>& mult,

@@ -287,7 +287,7 @@ int thz_plan_trace(thz_ctx* c, int n, const float* m_pre, const float* band, con
   CHECK_CTX(c);
   const bool pow2 = supported_n(n);
   if (!pow2 && !blue_supported(n))
-    return set_err(c, THZ_EINVAL, "n must be a power of two in [64, 8192] or any length in [2, 4096]");
+    return set_err(c, THZ_EINVAL, "n must be a power of two in [64, 8192] or any other length in [2, 8192]");
   int rc;
   // the reference's stage functions rebuild their window per call (math_tools.rs:356-371) and so do the shims that
   // mirror them: an identical plan is recognised here and costs nothing (no synchronisation, no upload)
@@ -346,9 +346,9 @@ int thz_plan_trace(thz_ctx* c, int n, const float* m_pre, const float* band, con
   int m = 0;
   if (build_bluestein_tables(n, band, chirp, bhat, hn, m) != THZ_OK) return set_err(c, THZ_EINVAL, "unsupported n");
   const FftTables* tb = nullptr;
-  if ((rc = get_tables(c, m, &tb)) != THZ_OK) return rc;
+  if ((rc = get_tables(c, m > 8192 ? m / 2 : m, &tb)) != THZ_OK) return rc;   // 16384: two 8192-point sub-spectra
   if ((rc = upload_vec(c, (float**)&p.d_chirp, (const float*)chirp.data(), 2 * (size_t)n)) != THZ_OK) return rc;
-  if ((rc = upload_vec(c, (float**)&p.d_bhat, (const float*)bhat.data(), 2 * (size_t)m)) != THZ_OK) return rc;
+  if ((rc = upload_vec(c, (float**)&p.d_bhat, (const float*)bhat.data(), 2 * bhat.size())) != THZ_OK) return rc;
   if ((rc = upload_vec(c, &p.d_hn, hn.data(), n)) != THZ_OK) return rc;
   THZ_CUDA(c, cudaStreamSynchronize(c->stream));
   p.blue_m = m;

@@ -10,6 +10,13 @@
 // N-point DFT is conj(DFT(conj(.))).  Two real traces are packed as re / im of one complex sequence as
 // in the power-of-two kernels; everything stays in registers / shared memory between the HBM read and
 // the HBM write.  One CTA of M/16 (>= 256) threads per pair-group, M in [64, 8192] => N <= 4096.
+//
+// 4096 < N <= 8192 needs M = 16384, for which no register plan exists (1024 threads x 128 registers).  The
+// sequence a = x w occupies [0, N) of the M-point frame with N <= M/2, so the M-point transforms split into two
+// 8192-point ones exactly like the zero-padded FIR transforms of thz_deconv.cu:
+//     A[2j] = FFT_8192(a)[j],   A[2j+1] = FFT_8192(a v)[j],   v[n] = exp(-2 pi i n / M)
+//     c[n]  = inv_8192(A_even Bhat_even)[n] + conj(v[n]) inv_8192(A_odd Bhat_odd)[n]      (n < 8192)
+// (SPLIT = true: the 8192-point geometry, a thread-private shared-memory stash holds a, then the even half of c).
 #include "thz_fft.cuh"
 #include "thz_internal.h"
 
@@ -23,6 +30,8 @@ template <int M> struct BGeo {
   static constexpr int G = NT / T;
   static constexpr int kScr = (32 + kNzWords) * G;
   static constexpr size_t smem_bytes = (size_t)G * padded_len(M) * sizeof(float2) + kScr * sizeof(float);
+  static constexpr size_t stash_off = (smem_bytes + 15) & ~(size_t)15;          // SPLIT kernels: [G][M] float2 behind it
+  static constexpr size_t smem_bytes_split = stash_off + (size_t)G * M * sizeof(float2);
   static constexpr int kMinBlocks = (NT == 256) ? 2 : 1;
 };
 
@@ -36,6 +45,7 @@ struct BlueArgs {
   const float* band;      // [F] or null (inverse kernel)
   const float2* chirp;    // [n] w[k] = exp(-i pi k^2 / n)
   const float2* bhat;     // [M] FFT_M(conj chirp, circular) / M in last-stage register order
+                          // (split plans: even bins [8192] | odd bins [8192] of the 16384-point spectrum | v[0..512))
   const float2* tw;
   float2* fft;            // [P][F]
   const float2* fft_in;
@@ -46,9 +56,25 @@ struct BlueArgs {
   int64_t P;
 };
 
-// N-point DFT of the packed sequence held in stage-0 layout (v[i] <-> element t + i*T, zero for >= n)
-template <int M>
-__device__ __forceinline__ void bluestein_dft(float2 (&v)[kE], int t, float2* sm, const BlueArgs& a) {
+// multiply by v[n] = exp(-2 pi i n / (2M)) (CONJ: by its conjugate) for n = t + i*T: v[t + i*T] = v[t] exp(-i pi i / 16)
+template <int M, bool CONJ>
+__device__ __forceinline__ void blue_modulate(float2 (&z)[kE], const float2* __restrict__ mod, int t) {
+  static_assert(kE == 16, "rotation constants are exp(-i pi i / 16)");
+  constexpr float kC[16] = {1.0f, 0.98078528f, 0.923879533f, 0.831469612f, 0.707106781f, 0.555570233f, 0.382683432f, 0.195090322f, 0.0f, -0.195090322f, -0.382683432f, -0.555570233f, -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f};
+  constexpr float kS[16] = {0.0f, -0.195090322f, -0.382683432f, -0.555570233f, -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f, -1.0f, -0.98078528f, -0.923879533f, -0.831469612f, -0.707106781f, -0.555570233f, -0.382683432f, -0.195090322f};
+  const float2 w0 = __ldg(mod + t);
+#pragma unroll
+  for (int i = 0; i < kE; ++i) {
+    const float2 w = make_float2(w0.x * kC[i] - w0.y * kS[i], w0.x * kS[i] + w0.y * kC[i]);
+    z[i] = CONJ ? cmul_conj(z[i], w) : cmul(z[i], w);
+  }
+}
+
+// N-point DFT of the packed sequence held in stage-0 layout (v[i] <-> element t + i*T, zero for >= n).
+// SPLIT: the chirp convolution runs on a 2M-point frame as two M-point sub-spectra (see the file header);
+// `stash` is this thread's private column of a [M] float2 shared-memory buffer.
+template <int M, bool SPLIT>
+__device__ __forceinline__ void bluestein_dft(float2 (&v)[kE], int t, float2* sm, const BlueArgs& a, float2* stash) {
   constexpr int T = BGeo<M>::T;
   constexpr int LAST = Plan<M>::ns - 1;
   constexpr int RL = Plan<M>::r[LAST];
@@ -58,6 +84,10 @@ __device__ __forceinline__ void bluestein_dft(float2 (&v)[kE], int t, float2* sm
     const int e = t + i * T;
     v[i] = (e < a.n) ? cmul(v[i], __ldg(a.chirp + e)) : make_float2(0.f, 0.f);
   }
+  if constexpr (SPLIT) {
+#pragma unroll
+    for (int i = 0; i < kE; ++i) stash[i * T] = v[i];
+  }
   fft_forward<M>(v, t, sm, a.tw);
 #pragma unroll
   for (int i = 0; i < kE; ++i) {
@@ -65,6 +95,25 @@ __device__ __forceinline__ void bluestein_dft(float2 (&v)[kE], int t, float2* sm
     v[i] = cmul(v[i], __ldg(a.bhat + m * (M / RL) + t + u * T));
   }
   fft_inverse<M>(v, t, sm, a.tw);
+  if constexpr (SPLIT) {
+    float2 z[kE];
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {   // a back into registers, the even half of c into the stash
+      z[i] = stash[i * T];
+      stash[i * T] = v[i];
+    }
+    blue_modulate<M, false>(z, a.bhat + 2 * M, t);
+    fft_forward<M>(z, t, sm, a.tw);
+#pragma unroll
+    for (int i = 0; i < kE; ++i) {
+      const int u = i % UL, m = i / UL;
+      z[i] = cmul(z[i], __ldg(a.bhat + M + m * (M / RL) + t + u * T));
+    }
+    fft_inverse<M>(z, t, sm, a.tw);
+    blue_modulate<M, true>(z, a.bhat + 2 * M, t);
+#pragma unroll
+    for (int i = 0; i < kE; ++i) v[i] = cadd(stash[i * T], z[i]);
+  }
 #pragma unroll
   for (int i = 0; i < kE; ++i) {
     const int e = t + i * T;
@@ -158,7 +207,7 @@ __device__ __forceinline__ void blue_store(float2 (&v)[kE], const BlueArgs& a, i
 }
 
 // fused chain for arbitrary n
-template <int M>
+template <int M, bool SPLIT = false>
 __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_fused(const BlueArgs a) {
   using GEO = BGeo<M>;
   constexpr int T = GEO::T, G = GEO::G;
@@ -168,6 +217,7 @@ __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_fused
   unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
   const int g = threadIdx.x / T, t = threadIdx.x % T;
   float2* sm = smem + (size_t)g * padded_len(M);
+  float2* stash = reinterpret_cast<float2*>(smem_raw + BGeo<M>::stash_off) + (size_t)g * M + t;   // SPLIT only
   const int64_t npairs = (a.P + 1) >> 1;
   const int64_t nitems = (npairs + G - 1) / G;
   int parity = 0;
@@ -178,14 +228,14 @@ __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_fused
     bool nz0, nz1, z0, z1;
     blue_load<M>(v, a, t, act0, act1, p0, nz0, nz1);
     nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
-    bluestein_dft<M>(v, t, sm, a);            // X[k], k < n
+    bluestein_dft<M, SPLIT>(v, t, sm, a, stash);            // X[k], k < n
 #pragma unroll
     for (int i = 0; i < kE; ++i) {            // band-pass, then conj for the inverse DFT
       const int e = t + i * T;
       const float h = (e < a.n) ? __ldg(a.hn + e) : 0.f;
       v[i] = make_float2(v[i].x * h, -v[i].y * h);
     }
-    bluestein_dft<M>(v, t, sm, a);
+    bluestein_dft<M, SPLIT>(v, t, sm, a, stash);
 #pragma unroll
     for (int i = 0; i < kE; ++i) v[i].y = -v[i].y;
     nz_resolve<T>(g, parity, nzbuf, z0, z1);
@@ -194,7 +244,7 @@ __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_fused
 }
 
 // forward: spectra materialised for arbitrary n (math_tools::fft)
-template <int M>
+template <int M, bool SPLIT = false>
 __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_forward(const BlueArgs a) {
   using GEO = BGeo<M>;
   constexpr int T = GEO::T, G = GEO::G;
@@ -204,6 +254,7 @@ __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_forwa
   unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
   const int g = threadIdx.x / T, t = threadIdx.x % T;
   float2* sm = smem + (size_t)g * padded_len(M);
+  float2* stash = reinterpret_cast<float2*>(smem_raw + BGeo<M>::stash_off) + (size_t)g * M + t;   // SPLIT only
   float* phs = reinterpret_cast<float*>(sm);
   const int64_t npairs = (a.P + 1) >> 1;
   const int64_t nitems = (npairs + G - 1) / G;
@@ -228,7 +279,7 @@ __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_forwa
         }
       }
     }
-    bluestein_dft<M>(v, t, sm, a);
+    bluestein_dft<M, SPLIT>(v, t, sm, a, stash);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kE; ++i) {
@@ -334,7 +385,7 @@ __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_forwa
 }
 
 // inverse: spectra in, arbitrary n (math_tools::ifft)
-template <int M>
+template <int M, bool SPLIT = false>
 __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_inverse(const BlueArgs a) {
   using GEO = BGeo<M>;
   constexpr int T = GEO::T, G = GEO::G;
@@ -344,6 +395,7 @@ __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_inver
   unsigned* nzbuf = reinterpret_cast<unsigned*>(scr + 32 * G);
   const int g = threadIdx.x / T, t = threadIdx.x % T;
   float2* sm = smem + (size_t)g * padded_len(M);
+  float2* stash = reinterpret_cast<float2*>(smem_raw + BGeo<M>::stash_off) + (size_t)g * M + t;   // SPLIT only
   const int64_t npairs = (a.P + 1) >> 1;
   const int64_t nitems = (npairs + G - 1) / G;
   const int n = a.n, F = n / 2 + 1;
@@ -382,7 +434,7 @@ __global__ void __launch_bounds__(BGeo<M>::NT, BGeo<M>::kMinBlocks) k_blue_inver
       const int e = t + i * T;
       v[i] = (e < n) ? sm[e] : make_float2(0.f, 0.f);
     }
-    bluestein_dft<M>(v, t, sm, a);
+    bluestein_dft<M, SPLIT>(v, t, sm, a, stash);
 #pragma unroll
     for (int i = 0; i < kE; ++i) v[i].y = -v[i].y;
     nz_resolve<T>(g, parity, nzbuf, z0, z1);
@@ -399,7 +451,8 @@ int blue_fft_size(int n) {
   return m;
 }
 
-bool blue_supported(int n) { return n >= 2 && 2 * n - 1 <= 8192; }
+bool blue_supported(int n) { return n >= 2 && 2 * n - 1 <= 16384; }
+constexpr int kBlueSplitM = 16384;   // plans of this size run as two 8192-point sub-spectra
 
 template <int M> static void blue_plan(int& ns, int (&r)[4]) {
   ns = Plan<M>::ns;
@@ -425,7 +478,8 @@ int build_bluestein_tables(int n, const float* band, std::vector<float2>& chirp,
                            std::vector<float>& hn, int& m_out) {
   const int m = blue_fft_size(n);
   int ns, r[4];
-  if (!blue_supported(n) || !blue_plan_of(m, ns, r)) return THZ_EINVAL;
+  const bool split = (m == kBlueSplitM);
+  if (!blue_supported(n) || !blue_plan_of(split ? m / 2 : m, ns, r)) return THZ_EINVAL;
   m_out = m;
   std::vector<double> cr(n), ci(n);
   chirp.resize(n);
@@ -470,20 +524,45 @@ int build_bluestein_tables(int n, const float* band, std::vector<float2>& chirp,
     }
   }
   const int RLs = r[ns - 1];
-  bhat.assign(m, make_float2(0.f, 0.f));
-  for (int beta = 0; beta < m / RLs; ++beta)
-    for (int mm = 0; mm < RLs; ++mm) {
-      int p = beta * RLs + mm, k = 0, w = 1, L = m;
-      for (int s = 0; s < ns; ++s) {
-        const int S = L / r[s];
-        const int q = p / S;
-        p -= q * S;
-        k += q * w;
-        w *= r[s];
-        L = S;
+  if (!split) {
+    bhat.assign(m, make_float2(0.f, 0.f));
+    for (int beta = 0; beta < m / RLs; ++beta)
+      for (int mm = 0; mm < RLs; ++mm) {
+        int p = beta * RLs + mm, k = 0, w = 1, L = m;
+        for (int s = 0; s < ns; ++s) {
+          const int S = L / r[s];
+          const int q = p / S;
+          p -= q * S;
+          k += q * w;
+          w *= r[s];
+          L = S;
+        }
+        bhat[(size_t)mm * (m / RLs) + beta] = make_float2((float)(br[k] / m), (float)(bi[k] / m));
       }
-      bhat[(size_t)mm * (m / RLs) + beta] = make_float2((float)(br[k] / m), (float)(bi[k] / m));
+  } else {
+    // even bins | odd bins, each in the register order of the (m/2)-point plan, then v[t] = exp(-2 pi i t / m), t < m/32
+    const int mh = m / 2;
+    bhat.assign((size_t)m + mh / kE, make_float2(0.f, 0.f));
+    for (int beta = 0; beta < mh / RLs; ++beta)
+      for (int mm = 0; mm < RLs; ++mm) {
+        int p = beta * RLs + mm, j = 0, w = 1, L = mh;
+        for (int s = 0; s < ns; ++s) {
+          const int S = L / r[s];
+          const int q = p / S;
+          p -= q * S;
+          j += q * w;
+          w *= r[s];
+          L = S;
+        }
+        const size_t o = (size_t)mm * (mh / RLs) + beta;
+        bhat[o] = make_float2((float)(br[2 * j] / m), (float)(bi[2 * j] / m));
+        bhat[(size_t)mh + o] = make_float2((float)(br[2 * j + 1] / m), (float)(bi[2 * j + 1] / m));
+      }
+    for (int t = 0; t < mh / kE; ++t) {
+      const double ang = -2.0 * M_PI * (double)t / (double)m;
+      bhat[(size_t)m + t] = make_float2((float)cos(ang), (float)sin(ang));
     }
+  }
   hn.assign(n, 0.f);
   for (int k = 0; k < n; ++k) {
     const int kk = (k <= n / 2) ? k : n - k;
@@ -493,9 +572,9 @@ int build_bluestein_tables(int n, const float* band, std::vector<float2>& chirp,
 }
 
 template <int M, typename K>
-static int launch_blue(thz_ctx* c, cudaStream_t s, K kernel, const BlueArgs& a) {
+static int launch_blue(thz_ctx* c, cudaStream_t s, K kernel, const BlueArgs& a, bool split = false) {
   using GEO = BGeo<M>;
-  const size_t smem = GEO::smem_bytes;
+  const size_t smem = split ? GEO::smem_bytes_split : GEO::smem_bytes;
   const void* key = (const void*)kernel;
   auto it = c->occ.find(key);
   if (it == c->occ.end()) {
@@ -522,8 +601,13 @@ template <int M> static int do_bfused(thz_ctx* c, cudaStream_t s, const BlueArgs
 template <int M> static int do_bforward(thz_ctx* c, cudaStream_t s, const BlueArgs& a) { return launch_blue<M>(c, s, k_blue_forward<M>, a); }
 template <int M> static int do_binverse(thz_ctx* c, cudaStream_t s, const BlueArgs& a) { return launch_blue<M>(c, s, k_blue_inverse<M>, a); }
 
+template <int M> static int do_bfused_split(thz_ctx* c, cudaStream_t s, const BlueArgs& a) { return launch_blue<M>(c, s, k_blue_fused<M, true>, a, true); }
+template <int M> static int do_bforward_split(thz_ctx* c, cudaStream_t s, const BlueArgs& a) { return launch_blue<M>(c, s, k_blue_forward<M, true>, a, true); }
+template <int M> static int do_binverse_split(thz_ctx* c, cudaStream_t s, const BlueArgs& a) { return launch_blue<M>(c, s, k_blue_inverse<M, true>, a, true); }
+
 #define THZ_DISPATCH_BM(m, FN, ...)                \
   switch (m) {                                     \
+    case kBlueSplitM: return FN##_split<kBlueSplitM / 2>(__VA_ARGS__); \
     case 64: return FN<64>(__VA_ARGS__);           \
     case 128: return FN<128>(__VA_ARGS__);         \
     case 256: return FN<256>(__VA_ARGS__);         \
@@ -539,7 +623,7 @@ static int blue_base(thz_ctx* c, BlueArgs& a, int64_t P) {
   const TracePlan& p = c->plan;
   if (p.blue_m == 0) return set_err(c, THZ_ESTATE, "no Bluestein plan");
   const FftTables* tb = nullptr;
-  int rc = get_tables(c, p.blue_m, &tb);
+  int rc = get_tables(c, p.blue_m == kBlueSplitM ? kBlueSplitM / 2 : p.blue_m, &tb);
   if (rc != THZ_OK) return rc;
   a = BlueArgs{};
   a.tw = tb->d_tw;
