@@ -672,6 +672,8 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_chain_energy
       if (cnt > 2 * G) cnt = 2 * G;
       prefetch_l2_slab(a.in + next * G * 2 * N, cnt * N);
     }
+    // (fetching the next pair into registers across the band sums, as k_trace_fused does across its stores, costs
+    // 1.5 % here: measured, gpurun call R of round 2)
     float2 v[kE];
     bool nz0, nz1, z0, z1;
     load_pair<N>(v, a, t, act0, act1, p0, nz0, nz1);
@@ -743,8 +745,12 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_chain_energy
     __syncthreads();
 #pragma unroll
     for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = v[i];   // mirrors of lower-half bins are upper-half registers
-    __syncthreads();
-    parseval_terms<N, true>(v, sm, t, q1o, q2o);
+    // POST != 2: the even bins need no exchange, so their mirrors go to the other half of the buffer (the mirrors of
+    // either sub-spectrum are bins >= N/2) and ONE barrier serves both sets of partner reads
+    if constexpr (POST == 2) {
+      __syncthreads();
+      parseval_terms<N, true>(v, sm, t, q1o, q2o);
+    }
     // ---- even bins: FFT_N(y) ----
     float2 z[kE];
 #pragma unroll
@@ -791,12 +797,14 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_chain_energy
         for (int i = 0; i < kE; ++i) __stcs(so + i * T, z[i]);
       }
     }
-    __syncthreads();   // the odd-bin partner reads (and the last exchange of the POST == 2 transform) are done
+    float2* sme = (POST == 2) ? sm : sm - pad_idx(N / 2);   // pad_idx(i) - pad_idx(N/2) = pad_idx(i - N/2) for i >= N/2
+    if constexpr (POST == 2) __syncthreads();   // the odd-bin partner reads and the last exchange of the transform are done
 #pragma unroll
-    for (int i = kE / 2; i < kE; ++i) sm[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
+    for (int i = kE / 2; i < kE; ++i) sme[pad_idx(pos_to_bin<N>(stage_elem<N, LAST>(t, i)))] = z[i];
     __syncthreads();
+    if constexpr (POST != 2) parseval_terms<N, true>(v, sm, t, q1o, q2o);
     float q1e[NLOW], q2e[NLOW];
-    parseval_terms<N, false>(z, sm, t, q1e, q2e);
+    parseval_terms<N, false>(z, sme, t, q1e, q2e);
     float ny1 = 0.f, ny2 = 0.f;   // bin M/2 = even index N/2: register (u = 0, digit RL/2) of thread 0
     if (t == 0) {
       const float2 zz = z[UL * (RL / 2)];

@@ -57,8 +57,16 @@ template <int N> struct TwTotal { static constexpr int value = TwOffset<N, Plan<
 // ------------------------------------------------------------------------------------
 // complex helpers
 // ------------------------------------------------------------------------------------
+#ifndef THZ_SCALAR_ADD
+// packed FP32 (add.rn.f32x2 / fma.rn.f32x2): one issue slot per complex add / subtract instead of two, same rounding
+// per lane.  15 % fewer instructions in the transform kernels, 1-2 % less time (the FP32 pipe spends two cycles on a
+// packed instruction; profiles/r02_ncu_full_chain_fused.txt).  -DTHZ_SCALAR_ADD builds the scalar form (A/B).
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
   return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
 }

@@ -90,6 +90,15 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(
     stager.issue(0, slab[0], a.in + (int64_t)blockIdx.x * G * 2 * N, slab_bytes(blockIdx.x));
   uint32_t it_count = 0;
 
+  // unstaged: the pair of an item is fetched into registers while the previous item is stored (loads in flight
+  // across the stores and the intensity reduction), so that their L2 latency does not open every item
+  float2 vn[STAGED ? 1 : kE];
+  if constexpr (!STAGED) {
+    if ((int64_t)blockIdx.x < nitems) {
+      const int64_t q0 = ((int64_t)blockIdx.x * G + g) * 2;
+      load_pair_raw<N>(vn, a.in, t, q0 < a.P, q0 + 1 < a.P, q0);
+    }
+  }
   for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1, ++it_count) {
     const int64_t pair = item * G + g;
     const int64_t p0 = pair * 2;
@@ -113,7 +122,9 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(
         if (cnt > 2 * G) cnt = 2 * G;
         prefetch_l2_slab(a.in + next * G * 2 * N, cnt * N);
       }
-      load_pair<N>(v, a, t, act0, act1, p0, nz0, nz1);
+#pragma unroll
+      for (int i = 0; i < kE; ++i) v[i] = vn[i];
+      finish_pair<N>(v, a, t, nz0, nz1);
     }
     nz_publish<T>(nz0, nz1, t, g, parity, nzbuf, z0, z1);
     // band-pass in digit-reversed order: register (u, m) <-> position (t + u*T)*RL + m, hq is stored
@@ -134,6 +145,13 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_trace_fused(
     }
     fft_inverse<N>(v, t, sm, a.tw);
     nz_resolve<T>(g, parity, nzbuf, z0, z1);
+    if constexpr (!STAGED) {
+      {   // (past the last item the predicates are false: no loads, and vn does not stay live around the loop)
+        const int64_t q0 = (next * G + g) * 2;
+        const bool more = next < nitems;
+        load_pair_raw<N>(vn, a.in, t, more && q0 < a.P, more && q0 + 1 < a.P, q0);
+      }
+    }
     store_pair<N>(v, a, t, g, act0, act1, p0, use_post, scr, z0, z1);
   }
 }

@@ -77,18 +77,28 @@ __device__ __forceinline__ void group_reduce2(float& a, float& b, int t, int g, 
   }
 }
 
-// Load the pair (p0, p1) into stage-0 register layout, multiplied by m_pre.
+// The two halves of load_pair, for kernels that fetch the NEXT pair while they finish the current one: the loads
+// alone (nothing depends on them, their L2 / DRAM latency hides behind the rest of the item), then the zero test
+// and the time-domain multiplier.
 template <int N>
-__device__ __forceinline__ void load_pair(float2 (&v)[kE], const TraceArgs& a, int t, bool act0, bool act1,
-                                          int64_t p0, bool& nz0, bool& nz1) {
+__device__ __forceinline__ void load_pair_raw(float2 (&v)[kE], const float* __restrict__ in, int t, bool act0, bool act1,
+                                              int64_t p0) {
   constexpr int T = Geo<N>::T;
-  const float* r0 = a.in + p0 * N + t;
+  const float* r0 = in + p0 * N + t;
   const float* r1 = r0 + N;
-  nz0 = nz1 = false;
 #pragma unroll
   for (int i = 0; i < kE; ++i) {
     v[i].x = act0 ? ld_stream(r0 + i * T) : 0.f;
     v[i].y = act1 ? ld_stream(r1 + i * T) : 0.f;
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void finish_pair(float2 (&v)[kE], const TraceArgs& a, int t, bool& nz0, bool& nz1) {
+  constexpr int T = Geo<N>::T;
+  nz0 = nz1 = false;
+#pragma unroll
+  for (int i = 0; i < kE; ++i) {
     nz0 |= (v[i].x != 0.f);
     nz1 |= (v[i].y != 0.f);
   }
@@ -109,6 +119,14 @@ __device__ __forceinline__ void load_pair(float2 (&v)[kE], const TraceArgs& a, i
       }
     }
   }
+}
+
+// Load the pair (p0, p1) into stage-0 register layout, multiplied by m_pre.
+template <int N>
+__device__ __forceinline__ void load_pair(float2 (&v)[kE], const TraceArgs& a, int t, bool act0, bool act1,
+                                          int64_t p0, bool& nz0, bool& nz1) {
+  load_pair_raw<N>(v, a.in, t, act0, act1, p0);
+  finish_pair<N>(v, a, t, nz0, nz1);
 }
 
 // multiply by m_post, store both traces, intensity = sum of squares of the stored values
