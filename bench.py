@@ -546,7 +546,7 @@ def run_ours(a):
         fl = rl_flops(bands, W, H) / world          # this rank's share
         tf = fl / (rl_ms / 1e3) / 1e12
         stages["richardson_lucy"] = {
-            "ms": rl_ms, "kernel": "k_rl_stream<1|2>", "iterations": n_rl_iter,
+            "ms": rl_ms, "kernel": "k_rl_multi<1|2> (batched over the bands; k_rl_stream band after band)", "iterations": n_rl_iter,
             "iters_per_s": n_rl_iter / (rl_ms / 1e3), "algorithm": "separable (row + column pass per filtering), f32",
             "tflops": tf, "flop_frac": tf / fp32["ffma_tflops"] if fp32["ffma_tflops"] > 0 else None,
             "flop_frac_of": "measured scalar FFMA rate of this GPU (fp32_peak.ffma_tflops); tensor cores not applicable",

@@ -54,7 +54,7 @@ def traffic_from_csv(src, dst):
         e["dram_bytes_read"] /= n
         e["dram_bytes_write"] /= n
     json.dump({"command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-                          "-k regex:k_fir|k_trace -c 14 python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e",
+                          "-k regex:k_fir|k_trace|k_chain -c 10 python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e",
                "workload": "C5 2048x2048x4096, 8 bands, 1 x B200, final round-2 build", "cube": [2048, 2048, 4096],
                "kernels": kernels}, open(os.path.join(P, dst), "w"), indent=1)
     shutil.copy(path, os.path.join(P, dst.replace("_traffic.json", "_ncu_cube_kernels_c5.csv")))
@@ -104,5 +104,8 @@ if __name__ == "__main__":
     ncu_summary(f"{tag}_prof_cube512.ncu-rep", "r02_ncu_full_cube_kernels_512x512.txt",
                 "ncu --set full --clock-control none --import-source on, cube kernels of the final round-2 build on a "
                 "512 x 512 x 4096 cube (1/16 of config 5, same work per trace)")
+    ncu_summary(f"{tag}_prof_trace_c4.ncu-rep", "r02_ncu_full_k_trace_fused_c4.txt",
+                "ncu --set full --clock-control none --import-source on -k regex:k_trace_fused, config 4 (1024 x 1024 x 2048, "
+                "default chain, no deconvolution)")
     ncu_summary(f"{tag}_prof_rl.ncu-rep", "r02_ncu_full_k_rl_multi.txt",
                 "ncu --set full --clock-control none --import-source on -k regex:k_rl_multi -s 600 -c 2, config 5 (band 0 alone, 47x57 PSF)")
