@@ -357,7 +357,9 @@ int thz_chain_host(thz_ctx* ctx, const float* cube, int rows, int cols, int n, c
  * pass of `Deconvolution::filter` in ONE kernel (the filtered pair is still on chip when its FIR band energies are
  * formed, src/data_thread.rs:1090-1190 followed by src/filters/deconvolution.rs:963-966), then Richardson-Lucy
  * and the gain application.  thz_plan_trace(n, ...) must have been called; d_out may alias d_in; d_img is [rows*cols].
- * thz_deconv_stage_ms then reports {trace pass + band energies, Richardson-Lucy, gain application, iterations}. */
+ * thz_deconv_stage_ms then reports {trace pass + band energies, Richardson-Lucy, gain application, iterations}.
+ * Returns THZ_ABORTED when abort_flag became non-zero; d_out is then undefined (it may hold the hand-off between the
+ * phases), so an in-place call that can be aborted should keep its input elsewhere. */
 int thz_chain_dev(thz_ctx* ctx, const float* d_in, int rows, int cols, int n, const thz_band_plan* bands,
                   int n_bands, float* d_out, float* d_img, const volatile uint8_t* abort_flag,
                   thz_progress_fn progress, void* progress_user);

@@ -245,3 +245,61 @@ def test_chain_dev_spectral_and_plain_agree(psfs, monkeypatch):
         finally:
             c.close()
     assert rel_err(outs[0][0], outs[1][0]) <= 1e-5 and rel_err(outs[0][1], outs[1][1]) <= 1e-5
+
+
+def test_chain_dev_odd_trace_count_and_long_traces(psfs, monkeypatch):
+    """Shapes off the fast path: an odd trace count (no whole pairs: the traces, not their spectra, are handed to pass
+    C) and n = 8192 (one 512-thread CTA per pair) -- thz_chain_dev against the stage calls."""
+    psf, _ = psfs
+    for k in ("THZ_CHAIN_FUSE", "THZ_CHAIN_EVEN", "THZ_EDGE_MMA", "THZ_CHAIN_SPECTRAL"):
+        monkeypatch.delenv(k, raising=False)
+    for n, w, h in ((1024, 37, 33), (8192, 36, 34)):
+        cube = synthetic_cube(w, h, n, seed=n + 1, noise=0.02)
+        t = time_axis(n)
+        bands, why = pkg().host.Deconvolution(n_filters=5, n_iterations=20).plan(t, (w, h), 1.0, 1.0, psf)
+        assert bands is not None, why
+        P = w * h
+        c = pkg().Context(0)
+        try:
+            c.plan_trace(n, *pkg().host.chain_multipliers(t))
+            d_in, d_a, d_b = c.to_device(cube), c.alloc(cube.nbytes), c.alloc(cube.nbytes)
+            d_ia, d_ib = c.alloc(P * 4), c.alloc(P * 4)
+            c.chain_dev(d_in.ptr, w, h, n, bands, d_a.ptr, d_ia.ptr)
+            c.trace_fused_dev(d_in.ptr, d_b.ptr, d_ib.ptr, P)
+            c._check(pkg().lib.thz_deconvolution_dev(c.handle, d_b.ptr, w, h, n, bands, len(bands), d_b.ptr, d_ib.ptr,
+                                                     None, None, None))
+            c.sync()
+            assert rel_err(d_a.download((w, h, n)), d_b.download((w, h, n))) <= 1e-5
+            assert rel_err(d_ia.download((w, h)), d_ib.download((w, h))) <= 1e-5
+        finally:
+            c.close()
+
+
+def test_chain_dev_abort_and_errors(psfs):
+    """abort flag (one byte, Rust AtomicBool layout) -> THZ_ABORTED before Richardson-Lucy; plan / pointer errors."""
+    import ctypes
+    psf, _ = psfs
+    n, w, h = 1024, 40, 36
+    cube = synthetic_cube(w, h, n, seed=3)
+    t = time_axis(n)
+    bands, _ = pkg().host.Deconvolution(n_filters=4, n_iterations=12).plan(t, (w, h), 1.0, 1.0, psf)
+    L = pkg().lib
+    c = pkg().Context(0)
+    try:
+        d_in, d_out, d_img = c.to_device(cube), c.alloc(cube.nbytes), c.alloc(w * h * 4)
+        # no plan yet
+        assert L.thz_chain_dev(c.handle, d_in.ptr, w, h, n, bands, len(bands), d_out.ptr, d_img.ptr, None, None, None) == -4
+        c.plan_trace(n, *pkg().host.chain_multipliers(t))
+        flag = ctypes.c_uint8(1)
+        rc = L.thz_chain_dev(c.handle, d_in.ptr, w, h, n, bands, len(bands), d_out.ptr, d_img.ptr,
+                             ctypes.addressof(flag), None, None)
+        assert rc == 1                                                  # THZ_ABORTED
+        assert L.thz_chain_dev(c.handle, d_in.ptr, w, h, n, bands, 0, d_out.ptr, d_img.ptr, None, None, None) == -1
+        assert L.thz_chain_dev(c.handle, d_in.ptr, w, h, n, bands, len(bands), d_out.ptr, None, None, None, None) == -1
+        assert L.thz_chain_energies_dev(c.handle, None, d_out.ptr, d_img.ptr, w * h, n, bands, len(bands), d_img.ptr) == -1
+        # and the context still works afterwards
+        c.chain_dev(d_in.ptr, w, h, n, bands, d_out.ptr, d_img.ptr)
+        c.sync()
+        assert np.isfinite(d_img.download((w, h))).all()
+    finally:
+        c.close()
