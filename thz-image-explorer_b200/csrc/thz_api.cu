@@ -159,7 +159,6 @@ int thz_ctx_create(int device, thz_ctx** out) {
   if (const char* f = getenv("THZ_RL_BATCH")) c->rl_batch = (strcmp(f, "off") != 0);
   if (const char* f = getenv("THZ_CHAIN_FUSE")) c->chain_fuse = (strcmp(f, "off") != 0);
   if (const char* f = getenv("THZ_CHAIN_SPECTRAL")) c->chain_spectral = (strcmp(f, "off") != 0);
-  if (const char* f = getenv("THZ_CHAIN_STASH")) c->chain_stash_global = (strcmp(f, "global") == 0);
   if (const char* f = getenv("THZ_CHAIN_EVEN")) c->chain_even_transform = (strcmp(f, "transform") == 0);
   if (const char* f = getenv("THZ_CHAIN_CHUNK_BYTES")) {
     const long long v = atoll(f);

@@ -73,7 +73,6 @@ struct FirArgs {
   // spectral hand-off between the fused trace + energy kernel and pass C (see k_chain_energy_fused)
   float* edges;          // [P][512]: samples [0, 256) and [N - 256, N) of every filtered trace
   const float2* xspec;   // [P / 2][N]: FFT_N of the filtered pair in Plan<N> register order (pass C input)
-  float2* gstash;        // [grid][G][N] scratch of k_chain_energy_fused<.., GST> (null: the stash lives in shared memory)
 };
 
 template <int M>
@@ -638,13 +637,11 @@ __global__ void __launch_bounds__(SGeo<N>::NT, SGeo<N>::kMinBlocks) k_fir_energy
 // of which they only touch the first and last 249 / 256 samples).  Trace counts must be even (whole pairs).
 // ------------------------------------------------------------------------------------
 template <int N> struct FGeo {
-  static constexpr size_t cs_off = (Geo<N>::smem_bytes + 15) & ~(size_t)15;                       // gate corrections [G][8]
-  static constexpr size_t stash_off = cs_off + (size_t)Geo<N>::G * 8 * sizeof(float2);
-  static constexpr size_t smem_bytes = stash_off + (size_t)Geo<N>::G * N * sizeof(float2);         // stash in shared memory
-  static constexpr size_t smem_bytes_gst = stash_off;                                              // stash in global memory (L2)
+  static constexpr size_t stash_off = (Geo<N>::smem_bytes + 15) & ~(size_t)15;
+  static constexpr size_t smem_bytes = stash_off + (size_t)Geo<N>::G * (N + 8) * sizeof(float2);
 };
 
-template <int N, int POST, bool SPEC, bool GST>
+template <int N, int POST, bool SPEC>
 __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_chain_energy_fused(const TraceArgs a, const FirArgs f) {
   using GEO = Geo<N>;
   constexpr int T = GEO::T, G = GEO::G;
@@ -654,11 +651,8 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_chain_energy
   float* scr = reinterpret_cast<float*>(smem + (size_t)G * padded_len(N));
   const int g = threadIdx.x / T, t = threadIdx.x % T;
   float2* sm = smem + (size_t)g * padded_len(N);
-  // [i * T]: thread-private.  GST: in a per-CTA global scratch instead (L2 resident, L1 bypassed), which leaves the
-  // unified L1 / shared memory to the tables (THZ_CHAIN_STASH=global)
-  float2* stash = GST ? f.gstash + ((size_t)blockIdx.x * G + g) * N + t
-                      : reinterpret_cast<float2*>(smem_raw + FGeo<N>::stash_off) + (size_t)g * N + t;
-  float2* cs = reinterpret_cast<float2*>(smem_raw + FGeo<N>::cs_off) + g * 8;   // gate corrections of the group
+  float2* stash = reinterpret_cast<float2*>(smem_raw + FGeo<N>::stash_off) + (size_t)g * N + t;   // [i * T]: thread-private
+  float2* cs = reinterpret_cast<float2*>(smem_raw + FGeo<N>::stash_off) + (size_t)G * N + g * 8;  // gate corrections of the group
   const int64_t npairs = (a.P + 1) >> 1;
   const int64_t nitems = (npairs + G - 1) / G;
   constexpr int LAST = Plan<N>::ns - 1;
@@ -702,10 +696,7 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_chain_energy
     }
     if constexpr (POST != 2) {
 #pragma unroll
-      for (int i = 0; i < kE; ++i) {
-        if constexpr (GST) __stcg(stash + i * T, v[i]);
-        else stash[i * T] = v[i];
-      }
+      for (int i = 0; i < kE; ++i) stash[i * T] = v[i];
     }
     fft_inverse<N>(v, t, sm, a.tw);
     nz_resolve<T>(g, parity, nzbuf, z0, z1);
@@ -745,10 +736,7 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_chain_energy
     }
     if constexpr (POST == 2) {
 #pragma unroll
-      for (int i = 0; i < kE; ++i) {
-        if constexpr (GST) __stcg(stash + i * T, v[i]);
-        else stash[i * T] = v[i];
-      }
+      for (int i = 0; i < kE; ++i) stash[i * T] = v[i];
     }
     // ---- odd bins: FFT_N(y w_M^n) ----
     float q1o[NLOW], q2o[NLOW];
@@ -766,7 +754,7 @@ __global__ void __launch_bounds__(Geo<N>::NT, Geo<N>::kMinBlocks) k_chain_energy
     // ---- even bins: FFT_N(y) ----
     float2 z[kE];
 #pragma unroll
-    for (int i = 0; i < kE; ++i) z[i] = GST ? __ldcg(stash + i * T) : stash[i * T];
+    for (int i = 0; i < kE; ++i) z[i] = stash[i * T];
     if constexpr (POST == 2) {
       fft_forward<N>(z, t, sm, a.tw);   // its first barrier orders the partner reads above before the exchange
     } else {
@@ -1935,11 +1923,11 @@ int deconv_energies(thz_ctx* c, cudaStream_t s, const float* d_cube, int64_t P, 
 }
 
 // ---- trace pass + band energies in one cube pass (k_chain_energy_fused) ----
-template <int N, int POST, bool SPEC, bool GST>
-static int launch_chain_fused(thz_ctx* c, cudaStream_t s, const TraceArgs& ta, const FirArgs& fa_in) {
+template <int N, int POST, bool SPEC>
+static int launch_chain_fused(thz_ctx* c, cudaStream_t s, const TraceArgs& ta, const FirArgs& fa) {
   using GEO = Geo<N>;
-  auto kernel = k_chain_energy_fused<N, POST, SPEC, GST>;
-  const size_t smem = GST ? FGeo<N>::smem_bytes_gst : FGeo<N>::smem_bytes;
+  auto kernel = k_chain_energy_fused<N, POST, SPEC>;
+  const size_t smem = FGeo<N>::smem_bytes;
   const void* key = (const void*)kernel;
   auto it = c->occ.find(key);
   if (it == c->occ.end()) {
@@ -1961,35 +1949,24 @@ static int launch_chain_fused(thz_ctx* c, cudaStream_t s, const TraceArgs& ta, c
   if (nitems <= 0) return THZ_OK;
   int64_t grid = (int64_t)c->sm_count * it->second;
   if (grid > nitems) grid = nitems;
-  FirArgs fa = fa_in;
-  if constexpr (GST) {   // one scratch per stream that may run this kernel concurrently
-    int lane = 0;
-    for (int k = 0; k < kHostStreams; ++k)
-      if (s == c->hstream[k]) lane = 1 + k;
-    void* ps = nullptr;
-    int rc = ws_get(c, WS_CHAIN_STASH + lane, (size_t)c->sm_count * it->second * GEO::G * N * sizeof(float2), &ps);
-    if (rc != THZ_OK) return rc;
-    fa.gstash = (float2*)ps;
-  }
   kernel<<<(unsigned)grid, GEO::NT, smem, s>>>(ta, fa);
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(c, e, "fused chain kernel launch");
   return THZ_OK;
 }
-template <int N, bool SPEC, bool GST>
-static int pick_chain_fused(thz_ctx* c, cudaStream_t s, const TraceArgs& ta, const FirArgs& fa, int post) {
-  if (post == 0) return launch_chain_fused<N, 0, SPEC, GST>(c, s, ta, fa);
-  if (post == 1) return launch_chain_fused<N, 1, SPEC, GST>(c, s, ta, fa);
-  return launch_chain_fused<N, 2, SPEC, GST>(c, s, ta, fa);
-}
 template <int N> static int do_chain_fused(thz_ctx* c, cudaStream_t s, const TraceArgs& ta, const FirArgs& fa, int post) {
   if constexpr (N < 512) {
     return THZ_EINVAL;
   } else {
-    const bool spec = fa.edges != nullptr;
-    if (c->chain_stash_global) return spec ? pick_chain_fused<N, true, true>(c, s, ta, fa, post) : pick_chain_fused<N, false, true>(c, s, ta, fa, post);
-    return spec ? pick_chain_fused<N, true, false>(c, s, ta, fa, post) : pick_chain_fused<N, false, false>(c, s, ta, fa, post);
+    if (fa.edges != nullptr) {
+      if (post == 0) return launch_chain_fused<N, 0, true>(c, s, ta, fa);
+      if (post == 1) return launch_chain_fused<N, 1, true>(c, s, ta, fa);
+      return launch_chain_fused<N, 2, true>(c, s, ta, fa);
+    }
+    if (post == 0) return launch_chain_fused<N, 0, false>(c, s, ta, fa);
+    if (post == 1) return launch_chain_fused<N, 1, false>(c, s, ta, fa);
+    return launch_chain_fused<N, 2, false>(c, s, ta, fa);
   }
 }
 static int dispatch_chain_fused(thz_ctx* c, cudaStream_t s, int n, const TraceArgs& ta, const FirArgs& fa, int post) {

@@ -103,7 +103,6 @@ struct thz_ctx {
   bool chain_fuse = true;                        // trace pass and band energies in one kernel (k_chain_energy_fused); THZ_CHAIN_FUSE=off: two passes
   bool chain_spectral = true;                    // whole-chain calls hand the spectra of the filtered pairs to pass C instead of the traces (THZ_CHAIN_SPECTRAL=off: traces)
   bool host_chain_spectral = false;              // mode chain_pass_in / thz_chain_begin_dev used, for the matching second half
-  bool chain_stash_global = false;               // THZ_CHAIN_STASH=global: the fused kernel keeps its stash in an L2-resident scratch instead of shared memory
   bool chain_even_transform = false;             // THZ_CHAIN_EVEN=transform: the fused kernel always transforms the stored trace for the even bins (A/B checks)
   bool rl_batch = true;                          // THZ_RL_BATCH=off: Richardson-Lucy band after band (A/B checks)
   bool unstaged_fir = true;                      // FIR passes read the cube directly so that L1 keeps the tables (THZ_FIR_STAGING=on: bulk-copy staging)
@@ -131,8 +130,7 @@ int ensure_scratch(thz_ctx* c, size_t bytes);
 // grow-only workspace: returns a device buffer of at least `bytes` for `slot`
 int ws_get(thz_ctx* c, int slot, size_t bytes, void** out);
 enum { WS_FIR = 1, WS_ENERGY, WS_GAIN, WS_RL_D, WS_RL_U, WS_RL_R, WS_RL_TAPS, WS_CONV_A, WS_CONV_B, WS_HOST_CUBE, WS_HOST_IMG, WS_MULT, WS_SCALE_IN, WS_SCALE_OUT, WS_ROI_PIX, WS_ROI_OUT, WS_TILT_IN, WS_TILT_OUT, WS_TILT_IDX, WS_TILT_TAPER, WS_VOX_KERNEL, WS_VOX_HIST, WS_HANDOFF, WS_MEANS_SPEC, WS_RL_MULTI, WS_EDGE_MMA, WS_EDGE_ROWS,
-       WS_EDGE_CORR /* + lane, lanes 0 .. kHostStreams */, WS_EDGE_CORR_LAST = WS_EDGE_CORR + kHostStreams,
-       WS_CHAIN_STASH /* + lane */, WS_CHAIN_STASH_LAST = WS_CHAIN_STASH + kHostStreams, WS_END };
+       WS_EDGE_CORR /* + lane, lanes 0 .. kHostStreams */, WS_EDGE_CORR_LAST = WS_EDGE_CORR + kHostStreams, WS_END };
 
 // thz_trace.cu
 int launch_trace_fused(thz_ctx* c, cudaStream_t s, const float* d_in, float* d_out, float* d_img, int64_t P);
