@@ -214,7 +214,7 @@ def test_spectral_handoff_equals_traces(psfs, monkeypatch, n, kind):
     peak = float(np.max(np.abs(plain[0])))
     for sl in (slice(0, 249), slice(n - 249, n)):
         # on the edges' own scale -- unless a gate has zeroed them (then they hold rounding noise of the whole trace)
-        scale = max(float(np.max(np.abs(plain[0][:, :, sl]))), 1e-2 * peak)
+        scale = max(float(np.max(np.abs(plain[0][:, :, sl]))), 0.1 * peak)
         assert float(np.max(np.abs(spec[0][:, :, sl].astype(np.float64) - plain[0][:, :, sl]))) <= 5e-6 * scale
     assert rel_err(spec[1], plain[1]) <= 1e-5
     if n >= 2048:      # tensor-core edges (TF32) in both: same bits; the transform edges agree to 1e-5
